@@ -1,0 +1,305 @@
+"""CPU parity oracle -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference``
+legs may import this package, and there only as the checker (or as the reported CPU baseline),
+never as the product path.  ``pointcloudtraj_b200`` never imports it.
+
+Two backends with one interface:
+
+* :class:`KdOracle`     -- this repo's C restatement (``kd_oracle.c`` / ``planner_oracle.c``).
+* :class:`KdReference`  -- the UNMODIFIED reference ``Utils/kdtree`` (``kdtree.c``) compiled by
+  ``oracle/Makefile`` from ``/root/reference`` into ``oracle/_ref/libkdtree_ref.so`` and driven
+  through its public ``kd_*`` API by ``ref_harness.c``.
+
+Reference anchors: Utils/kdtree/src/kdtree.c:112-126 (kd_create), :244-251 (kd_insert3),
+:493-500 (kd_nearest3), :595-602 (kd_nearest_range3), :613-650 (kd_res_*).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_REF_PATH = os.path.join(_HERE, "_ref", "libkdtree_ref.so")
+
+_i64p = C.POINTER(C.c_int64)
+_i32p = C.POINTER(C.c_int32)
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+
+
+def build(verbose: bool = False) -> None:
+    """Compile liboracle.so and (when /root/reference is present) _ref/libkdtree_ref.so."""
+    out = subprocess.run(["make", "-C", _HERE, "all"], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout, out.stderr)
+    if out.returncode != 0:
+        raise RuntimeError("oracle build failed")
+
+
+def have_reference() -> bool:
+    return os.path.exists(_REF_PATH)
+
+
+def _ptr(a, typ):
+    return None if a is None else a.ctypes.data_as(typ)
+
+
+def _as_f32_rows(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] not in (3, 4):
+        raise ValueError("expected an (n, 3) or (n, 4) float32 array")
+    return a
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = C.CDLL(_LIB_PATH)
+        L.kdo_create.restype = C.c_void_p
+        L.kdo_free.argtypes = [C.c_void_p]
+        L.kdo_clear.argtypes = [C.c_void_p]
+        L.kdo_size.argtypes = [C.c_void_p]
+        L.kdo_size.restype = C.c_int64
+        L.kdo_depth.argtypes = [C.c_void_p]
+        L.kdo_depth.restype = C.c_int64
+        L.kdo_insert3.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int64]
+        L.kdo_build.argtypes = [C.c_void_p, _f32p, C.c_int64, C.c_int64, _i64p]
+        L.kdo_nearest3.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, _i64p, _f64p, _f64p]
+        L.kdo_nearest_batch.argtypes = [C.c_void_p, _f32p, C.c_int64, C.c_int64, _i64p, _f64p, C.c_int]
+        L.kdo_range3.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, _i64p, C.c_int64]
+        L.kdo_range3.restype = C.c_int64
+        L.kdo_range_count_batch.argtypes = [C.c_void_p, _f32p, C.c_int64, C.c_int64, _f64p, C.c_int, _i64p, C.c_int]
+        L.kdo_range_fill_batch.argtypes = [C.c_void_p, _f32p, C.c_int64, C.c_int64, _f64p, C.c_int, _i64p, _i64p, C.c_int]
+        L.kdo_brute_nearest_batch.argtypes = [_f32p, C.c_int64, C.c_int64, _f32p, C.c_int64, C.c_int64,
+                                              _i64p, _f64p, _i32p, C.c_int]
+        L.kdo_pair_d2.argtypes = [_f32p, C.c_int64, _f32p, C.c_int64, _i64p, C.c_int64, _f64p]
+        L.po_radius_search.argtypes = [C.c_void_p, C.c_void_p, _f64p, _i64p]
+        L.po_radius_search.restype = C.c_double
+        L.po_radius_batch.argtypes = [C.c_void_p, C.c_void_p, _f32p, C.c_int64, C.c_int64, _f64p, _i64p]
+        L.po_binomial.argtypes = [C.c_int, C.c_int]
+        L.po_binomial.restype = C.c_double
+        L.po_bezier_pos.argtypes = [_f64p, C.c_int, C.c_double, _f64p]
+        L.po_check_safe_trajectory.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, _i32p, _f64p, _f64p, C.c_int64,
+                                               C.c_double, C.c_double, C.c_double, C.c_int64, _f32p, _f64p,
+                                               _i64p, _f64p]
+        L.po_check_safe_trajectory.restype = C.c_int64
+        _lib = L
+    return _lib
+
+
+_ref = None
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        if not os.path.exists(_REF_PATH):
+            raise FileNotFoundError(
+                f"{_REF_PATH} missing: run `make -C oracle` in the container that has /root/reference")
+        L = C.CDLL(_REF_PATH)
+        L.refh_create.restype = C.c_void_p
+        L.refh_free.argtypes = [C.c_void_p]
+        L.refh_clear.argtypes = [C.c_void_p]
+        L.refh_build.argtypes = [C.c_void_p, _f32p, C.c_int64, C.c_int64, _i64p]
+        L.refh_max_threads.restype = C.c_int
+        L.refh_nearest_batch.argtypes = [C.c_void_p, _f32p, C.c_int64, C.c_int64, _i64p, _f64p, C.c_int]
+        L.refh_range3.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, _i64p, C.c_int64]
+        L.refh_range3.restype = C.c_int64
+        L.refh_range_count_batch.argtypes = [C.c_void_p, _f32p, C.c_int64, C.c_int64, _f64p, C.c_int, _i64p, C.c_int]
+        L.refh_range_fill_batch.argtypes = [C.c_void_p, _f32p, C.c_int64, C.c_int64, _f64p, C.c_int, _i64p, _i64p, C.c_int]
+        L.refh_radius_batch.argtypes = [C.c_void_p, _f32p, C.c_int64, C.c_int64, _f64p, _f64p, C.c_int]
+        _ref = L
+    return _ref
+
+
+class RadiusParams(C.Structure):
+    """Mirror of po_radius_params / pc_radius_params (safeRegionRrtStar::setParam,
+    Planner/src/corridor_finder.cpp:17-23; start_pt from setStartPt :43-50)."""
+    _fields_ = [("search_margin", C.c_double), ("max_radius", C.c_double),
+                ("sample_range", C.c_double), ("start", C.c_double * 3)]
+
+    @classmethod
+    def make(cls, search_margin=0.25, max_radius=1.5, sample_range=30.0, start=(0.0, 0.0, 0.0)):
+        p = cls()
+        p.search_margin, p.max_radius, p.sample_range = search_margin, max_radius, sample_range
+        p.start[0], p.start[1], p.start[2] = [float(v) for v in start]
+        return p
+
+
+class _KdBase:
+    """Shared batch interface over a tree handle."""
+    _prefix = ""
+
+    def __init__(self):
+        self._L = None
+        self._h = None
+        self.n = 0
+
+    # -- building ---------------------------------------------------------------------------
+    def build(self, xyz, order=None):
+        """kd_clear + n x kd_insert3(x, y, z, (void*)i) in `order` (default 0..n-1)."""
+        xyz = _as_f32_rows(xyz)
+        self._xyz = xyz
+        o = None if order is None else np.ascontiguousarray(order, dtype=np.int64)
+        rc = getattr(self._L, self._prefix + "build")(self._h, _ptr(xyz, _f32p), xyz.shape[0], xyz.shape[1], _ptr(o, _i64p))
+        if rc != 0:
+            raise MemoryError("kd build failed")
+        self.n = xyz.shape[0]
+        return self
+
+    # -- nearest ----------------------------------------------------------------------------
+    def nearest(self, q, nthreads=0):
+        """Returns (idx int64[m], d2 float64[m]); idx -1 / d2 inf on an empty tree."""
+        q = _as_f32_rows(q)
+        m = q.shape[0]
+        idx = np.empty(m, dtype=np.int64)
+        d2 = np.empty(m, dtype=np.float64)
+        getattr(self._L, self._prefix + "nearest_batch")(self._h, _ptr(q, _f32p), m, q.shape[1],
+                                                         _ptr(idx, _i64p), _ptr(d2, _f64p), nthreads)
+        return idx, d2
+
+    # -- range ------------------------------------------------------------------------------
+    def range(self, q, r, nthreads=0):
+        """kd_nearest_range3 per query; returns (offsets int64[m+1], idx int64[total]) with each
+        list in the reference result set's iteration order."""
+        q = _as_f32_rows(q)
+        m = q.shape[0]
+        r = np.ascontiguousarray(np.atleast_1d(r), dtype=np.float64)
+        scalar = 1 if r.shape[0] == 1 else 0
+        counts = np.empty(m, dtype=np.int64)
+        getattr(self._L, self._prefix + "range_count_batch")(self._h, _ptr(q, _f32p), m, q.shape[1],
+                                                             _ptr(r, _f64p), scalar, _ptr(counts, _i64p), nthreads)
+        off = np.zeros(m + 1, dtype=np.int64)
+        np.cumsum(counts, out=off[1:])
+        out = np.empty(max(int(off[-1]), 1), dtype=np.int64)
+        getattr(self._L, self._prefix + "range_fill_batch")(self._h, _ptr(q, _f32p), m, q.shape[1],
+                                                            _ptr(r, _f64p), scalar, _ptr(off, _i64p), _ptr(out, _i64p), nthreads)
+        return off, out[: int(off[-1])]
+
+
+class KdOracle(_KdBase):
+    """This repo's restatement (kd_oracle.c)."""
+    _prefix = "kdo_"
+
+    def __init__(self):
+        super().__init__()
+        self._L = lib()
+        self._h = C.c_void_p(self._L.kdo_create())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.kdo_free(self._h)
+            self._h = None
+
+    def insert3(self, x, y, z, payload):
+        rc = self._L.kdo_insert3(self._h, x, y, z, payload)
+        self.n += 1
+        return rc
+
+    def depth(self):
+        return int(self._L.kdo_depth(self._h))
+
+    # planner-side restatements -------------------------------------------------------------
+    def radius_search(self, params: RadiusParams, p):
+        """safeRegionRrtStar::radiusSearch on one double-precision point."""
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        idx = C.c_int64(-1)
+        r = self._L.po_radius_search(self._h, C.byref(params), _ptr(p, _f64p), C.byref(idx))
+        return r, idx.value
+
+    def radius_batch(self, params: RadiusParams, q):
+        q = _as_f32_rows(q)
+        m = q.shape[0]
+        out = np.empty(m, dtype=np.float64)
+        idx = np.empty(m, dtype=np.int64)
+        self._L.po_radius_batch(self._h, C.byref(params), _ptr(q, _f32p), m, q.shape[1], _ptr(out, _f64p), _ptr(idx, _i64p))
+        return out, idx
+
+    def check_safe_trajectory(self, params: RadiusParams, order, T, coef, t_now, stop_time, dt=0.02, cap=4096):
+        """checkSafeTrajectory full walk. Returns dict(first_hit, n_samples, min_radius, pts, radius)."""
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        coef = np.ascontiguousarray(coef, dtype=np.float64)
+        n_seg = order.shape[0]
+        ld = coef.shape[1] if coef.ndim == 2 and n_seg > 0 else 0
+        pts = np.zeros((cap, 3), dtype=np.float32)
+        rad = np.zeros(cap, dtype=np.float64)
+        ns = C.c_int64(0)
+        rmin = C.c_double(0.0)
+        fh = self._L.po_check_safe_trajectory(self._h, C.byref(params), n_seg, _ptr(order, _i32p), _ptr(T, _f64p),
+                                              _ptr(coef, _f64p), ld, t_now, stop_time, dt, cap,
+                                              _ptr(pts, _f32p), _ptr(rad, _f64p), C.byref(ns), C.byref(rmin))
+        n = min(ns.value, cap)
+        return dict(first_hit=int(fh), n_samples=int(ns.value), min_radius=rmin.value, pts=pts[:n], radius=rad[:n])
+
+
+class KdReference(_KdBase):
+    """The unmodified reference Utils/kdtree through ref_harness.c."""
+    _prefix = "refh_"
+
+    def __init__(self):
+        super().__init__()
+        self._L = ref_lib()
+        self._h = C.c_void_p(self._L.refh_create())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.refh_free(self._h)
+            self._h = None
+
+    def max_threads(self):
+        return int(self._L.refh_max_threads())
+
+    def radius_batch(self, params: RadiusParams, q, nthreads=0):
+        q = _as_f32_rows(q)
+        m = q.shape[0]
+        out = np.empty(m, dtype=np.float64)
+        pv = np.array([params.search_margin, params.max_radius, params.sample_range,
+                       params.start[0], params.start[1], params.start[2]], dtype=np.float64)
+        self._L.refh_radius_batch(self._h, _ptr(q, _f32p), m, q.shape[1], _ptr(pv, _f64p), _ptr(out, _f64p), nthreads)
+        return out
+
+
+def brute_nearest(xyz, q, nthreads=0):
+    """Exact fp64 minimum in the reference's operation order, lowest index on ties.
+    Returns (idx int64[m], d2 float64[m], n_ties int32[m])."""
+    xyz = _as_f32_rows(xyz)
+    q = _as_f32_rows(q)
+    m = q.shape[0]
+    idx = np.empty(m, dtype=np.int64)
+    d2 = np.empty(m, dtype=np.float64)
+    ties = np.empty(m, dtype=np.int32)
+    lib().kdo_brute_nearest_batch(_ptr(xyz, _f32p), xyz.shape[0], xyz.shape[1], _ptr(q, _f32p), m, q.shape[1],
+                                  _ptr(idx, _i64p), _ptr(d2, _f64p), _ptr(ties, _i32p), nthreads)
+    return idx, d2, ties
+
+
+def pair_d2(xyz, q, idx):
+    """fp64 d2 between point idx[k] and query k in the reference's operation order."""
+    xyz = _as_f32_rows(xyz)
+    q = _as_f32_rows(q)
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    out = np.empty(idx.shape[0], dtype=np.float64)
+    lib().kdo_pair_d2(_ptr(xyz, _f32p), xyz.shape[1], _ptr(q, _f32p), q.shape[1], _ptr(idx, _i64p), idx.shape[0], _ptr(out, _f64p))
+    return out
+
+
+def bezier_pos(coef_row, order, u):
+    coef_row = np.ascontiguousarray(coef_row, dtype=np.float64)
+    out = np.zeros(3, dtype=np.float64)
+    lib().po_bezier_pos(_ptr(coef_row, _f64p), order, u, _ptr(out, _f64p))
+    return out
+
+
+def binomial(n, k):
+    return lib().po_binomial(n, k)
