@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps K --warmup W              # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU kd-tree on the host cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...      # one rank per GPU, weak scaling
+
+A step = one pass of the hot path over one batch: `pc_radius_batch` (safeRegionRrtStar::radiusSearch,
+Planner/src/corridor_finder.cpp:113-133) for a batch of RRT* sample points against the resident index of the
+C2 map (1M-point synthetic forest, clean_demo parameters).  `value` = queries/s with the batch resident in
+HBM; `e2e` = the same call with pinned HOST buffers (H2D + D2H inside the timed region).  One JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "exact NN radius queries/s on 1M-pt cloud"
+UNIT = "queries/s"
+N_POINTS = 1_000_000
+CLOUD_SEED = 1
+PARAMS = dict(search_margin=0.25, max_radius=1.5, sample_range=30.0)   # clean_demo.launch:31-34
+BYTES_PER_QUERY = 16            # algorithmic: 12 B query (xyz float32) in + 4 B radius out
+FRAME_POINTS = 300_000          # C3 frame for the build-ms metric
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--queries", type=int, default=10_000_000, help="queries per step per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=1_000_000)
+    ap.add_argument("--ref-sample", type=int, default=200_000, help="queries per step of the reference arm")
+    return ap.parse_args()
+
+
+def workload_config(args, extra=None):
+    cfg = {"workload": "C2: 1M-point synthetic forest map (jittered lattice, seed 1), radiusSearch batches of "
+                       f"{args.queries} uniform in-box RRT* samples per GPU, clean_demo params "
+                       "(search_margin 0.25, max_radius 1.5, sample_range 30)",
+           "points": N_POINTS, "queries_per_step_per_gpu": args.queries,
+           "l2_policy": "inputs+outputs per step (16 B/query x 1e7 = 160 MB) exceed the 126 MB L2"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+def make_cloud():
+    from pointcloudtraj_b200 import synth
+    return synth.forest_cloud(N_POINTS, seed=CLOUD_SEED, variant="J", return_half=True)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self._stop_evt = gpu, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ---- CPU legs (the only places that execute oracle/) --------------------------------------------------
+def cpu_reference_tree(pts):
+    import oracle
+    order = np.random.default_rng(0).permutation(len(pts))
+    if oracle.have_reference():
+        return oracle.KdReference().build(pts, order), "reference"
+    return oracle.KdOracle().build(pts, order), "port"
+
+
+def cpu_radius(tree, kind, q, start):
+    import oracle
+    P = oracle.RadiusParams.make(start=start, **PARAMS)
+    if kind == "reference":
+        return tree.radius_batch(P, q, nthreads=0)
+    return tree.radius_batch(P, q)[0]
+
+
+def cpu_baseline(pts, q, start, sample):
+    import oracle
+    t0 = time.perf_counter()
+    tree, kind = cpu_reference_tree(pts)
+    t_build = time.perf_counter() - t0
+    qs = q[:sample]
+    t0 = time.perf_counter()
+    r = cpu_radius(tree, kind, qs, start)
+    dt = time.perf_counter() - t0
+    cores = tree.max_threads() if kind == "reference" else 1
+    return {"value": len(qs) / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"first {len(qs)} queries of the step batch on the same 1M-point cloud "
+                      f"(kd_insert3 build {t_build * 1e3:.0f} ms single-threaded, not included)",
+            "build_ms": t_build * 1e3}, r
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from pointcloudtraj_b200 import synth
+    pts, half = make_cloud()
+    start = (0.0, 0.0, 2.0)
+    tree, kind = cpu_reference_tree(pts)
+    cores = tree.max_threads() if kind == "reference" else 1
+    m = args.ref_sample
+    qs = [synth.rrt_queries(m, half, seed=100 + s) for s in range(args.warmup + args.steps)]
+    for s in range(args.warmup):
+        cpu_radius(tree, kind, qs[s], start)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        cpu_radius(tree, kind, qs[args.warmup + s], start)
+    dt = time.perf_counter() - t0
+    val = m * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, {"reference_step_sample": m}),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"{m} queries per step (bounded sample of the {args.queries}-query batch), "
+                                       "kd_nearest3 + radiusSearch epilogue, OpenMP over queries"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---- this repo's arm -----------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from pointcloudtraj_b200 import PC_DEVICE, PcRadiusParams, PointCloudIndex, synth  # noqa: F401
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    M = args.queries
+    start = (0.0, 0.0, 2.0)
+
+    # the cloud: generated on rank 0, replicated with one NCCL broadcast, indexed on every rank
+    if rank == 0:
+        pts, half = make_cloud()
+        t_pts = torch.from_numpy(pts).to(dev)
+        meta = torch.tensor([half], dtype=torch.float64, device=dev)
+    else:
+        t_pts = torch.empty((N_POINTS, 3), dtype=torch.float32, device=dev)
+        meta = torch.zeros(1, dtype=torch.float64, device=dev)
+    bcast_ms = 0.0
+    if world > 1:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        e0.record()
+        dist.broadcast(t_pts, 0)
+        dist.broadcast(meta, 0)
+        e1.record()
+        torch.cuda.synchronize()
+        bcast_ms = e0.elapsed_time(e1)
+    half = float(meta.item())
+
+    stream = torch.cuda.current_stream().cuda_stream
+    ix = PointCloudIndex(max_points=N_POINTS, device=local, stream=stream)
+    build_ms = []
+    for _ in range(5):
+        ix.build(t_pts)
+        build_ms.append(ix.last_build_ms())
+    P = PcRadiusParams.make(start=start, **PARAMS)
+
+    # per-rank query batch (weak scaling: every GPU answers its own M queries per step)
+    q_host = synth.rrt_queries(M, half, seed=1000 + rank)
+    q_pin = torch.from_numpy(q_host).pin_memory()
+    t_q = q_pin.to(dev, non_blocking=True)
+    t_r = torch.empty(M, dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    import ctypes as C
+    lib = ix._L
+
+    def step_device():
+        rc = lib.pc_radius_batch(ix._h, C.c_void_p(t_q.data_ptr()), M, 3, PC_DEVICE, 0, C.byref(P), C.c_void_p(t_r.data_ptr()), None)
+        if rc != 0:
+            raise RuntimeError(lib.pc_last_error(ix._h).decode())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ix.profile(True)
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ix.launches(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    search_ms, order_ms = [], []
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    launches = ix.launches()
+    elapsed_ms = e0.elapsed_time(e1)
+    # kernel-level durations of the dominant kernel, measured with CUDA events around it (separate short loop so
+    # that reading the events does not stall the timed region above)
+    for _ in range(min(args.steps, 10)):
+        step_device()
+        a, b = ix.last_batch_ms()
+        order_ms.append(a)
+        search_ms.append(b)
+    ix.profile(False)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * M * args.steps / (elapsed_ms * 1e-3)
+
+    # e2e: the same call through the C ABI with pinned HOST buffers (H2D of the batch + D2H of the radii inside the timed region)
+    r_pin = torch.empty(M, dtype=torch.float32).pin_memory()
+    qp, rp = q_pin.numpy(), r_pin.numpy()
+
+    def step_host():
+        rc = lib.pc_radius_batch(ix._h, C.c_void_p(qp.ctypes.data), M, 3, 0, 0, C.byref(P), C.c_void_p(rp.ctypes.data), None)
+        if rc != 0:
+            raise RuntimeError(lib.pc_last_error(ix._h).decode())
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * M * e2e_steps / float(t.item())
+    same = bool((r_pin.to(dev) == t_r).all().item())
+
+    # C3: index rebuild of a 300k-point frame (ms/frame), device-resident frame
+    frame = t_pts[:FRAME_POINTS].contiguous()
+    ixf = PointCloudIndex(max_points=FRAME_POINTS, device=local, stream=stream)
+    fms = []
+    for _ in range(12):
+        ixf.build(frame)
+        fms.append(ixf.last_build_ms())
+    ixf.close()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        k_ms = float(np.mean(search_ms))
+        achieved = BYTES_PER_QUERY * M / (k_ms * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": None, "kernel": "pc_radius_kernel", "kernel_ms": k_ms,
+                             "batch_order_ms": float(np.mean(order_ms)),
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                             "algorithmic_bytes_per_query": BYTES_PER_QUERY},
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 12 * M, "d2h_bytes_per_step": 4 * M,
+                        "steps": e2e_steps, "matches_device_result": same},
+                "gpu_launches": launches, "clocks": clocks,
+                "index_build_ms_per_frame": {"points": FRAME_POINTS, "median": float(np.median(fms[2:])), "min": float(min(fms))},
+                "index_build_ms_1M": float(np.median(build_ms[1:])), "broadcast_ms": bcast_ms}
+        if not args.no_cpu_baseline and world == 1:
+            cb, r_cpu = cpu_baseline(t_pts.cpu().numpy(), q_host, start, args.cpu_sample)
+            cb["gpu_matches_cpu_sample"] = bool((r_cpu.astype(np.float32) == t_r[: len(r_cpu)].cpu().numpy()).all())
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    ix.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -1,0 +1,169 @@
+/*
+ * pc_index.h -- C ABI of libpcindex.so: exact nearest-obstacle queries against a raw point cloud
+ * on one NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary for pointcloudTraj's hot path.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference checkout):
+ *
+ *   pc_index_create / destroy   kd_create / kd_free                 Utils/kdtree/include/kdtree/kdtree.h:39-46
+ *                                                                   (Utils/kdtree/src/kdtree.c:112-134)
+ *   pc_index_build              kd_clear + n x kd_insert3(x,y,z,(void*)i)   kdtree.h:49,58  (kdtree.c:143-159,244-251)
+ *                               == safeRegionRrtStar::setInput      Planner/src/corridor_finder.cpp:93-99
+ *   pc_nearest_batch            kd_nearest3 + kd_res_item + kd_res_free     kdtree.h:67,113,97 (kdtree.c:493-500,641-650,613)
+ *   pc_range_batch              kd_nearest_range3 + kd_res_size/next/item   kdtree.h:92,100-113 (kdtree.c:595-602)
+ *   pc_radius_batch             safeRegionRrtStar::radiusSearch     Planner/src/corridor_finder.cpp:113-133
+ *                               (parameters of setParam :17-23, start point of setStartPt :43-50)
+ *   pc_clearance_batch          checkSafeTrajectory + getPosFromBezier + checkTrajPtCol
+ *                               Planner/src/sim_planning_demo.cpp:729-781, :715-727; corridor_finder.cpp:412-416
+ *   pc_comm_* / pc_index_broadcast   (no counterpart: the reference is single-process) -- replicate the
+ *                               built index to the other GPUs of the host with one ncclBroadcast.
+ *
+ * Conventions (kept from the reference's C API): opaque handle created and destroyed by the
+ * caller; int return, 0 = success, negative = error (never aborts, never throws); an empty index
+ * is legal (kd_nearest3 returns NULL -> idx -1, d2 +inf); the caller owns every in/out buffer;
+ * the index copies the cloud.  One host thread per handle.
+ *
+ * Memory spaces: every batch call takes `space` = PC_HOST or PC_DEVICE and ALL of its array
+ * arguments live in that space.  PC_DEVICE calls are asynchronous on the handle's stream (call
+ * pc_index_sync or synchronise the stream you passed to pc_index_create); PC_HOST calls return
+ * when the results are in the caller's host buffers (pinned buffers from pc_host_alloc make the
+ * copies asynchronous and pipelined with the kernels).
+ *
+ * Exactness contract (DESIGN.md "Tie rule"): out_idx is the point that minimises the reference's
+ * fp64 expression d2 = ((px-qx)^2 + (py-qy)^2) + (pz-qz)^2 (float32 inputs widened to double,
+ * no FMA contraction); among several exact minimisers the LOWEST original index is returned.
+ * out_d2 / out_radius are the fp64 values rounded once to float32.
+ */
+#ifndef PC_INDEX_H_
+#define PC_INDEX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PC_OK          0
+#define PC_EINVAL     (-1)  /* bad argument                                              */
+#define PC_ENOMEM     (-2)  /* host or device allocation failed (kd_insert returns -1)   */
+#define PC_ECUDA      (-3)  /* CUDA runtime error, see pc_last_error                     */
+#define PC_ECAP       (-4)  /* output capacity too small; counts/offsets are still valid */
+#define PC_ENCCL      (-5)  /* NCCL not available or NCCL error                          */
+#define PC_ENOTIMPL   (-6)
+
+#define PC_HOST   0
+#define PC_DEVICE 1
+
+/* flags for pc_radius_batch / pc_clearance_batch */
+#define PC_RADIUS_BOUNDED   0  /* default: search only within max_radius + search_margin (exact for the radius) */
+#define PC_RADIUS_FULL_NN   1  /* unbounded search: out_idx is the true nearest point even where the radius clamps */
+/* flags for pc_nearest_batch / pc_radius_batch: reorder the batch along a Morton curve first (same results) */
+#define PC_QUERY_AUTO      0
+#define PC_QUERY_UNSORTED  2
+#define PC_QUERY_SORTED    4
+
+typedef struct pc_index pc_index;
+
+/* safeRegionRrtStar::setParam (corridor_finder.cpp:17-23) + start_pt (corridor_finder.cpp:43-50).
+ * sample_range < 0 disables the out-of-sensing-range early-out of radiusSearch (:115-116). */
+typedef struct pc_radius_params {
+    double search_margin;
+    double max_radius;
+    double sample_range;
+    double start[3];
+} pc_radius_params;
+
+/* One piecewise Bezier trajectory = segments [first_seg, first_seg + num_seg) of the segment arrays;
+ * t_now = max(0, odom stamp - trajectory start) of checkSafeTrajectory (sim_planning_demo.cpp:735). */
+typedef struct pc_traj {
+    int32_t first_seg;
+    int32_t num_seg;
+    double  t_now;
+} pc_traj;
+
+/* device-side layout of a built index (for inspection and for replication across GPUs) */
+typedef struct pc_index_view {
+    int64_t n_points;      /* points in the cloud                                           */
+    int64_t n_leaves;      /* ceil(n_points / 8)                                            */
+    int64_t leaf_base;     /* P: power of two >= max(2, n_leaves); node ids are [1, 2P)      */
+    const void *points;    /* float4[8 * n_leaves]: x, y, z, original index (int bits)      */
+    const void *nodes;     /* float4[4 * P]: node i -> lo = nodes[2i], hi = nodes[2i+1]      */
+    float bbox_lo[3], bbox_hi[3];
+} pc_index_view;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int  pc_index_create(pc_index **out, int device, int64_t max_points, void *cuda_stream /* nullable */);
+void pc_index_destroy(pc_index *ix);
+int  pc_index_sync(pc_index *ix);                       /* wait for the handle's stream */
+const char *pc_last_error(const pc_index *ix);          /* ix may be NULL: last create() failure */
+const char *pc_version(void);
+
+/* ---- index ---------------------------------------------------------------------------------- */
+/* stride_floats = 3 (packed xyz) or 4 (pcl::PointXYZ / PointCloud2 x,y,z,pad layout). n == 0 is legal. */
+int  pc_index_build(pc_index *ix, const float *xyz, int64_t n, int64_t stride_floats, int space);
+int64_t pc_index_size(const pc_index *ix);
+int  pc_index_view_get(const pc_index *ix, pc_index_view *out);
+/* device time of the last pc_index_build on this handle, ms (CUDA events; syncs the stream) */
+int  pc_index_last_build_ms(pc_index *ix, float *ms);
+
+/* ---- queries -------------------------------------------------------------------------------- */
+/* out_idx: -1 when the index is empty; out_d2: +inf when empty.  Either output may be NULL. */
+int  pc_nearest_batch(pc_index *ix, const float *q_xyz, int64_t m, int64_t q_stride, int space, int flags,
+                      int32_t *out_idx, float *out_d2);
+
+/* out_radius = min(sqrt(d2) - search_margin, max_radius), or max_radius - search_margin for the
+ * early-outs (query farther than sample_range + max_radius from start; empty index).
+ * out_idx (nullable): nearest point, -1 for early-outs and (PC_RADIUS_BOUNDED) where the radius clamps. */
+int  pc_radius_batch(pc_index *ix, const float *q_xyz, int64_t m, int64_t q_stride, int space, int flags,
+                     const pc_radius_params *params, float *out_radius, int32_t *out_idx);
+
+/* All points with d2 <= range^2 (inclusive, kdtree.c:273).  range: one value (range_is_scalar) or m values.
+ * out_offsets[m+1] is the CSR row pointer; out_idx[cap] the concatenated lists (each list ascending by
+ * original index).  If the total exceeds cap: returns PC_ECAP, out_offsets is still complete, out_idx untouched
+ * beyond what fits.  Pass out_idx == NULL, cap == 0 to get the offsets only (returns PC_OK). */
+int  pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64_t q_stride, int space,
+                    const double *range, int range_is_scalar,
+                    int64_t *out_offsets, int32_t *out_idx, int64_t cap);
+
+/* Per trajectory: walk the segments from t_now in steps of dt while the accumulated time <= horizon
+ * (sim_planning_demo.cpp:745-749), evaluate p = T_i * sum_j C(n,j) c_ij u^j (1-u)^(n-j), u = t/T_i,
+ * cast to float32 and apply radiusSearch.  seg_coef_off[s] is the offset (in doubles) of segment s's
+ * [x_0..x_n | y_0..y_n | z_0..z_n] block in coef; seg_order[s] = n in [1, 12].
+ * out_first_hit[t]  : ordinal of the first sample with radius < 0 (the reference returns true there), -1 if none
+ * out_min_radius[t] : min radiusSearch value over all samples within the horizon (+inf if no samples)
+ * out_n_samples[t]  : samples within the horizon (nullable) */
+int  pc_clearance_batch(pc_index *ix, const pc_traj *traj, int64_t n_traj,
+                        const int32_t *seg_order, const double *seg_T, const int64_t *seg_coef_off,
+                        int64_t n_seg, const double *coef, int64_t n_coef, int space,
+                        double dt, double horizon, const pc_radius_params *params,
+                        int32_t *out_first_hit, float *out_min_radius, int32_t *out_n_samples);
+
+/* ---- pinned host memory for PC_HOST calls ------------------------------------------------------ */
+void *pc_host_alloc(int64_t bytes);
+void  pc_host_free(void *p);
+
+/* ---- multi-GPU (one process per GPU) ------------------------------------------------------------ */
+#define PC_NCCL_UNIQUE_ID_BYTES 128
+typedef struct pc_comm pc_comm;
+int  pc_comm_unique_id(char id[PC_NCCL_UNIQUE_ID_BYTES]);           /* rank 0; ship the bytes to the other ranks */
+int  pc_comm_init(pc_comm **out, int rank, int n_ranks, const char id[PC_NCCL_UNIQUE_ID_BYTES], int device);
+void pc_comm_destroy(pc_comm *c);
+/* Replicate root's built index (points + nodes + header) into every rank's handle: ncclBroadcast on the
+ * handle's stream.  After it returns every rank answers queries against the same index. */
+int  pc_index_broadcast(pc_index *ix, pc_comm *c, int root);
+/* contiguous slice [begin, end) of m units owned by `rank` (queries or trajectories) */
+void pc_shard_range(int64_t m, int rank, int n_ranks, int64_t *begin, int64_t *end);
+
+/* ---- instrumentation -------------------------------------------------------------------------- */
+/* number of kernels this library launched on the handle since the last reset (for bench.py's gpu_launches) */
+int64_t pc_launch_count(const pc_index *ix, int reset);
+/* When enabled, PC_DEVICE query batches record CUDA events around their two phases on the handle's stream;
+ * pc_profile_last_batch waits for them and returns the device time of the Morton ordering of the batch
+ * (0 when the batch was not reordered) and of the search kernel, in ms. */
+int  pc_profile_enable(pc_index *ix, int on);
+int  pc_profile_last_batch(pc_index *ix, float *order_ms, float *search_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PC_INDEX_H_ */

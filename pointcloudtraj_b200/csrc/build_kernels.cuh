@@ -1,0 +1,165 @@
+// build_kernels.cuh -- index construction kernels (bbox, Morton keys, leaf gather, bounding-box tree).
+//
+// Index layout in HBM (all float4, 16-byte aligned, see DESIGN.md "Data layout"):
+//   points[8 * n_leaves] : the cloud in Morton order, (x, y, z, original index as int bits); the tail of the
+//                          last leaf repeats the last real point so leaf scans need no bounds check
+//   nodes[4 * P]         : implicit complete binary tree in heap numbering over P = 2^k >= n_leaves leaf
+//                          slots; node i owns nodes[2i] = box min (xyz), nodes[2i+1] = box max (xyz);
+//                          children 2i, 2i+1 are adjacent (one aligned 64-byte pair); leaf j is node P + j;
+//                          unused slots hold the empty box (min = +inf, max = -inf)
+// replaces struct kdtree / struct kdnode / struct kdhyperrect (Utils/kdtree/src/kdtree.c:56-80) and
+// hyperrect_extend (kdtree.c:729-741).
+#pragma once
+#include "common.cuh"
+
+#define PC_BUILD_THREADS 256
+
+// ---- bounding box of the cloud: bbox[0..2] = ordered(min), bbox[3..5] = ordered(max) ----------------
+__global__ void __launch_bounds__(PC_BUILD_THREADS)
+pc_bbox_kernel(const float *__restrict__ xyz, int64_t n, int stride, uint32_t *__restrict__ bbox)
+{
+    float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float *p = xyz + i * stride;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            float v = p[a];
+            lo[a] = fminf(lo[a], v);   // fminf/fmaxf drop NaNs
+            hi[a] = fmaxf(hi[a], v);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(PC_FULL_MASK, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(PC_FULL_MASK, hi[a], o));
+        }
+    }
+    __shared__ float s_lo[PC_BUILD_THREADS / 32][3], s_hi[PC_BUILD_THREADS / 32][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) { s_lo[warp][a] = lo[a]; s_hi[warp][a] = hi[a]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        int a = threadIdx.x;
+        float l = s_lo[0][a], h = s_hi[0][a];
+        for (int w = 1; w < PC_BUILD_THREADS / 32; w++) { l = fminf(l, s_lo[w][a]); h = fmaxf(h, s_hi[w][a]); }
+        atomicMin(&bbox[a], pc_float_to_ordered(l));
+        atomicMax(&bbox[3 + a], pc_float_to_ordered(h));
+    }
+}
+
+// decode the bbox into the quantisation frame (device-side, no host round trip)
+__device__ __forceinline__ pc_frame pc_make_frame(const uint32_t *bbox, int bits)
+{
+    pc_frame f;
+    float ext = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        float lo = pc_ordered_to_float(bbox[a]), hi = pc_ordered_to_float(bbox[3 + a]);
+        f.lo[a] = lo;
+        ext = fmaxf(ext, hi - lo);
+    }
+    f.max_cell = (1u << bits) - 1u;
+    // cells of edge ext / 2^bits; a degenerate cloud (ext == 0) maps everything to cell 0
+    f.inv_cell = (ext > 0.0f && ext < INFINITY) ? ((float)(1u << bits) * (1.0f - 1e-6f)) / ext : 0.0f;
+    return f;
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(PC_BUILD_THREADS)
+pc_keygen_kernel(const float *__restrict__ xyz, int64_t n, int stride, const uint32_t *__restrict__ bbox, int bits,
+                 KeyT *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    const pc_frame f = pc_make_frame(bbox, bits);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float *p = xyz + i * stride;
+        if (sizeof(KeyT) == 4) keys[i] = (KeyT)pc_morton30(p[0], p[1], p[2], f);
+        else keys[i] = (KeyT)pc_morton63(p[0], p[1], p[2], f);
+        vals[i] = (uint32_t)i;
+    }
+}
+
+// ---- leaves: gather the cloud into Morton order (one thread per point slot) and box every 8 slots ----
+__global__ void __launch_bounds__(PC_BUILD_THREADS)
+pc_leaf_kernel(const float *__restrict__ xyz, int stride, const uint32_t *__restrict__ order, int64_t n,
+               int64_t n_leaves, int64_t P, float4 *__restrict__ points, float4 *__restrict__ nodes)
+{
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // grid covers 8 * n_leaves (rounded up to 8 lanes)
+    const bool in_range = slot < n_leaves * PC_LEAF;
+    int64_t s = slot < n ? slot : n - 1;                                    // tail slots repeat the last real point
+    float x = 0.f, y = 0.f, z = 0.f; uint32_t src = 0;
+    if (in_range) {
+        src = order[s];
+        const float *p = xyz + (int64_t)src * stride;
+        x = p[0]; y = p[1]; z = p[2];
+        points[slot] = make_float4(x, y, z, __uint_as_float(src));
+    }
+    // NaN coordinates must not poison the box: fminf/fmaxf ignore them
+    float lx = in_range ? x : INFINITY, ly = in_range ? y : INFINITY, lz = in_range ? z : INFINITY;
+    float hx = in_range ? x : -INFINITY, hy = in_range ? y : -INFINITY, hz = in_range ? z : -INFINITY;
+#pragma unroll
+    for (int o = 1; o < PC_LEAF; o <<= 1) {
+        lx = fminf(lx, __shfl_xor_sync(PC_FULL_MASK, lx, o)); hx = fmaxf(hx, __shfl_xor_sync(PC_FULL_MASK, hx, o));
+        ly = fminf(ly, __shfl_xor_sync(PC_FULL_MASK, ly, o)); hy = fmaxf(hy, __shfl_xor_sync(PC_FULL_MASK, hy, o));
+        lz = fminf(lz, __shfl_xor_sync(PC_FULL_MASK, lz, o)); hz = fmaxf(hz, __shfl_xor_sync(PC_FULL_MASK, hz, o));
+    }
+    if ((threadIdx.x & (PC_LEAF - 1)) == 0) {
+        int64_t leaf = slot / PC_LEAF;
+        // leaf n_leaves (if inside the array) is written as the empty box: it is the sibling of the last leaf when n_leaves is odd
+        if (leaf <= n_leaves && leaf < P) {
+            nodes[2 * (P + leaf)] = make_float4(lx, ly, lz, 0.f);
+            nodes[2 * (P + leaf) + 1] = make_float4(hx, hy, hz, 0.f);
+        }
+    }
+}
+
+// ---- upper levels: each CTA folds 2*PC_UP_THREADS nodes of level `lvl0` into up to PC_UP_LEVELS levels above ----
+// Level l has base id P >> l and cnt_l = ceil(cnt_{l-1} / 2) real nodes (cnt_0 = n_leaves); node cnt_l of a level
+// (the possible sibling of its last real node) is written as the empty box.
+#define PC_UP_THREADS 128
+#define PC_UP_LEVELS 8   // log2(2 * PC_UP_THREADS)
+
+__global__ void __launch_bounds__(PC_UP_THREADS)
+pc_upper_kernel(float4 *__restrict__ nodes, int64_t P, int lvl0, int64_t cnt0, int n_levels)
+{
+    __shared__ float4 s_lo[PC_UP_THREADS], s_hi[PC_UP_THREADS];
+    const int t = threadIdx.x;
+    int64_t child_first = (int64_t)blockIdx.x * (2 * PC_UP_THREADS);   // index inside level lvl0
+    int64_t cnt_child = cnt0;
+    float4 lo, hi;
+    for (int s = 1; s <= n_levels; s++) {
+        const int lvl = lvl0 + s;
+        const int64_t base = P >> lvl;                 // id of the first node of this level
+        const int64_t cnt = (cnt_child + 1) >> 1;      // real nodes on this level
+        const int width = (2 * PC_UP_THREADS) >> s;    // nodes of this level owned by this CTA
+        const int64_t k = (child_first >> s) + t;      // node index inside the level
+        if (t < width) {
+            float4 alo, ahi, blo, bhi;
+            if (s == 1) {
+                const int64_t cbase = P >> lvl0;
+                const int64_t c = 2 * k;
+                const float4 e_lo = make_float4(INFINITY, INFINITY, INFINITY, 0.f), e_hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
+                if (c < cnt_child) { alo = nodes[2 * (cbase + c)]; ahi = nodes[2 * (cbase + c) + 1]; } else { alo = e_lo; ahi = e_hi; }
+                if (c + 1 < cnt_child) { blo = nodes[2 * (cbase + c + 1)]; bhi = nodes[2 * (cbase + c + 1) + 1]; } else { blo = e_lo; bhi = e_hi; }
+            } else {
+                alo = s_lo[2 * t]; ahi = s_hi[2 * t]; blo = s_lo[2 * t + 1]; bhi = s_hi[2 * t + 1];
+            }
+            lo = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.f);
+            hi = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.f);
+        }
+        __syncthreads();   // everyone has read the previous level from shared memory
+        if (t < width) {
+            s_lo[t] = lo; s_hi[t] = hi;
+            if (k <= cnt && k < base) {   // base == number of slots on this level
+                nodes[2 * (base + k)] = lo;
+                nodes[2 * (base + k) + 1] = hi;
+            }
+        }
+        __syncthreads();
+        cnt_child = cnt;
+    }
+}

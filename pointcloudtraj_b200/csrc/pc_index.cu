@@ -1,0 +1,571 @@
+// pc_index.cu -- C ABI of libpcindex.so (see include/pc_index.h) and the host-side orchestration:
+// arena management, stream ordering, the chunked H2D / kernel / D2H pipeline for PC_HOST calls.
+//
+// No CPU fallback exists: every entry point either launches the sm_100a kernels or returns an error.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdarg.h>
+#include <math.h>
+#include <dlfcn.h>
+#include <new>
+
+#include "../../include/pc_index.h"
+#include "common.cuh"
+#include "radix_sort.cuh"
+#include "build_kernels.cuh"
+#include "query_kernels.cuh"
+#include "range_kernels.cuh"
+#include "clearance_kernels.cuh"
+
+#define PC_VERSION_STRING "pcindex 0.1 (sm_100a)"
+#define PC_PIPE_LANES 3                 // concurrent H2D / kernel / D2H chunks for PC_HOST calls
+#define PC_HOST_CHUNK (1 << 20)         // queries per pipelined chunk
+#define PC_SORT_MIN_BATCH (1 << 15)     // PC_QUERY_AUTO sorts batches at least this large
+
+static thread_local char g_create_error[256] = "";
+
+// per-lane scratch for query batches (device staging for PC_HOST calls, sort buffers for Morton-ordered batches)
+struct pc_lane {
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    float *d_q = nullptr; int64_t q_cap = 0;                 // floats
+    int32_t *d_i32 = nullptr; int64_t i32_cap = 0;
+    float *d_f32 = nullptr; int64_t f32_cap = 0;
+    uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr; int64_t sort_cap = 0;
+    uint32_t *tile_hist = nullptr; int64_t hist_cap = 0;
+    uint32_t *digit_total = nullptr;
+    cudaEvent_t done = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr;   // profiling: batch start / ordered / searched
+};
+
+struct pc_index {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+
+    // cloud / index
+    int64_t cap = 0;          // points the arena can hold
+    int64_t n = 0, n_leaves = 0, P = 2;
+    int key_bytes = 4;
+    float *d_xyz = nullptr;   // staging copy of the caller's cloud for PC_HOST builds (cap * 4 floats)
+    uint32_t *d_bbox = nullptr;
+    void *keys_a = nullptr, *keys_b = nullptr;
+    uint32_t *vals_a = nullptr, *vals_b = nullptr;
+    uint32_t *tile_hist = nullptr; int64_t hist_cap = 0;
+    uint32_t *digit_total = nullptr;
+    float4 *points = nullptr; int64_t points_cap = 0;
+    float4 *nodes = nullptr; int64_t nodes_cap = 0;
+    cudaEvent_t ev_b0 = nullptr, ev_b1 = nullptr, ev_ready = nullptr;
+    bool build_timed = false;
+
+    pc_lane lane[PC_PIPE_LANES];
+
+    // generic device scratch for range / clearance
+    void *scratch = nullptr; int64_t scratch_cap = 0;
+
+    int64_t launches = 0;
+    bool profile = false, profiled = false;
+    char err[256] = "";
+};
+
+// ---- error helpers ---------------------------------------------------------------------------------
+static int pc_fail(pc_index *ix, int code, const char *fmt, ...)
+{
+    char *dst = ix ? ix->err : g_create_error;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 256, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define PC_CUDA(ix, call)                                                                            \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return pc_fail((ix), e_ == cudaErrorMemoryAllocation ? PC_ENOMEM : PC_ECUDA, "%s: %s", #call, \
+                           cudaGetErrorString(e_));                                                  \
+    } while (0)
+
+#define PC_CHECK_LAUNCH(ix) PC_CUDA(ix, cudaGetLastError())
+
+template <typename T>
+static int pc_grow(pc_index *ix, T **ptr, int64_t *cap, int64_t want, int64_t min_cap = 0)
+{
+    if (want <= *cap) return PC_OK;
+    int64_t c = want > min_cap ? want : min_cap;
+    if (*ptr) { PC_CUDA(ix, cudaFree(*ptr)); *ptr = nullptr; *cap = 0; }
+    PC_CUDA(ix, cudaMalloc((void **)ptr, (size_t)c * sizeof(T)));
+    *cap = c;
+    return PC_OK;
+}
+
+static int64_t pc_pow2_ge(int64_t v)
+{
+    int64_t p = 2;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static int pc_key_bits_per_axis(int64_t n)
+{
+    // 10 bits per axis (30-bit keys, 4 radix passes) up to 4 Mi points; beyond that one more bit per axis for
+    // every 4x points so that leaves stay spatially tight (surface-like clouds fill ~4^b cells)
+    int b = 10;
+    int64_t lim = (int64_t)1 << 22;
+    while (n > lim && b < 21) { b++; lim <<= 2; }
+    return b;
+}
+
+// ---- lifetime ----------------------------------------------------------------------------------------
+static int pc_reserve_cloud(pc_index *ix, int64_t n)
+{
+    if (n <= ix->cap) return PC_OK;
+    int64_t cap = n;
+    // free the old arena
+    cudaFree(ix->d_xyz); cudaFree(ix->keys_a); cudaFree(ix->keys_b); cudaFree(ix->vals_a); cudaFree(ix->vals_b);
+    cudaFree(ix->points); cudaFree(ix->nodes); cudaFree(ix->tile_hist);
+    ix->d_xyz = nullptr; ix->keys_a = ix->keys_b = nullptr; ix->vals_a = ix->vals_b = nullptr;
+    ix->points = ix->nodes = nullptr; ix->tile_hist = nullptr; ix->cap = 0; ix->hist_cap = 0;
+    ix->key_bytes = pc_key_bits_per_axis(cap) > 10 ? 8 : 4;
+    PC_CUDA(ix, cudaMalloc((void **)&ix->d_xyz, (size_t)cap * 4 * sizeof(float)));
+    PC_CUDA(ix, cudaMalloc(&ix->keys_a, (size_t)cap * ix->key_bytes));
+    PC_CUDA(ix, cudaMalloc(&ix->keys_b, (size_t)cap * ix->key_bytes));
+    PC_CUDA(ix, cudaMalloc((void **)&ix->vals_a, (size_t)cap * sizeof(uint32_t)));
+    PC_CUDA(ix, cudaMalloc((void **)&ix->vals_b, (size_t)cap * sizeof(uint32_t)));
+    int64_t leaves = (cap + PC_LEAF - 1) / PC_LEAF;
+    int64_t P = pc_pow2_ge(leaves);
+    ix->points_cap = (leaves + 1) * PC_LEAF;
+    ix->nodes_cap = 4 * P;
+    PC_CUDA(ix, cudaMalloc((void **)&ix->points, (size_t)ix->points_cap * sizeof(float4)));
+    PC_CUDA(ix, cudaMalloc((void **)&ix->nodes, (size_t)ix->nodes_cap * sizeof(float4)));
+    ix->hist_cap = (int64_t)RS_RADIX * (rs_num_tiles<8>(cap) + 1);
+    PC_CUDA(ix, cudaMalloc((void **)&ix->tile_hist, (size_t)ix->hist_cap * sizeof(uint32_t)));
+    ix->cap = cap;
+    return PC_OK;
+}
+
+extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, void *cuda_stream)
+{
+    if (!out || max_points < 0 || max_points > ((int64_t)1 << 31) - 16) return pc_fail(nullptr, PC_EINVAL, "pc_index_create: bad argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return pc_fail(nullptr, PC_ECUDA, "pc_index_create: no CUDA device (%s) -- libpcindex has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return pc_fail(nullptr, PC_EINVAL, "pc_index_create: device %d of %d", device, ndev);
+    pc_index *ix = new (std::nothrow) pc_index();
+    if (!ix) return pc_fail(nullptr, PC_ENOMEM, "pc_index_create: host allocation failed");
+    ix->device = device;
+    int rc = PC_OK;
+    do {
+#define TRY(call) if ((e = (call)) != cudaSuccess) { rc = pc_fail(nullptr, e == cudaErrorMemoryAllocation ? PC_ENOMEM : PC_ECUDA, "%s: %s", #call, cudaGetErrorString(e)); break; }
+        TRY(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        TRY(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) { rc = pc_fail(nullptr, PC_ECUDA, "pc_index_create: device is sm_%d%d, this library is built for sm_100a only", prop.major, prop.minor); break; }
+        ix->sm_count = prop.multiProcessorCount;
+        if (cuda_stream) { ix->stream = (cudaStream_t)cuda_stream; ix->own_stream = false; }
+        else { TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking)); ix->own_stream = true; }
+        TRY(cudaEventCreate(&ix->ev_b0));
+        TRY(cudaEventCreate(&ix->ev_b1));
+        TRY(cudaEventCreateWithFlags(&ix->ev_ready, cudaEventDisableTiming));
+        TRY(cudaMalloc((void **)&ix->d_bbox, 8 * sizeof(uint32_t)));
+        TRY(cudaMalloc((void **)&ix->digit_total, RS_RADIX * sizeof(uint32_t)));
+        for (int l = 0; l < PC_PIPE_LANES; l++) {
+            // lane 0 shares the handle's stream (PC_DEVICE calls are ordered on it); the others overlap copies
+            if (l == 0) { ix->lane[l].stream = ix->stream; ix->lane[l].own_stream = false; }
+            else { TRY(cudaStreamCreateWithFlags(&ix->lane[l].stream, cudaStreamNonBlocking)); ix->lane[l].own_stream = true; }
+            TRY(cudaEventCreateWithFlags(&ix->lane[l].done, cudaEventDisableTiming));
+            TRY(cudaEventCreate(&ix->lane[l].t0));
+            TRY(cudaEventCreate(&ix->lane[l].t1));
+            TRY(cudaEventCreate(&ix->lane[l].t2));
+            TRY(cudaMalloc((void **)&ix->lane[l].digit_total, RS_RADIX * sizeof(uint32_t)));
+        }
+        if (rc != PC_OK) break;
+#undef TRY
+        if (max_points > 0) {
+            rc = pc_reserve_cloud(ix, max_points);
+            if (rc != PC_OK) { strncpy(g_create_error, ix->err, 255); break; }
+        }
+    } while (0);
+    if (rc != PC_OK) { pc_index_destroy(ix); return rc; }
+    *out = ix;
+    return PC_OK;
+}
+
+extern "C" void pc_index_destroy(pc_index *ix)
+{
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    for (int l = 0; l < PC_PIPE_LANES; l++) {
+        pc_lane &L = ix->lane[l];
+        if (L.stream && L.own_stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
+        cudaFree(L.d_q); cudaFree(L.d_i32); cudaFree(L.d_f32);
+        cudaFree(L.keys_a); cudaFree(L.keys_b); cudaFree(L.vals_a); cudaFree(L.vals_b);
+        cudaFree(L.tile_hist); cudaFree(L.digit_total);
+        if (L.done) cudaEventDestroy(L.done);
+        if (L.t0) cudaEventDestroy(L.t0);
+        if (L.t1) cudaEventDestroy(L.t1);
+        if (L.t2) cudaEventDestroy(L.t2);
+    }
+    cudaFree(ix->d_xyz); cudaFree(ix->d_bbox); cudaFree(ix->keys_a); cudaFree(ix->keys_b);
+    cudaFree(ix->vals_a); cudaFree(ix->vals_b); cudaFree(ix->tile_hist); cudaFree(ix->digit_total);
+    cudaFree(ix->points); cudaFree(ix->nodes); cudaFree(ix->scratch);
+    if (ix->ev_b0) cudaEventDestroy(ix->ev_b0);
+    if (ix->ev_b1) cudaEventDestroy(ix->ev_b1);
+    if (ix->ev_ready) cudaEventDestroy(ix->ev_ready);
+    if (ix->own_stream && ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+}
+
+extern "C" int pc_index_sync(pc_index *ix)
+{
+    if (!ix) return PC_EINVAL;
+    PC_CUDA(ix, cudaSetDevice(ix->device));
+    PC_CUDA(ix, cudaStreamSynchronize(ix->stream));
+    return PC_OK;
+}
+
+extern "C" const char *pc_last_error(const pc_index *ix) { return ix ? ix->err : g_create_error; }
+extern "C" const char *pc_version(void) { return PC_VERSION_STRING; }
+extern "C" int64_t pc_index_size(const pc_index *ix) { return ix ? ix->n : 0; }
+
+extern "C" int64_t pc_launch_count(const pc_index *ix, int reset)
+{
+    if (!ix) return 0;
+    int64_t v = ix->launches;
+    if (reset) const_cast<pc_index *>(ix)->launches = 0;
+    return v;
+}
+
+extern "C" void *pc_host_alloc(int64_t bytes)
+{
+    void *p = nullptr;
+    if (bytes <= 0) return nullptr;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+extern "C" void pc_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" void pc_shard_range(int64_t m, int rank, int n_ranks, int64_t *begin, int64_t *end)
+{
+    if (n_ranks < 1) n_ranks = 1;
+    if (rank < 0) rank = 0;
+    if (rank >= n_ranks) rank = n_ranks - 1;
+    int64_t base = m / n_ranks, rem = m % n_ranks;
+    int64_t b = rank * base + (rank < rem ? rank : rem);
+    int64_t e = b + base + (rank < rem ? 1 : 0);
+    if (begin) *begin = b;
+    if (end) *end = e;
+}
+
+// ---- index build -----------------------------------------------------------------------------------
+template <typename KeyT, int ITEMS>
+static int pc_build_sorted(pc_index *ix, const float *src, int stride, int64_t n, int bits, uint32_t **order_out)
+{
+    cudaStream_t st = ix->stream;
+    const int grid = (int)((n + PC_BUILD_THREADS - 1) / PC_BUILD_THREADS < (int64_t)ix->sm_count * 8
+                               ? (n + PC_BUILD_THREADS - 1) / PC_BUILD_THREADS : (int64_t)ix->sm_count * 8);
+    pc_keygen_kernel<KeyT><<<grid, PC_BUILD_THREADS, 0, st>>>(src, n, stride, ix->d_bbox, bits, (KeyT *)ix->keys_a, ix->vals_a);
+    ix->launches++;
+    PC_CHECK_LAUNCH(ix);
+    int key_bits = 3 * bits;
+    int end_bit = ((key_bits + 7) / 8) * 8;
+    int which = rs_sort_pairs<KeyT, ITEMS>((KeyT *)ix->keys_a, ix->vals_a, (KeyT *)ix->keys_b, ix->vals_b, n, 0, end_bit,
+                                           ix->tile_hist, ix->digit_total, st, &ix->launches);
+    PC_CHECK_LAUNCH(ix);
+    *order_out = which ? ix->vals_b : ix->vals_a;
+    return PC_OK;
+}
+
+extern "C" int pc_index_build(pc_index *ix, const float *xyz, int64_t n, int64_t stride_floats, int space)
+{
+    if (!ix) return PC_EINVAL;
+    if (n < 0 || (n > 0 && !xyz) || (stride_floats != 3 && stride_floats != 4) || (space != PC_HOST && space != PC_DEVICE))
+        return pc_fail(ix, PC_EINVAL, "pc_index_build: bad argument (n=%lld stride=%lld space=%d)", (long long)n, (long long)stride_floats, space);
+    if (n > ((int64_t)1 << 31) - 16) return pc_fail(ix, PC_EINVAL, "pc_index_build: at most 2^31-16 points");
+    PC_CUDA(ix, cudaSetDevice(ix->device));
+    if (n == 0) { ix->n = 0; ix->n_leaves = 0; ix->P = 2; ix->build_timed = false; return PC_OK; }
+    if (n > ix->cap) {
+        PC_CUDA(ix, cudaStreamSynchronize(ix->stream));
+        int rc = pc_reserve_cloud(ix, n);
+        if (rc != PC_OK) return rc;
+    }
+    cudaStream_t st = ix->stream;
+    const int stride = (int)stride_floats;
+    const float *src = xyz;
+    if (space == PC_HOST) {
+        PC_CUDA(ix, cudaMemcpyAsync(ix->d_xyz, xyz, (size_t)n * stride * sizeof(float), cudaMemcpyHostToDevice, st));
+        src = ix->d_xyz;
+    }
+    PC_CUDA(ix, cudaEventRecord(ix->ev_b0, st));
+    // bbox: [0..2] = 0xffffffff (ordered +max) for the minima, [3..5] = 0 for the maxima
+    PC_CUDA(ix, cudaMemsetAsync(ix->d_bbox, 0xff, 3 * sizeof(uint32_t), st));
+    PC_CUDA(ix, cudaMemsetAsync(ix->d_bbox + 3, 0x00, 3 * sizeof(uint32_t), st));
+    {
+        int64_t blocks = (n + PC_BUILD_THREADS - 1) / PC_BUILD_THREADS;
+        int grid = (int)(blocks < (int64_t)ix->sm_count * 4 ? blocks : (int64_t)ix->sm_count * 4);
+        pc_bbox_kernel<<<grid, PC_BUILD_THREADS, 0, st>>>(src, n, stride, ix->d_bbox);
+        ix->launches++;
+        PC_CHECK_LAUNCH(ix);
+    }
+    const int bits = pc_key_bits_per_axis(n);
+    uint32_t *order = nullptr;
+    int rc;
+    const bool big = n > ((int64_t)1 << 21);
+    if (bits <= 10) {
+        if (ix->key_bytes < 4) return pc_fail(ix, PC_ECUDA, "internal: key buffer");
+        rc = big ? pc_build_sorted<uint32_t, 16>(ix, src, stride, n, bits, &order)
+                 : pc_build_sorted<uint32_t, 8>(ix, src, stride, n, bits, &order);
+    } else {
+        if (ix->key_bytes < 8) return pc_fail(ix, PC_ECUDA, "internal: key buffer too narrow");
+        rc = pc_build_sorted<uint64_t, 16>(ix, src, stride, n, bits, &order);
+    }
+    if (rc != PC_OK) return rc;
+
+    const int64_t n_leaves = (n + PC_LEAF - 1) / PC_LEAF;
+    const int64_t P = pc_pow2_ge(n_leaves);
+    {
+        int64_t slots = (n_leaves + 1) * PC_LEAF;
+        int grid = (int)((slots + PC_BUILD_THREADS - 1) / PC_BUILD_THREADS);
+        pc_leaf_kernel<<<grid, PC_BUILD_THREADS, 0, st>>>(src, stride, order, n, n_leaves, P, ix->points, ix->nodes);
+        ix->launches++;
+        PC_CHECK_LAUNCH(ix);
+    }
+    int top = 0;
+    while (((int64_t)1 << top) < P) top++;
+    int64_t cnt = n_leaves;
+    for (int lvl0 = 0; lvl0 < top;) {
+        int nl = top - lvl0 < PC_UP_LEVELS ? top - lvl0 : PC_UP_LEVELS;
+        int grid = (int)((cnt + 2 + 2 * PC_UP_THREADS - 1) / (2 * PC_UP_THREADS));
+        pc_upper_kernel<<<grid, PC_UP_THREADS, 0, st>>>(ix->nodes, P, lvl0, cnt, nl);
+        ix->launches++;
+        PC_CHECK_LAUNCH(ix);
+        for (int s = 0; s < nl; s++) cnt = (cnt + 1) >> 1;
+        lvl0 += nl;
+    }
+    PC_CUDA(ix, cudaEventRecord(ix->ev_b1, st));
+    ix->n = n; ix->n_leaves = n_leaves; ix->P = P; ix->build_timed = true;
+    if (space == PC_HOST) PC_CUDA(ix, cudaStreamSynchronize(st));
+    return PC_OK;
+}
+
+extern "C" int pc_index_last_build_ms(pc_index *ix, float *ms)
+{
+    if (!ix || !ms) return PC_EINVAL;
+    if (!ix->build_timed) { *ms = 0.f; return PC_OK; }
+    PC_CUDA(ix, cudaSetDevice(ix->device));
+    PC_CUDA(ix, cudaEventSynchronize(ix->ev_b1));
+    PC_CUDA(ix, cudaEventElapsedTime(ms, ix->ev_b0, ix->ev_b1));
+    return PC_OK;
+}
+
+extern "C" int pc_index_view_get(const pc_index *ixc, pc_index_view *out)
+{
+    pc_index *ix = const_cast<pc_index *>(ixc);
+    if (!ix || !out) return PC_EINVAL;
+    memset(out, 0, sizeof *out);
+    out->n_points = ix->n; out->n_leaves = ix->n_leaves; out->leaf_base = ix->P;
+    out->points = ix->points; out->nodes = ix->nodes;
+    if (ix->n > 0) {
+        uint32_t h[6];
+        PC_CUDA(ix, cudaSetDevice(ix->device));
+        PC_CUDA(ix, cudaMemcpyAsync(h, ix->d_bbox, sizeof h, cudaMemcpyDeviceToHost, ix->stream));
+        PC_CUDA(ix, cudaStreamSynchronize(ix->stream));
+        for (int a = 0; a < 3; a++) { out->bbox_lo[a] = pc_ordered_to_float(h[a]); out->bbox_hi[a] = pc_ordered_to_float(h[3 + a]); }
+    }
+    return PC_OK;
+}
+
+// ---- query plumbing ----------------------------------------------------------------------------------
+static pc_tree pc_tree_of(const pc_index *ix)
+{
+    pc_tree T;
+    T.nodes = ix->nodes; T.points = ix->points; T.n_points = ix->n; T.P = (uint32_t)ix->P;
+    return T;
+}
+
+// Morton-order a device-resident batch on lane L: returns the permutation (device pointer) in *perm
+static int pc_sort_queries(pc_index *ix, pc_lane &L, const float *d_q, int64_t m, int qstride, const uint32_t **perm)
+{
+    if (m > L.sort_cap) {
+        int64_t c = m;
+        cudaFree(L.keys_a); cudaFree(L.keys_b); cudaFree(L.vals_a); cudaFree(L.vals_b);
+        L.keys_a = L.keys_b = L.vals_a = L.vals_b = nullptr; L.sort_cap = 0;
+        PC_CUDA(ix, cudaMalloc((void **)&L.keys_a, (size_t)c * 4));
+        PC_CUDA(ix, cudaMalloc((void **)&L.keys_b, (size_t)c * 4));
+        PC_CUDA(ix, cudaMalloc((void **)&L.vals_a, (size_t)c * 4));
+        PC_CUDA(ix, cudaMalloc((void **)&L.vals_b, (size_t)c * 4));
+        L.sort_cap = c;
+    }
+    int64_t need_hist = (int64_t)RS_RADIX * (rs_num_tiles<16>(m) + 1);
+    int rc = pc_grow(ix, &L.tile_hist, &L.hist_cap, need_hist);
+    if (rc != PC_OK) return rc;
+    // keep the top 16 of the 30 Morton bits: 2 radix passes, cells of ~1/40 of the cloud's extent
+    const int drop = 14;
+    pc_query_key_kernel<<<(int)((m + 255) / 256), 256, 0, L.stream>>>(d_q, m, qstride, ix->d_bbox, drop, L.keys_a, L.vals_a);
+    ix->launches++;
+    PC_CHECK_LAUNCH(ix);
+    int which = rs_sort_pairs<uint32_t, 16>(L.keys_a, L.vals_a, L.keys_b, L.vals_b, m, 0, 16, L.tile_hist, L.digit_total, L.stream, &ix->launches);
+    PC_CHECK_LAUNCH(ix);
+    *perm = which ? L.vals_b : L.vals_a;
+    return PC_OK;
+}
+
+static bool pc_want_sort(const pc_index *ix, int flags, int64_t m)
+{
+    if (ix->n == 0) return false;
+    if (flags & PC_QUERY_SORTED) return true;
+    if (flags & PC_QUERY_UNSORTED) return false;
+    return m >= PC_SORT_MIN_BATCH;
+}
+
+enum pc_qkind { PC_Q_NEAREST, PC_Q_RADIUS };
+
+struct pc_qargs {
+    pc_qkind kind;
+    pc_radius_dev R;
+    int flags;
+};
+
+// run one device-resident batch on lane L
+static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float *d_q, int64_t m, int qstride,
+                        int32_t *d_idx, float *d_f)
+{
+    if (m == 0) return PC_OK;
+    const uint32_t *perm = nullptr;
+    const bool prof = ix->profile && &L == &ix->lane[0];
+    if (prof) PC_CUDA(ix, cudaEventRecord(L.t0, L.stream));
+    if (pc_want_sort(ix, A.flags, m)) {
+        int rc = pc_sort_queries(ix, L, d_q, m, qstride, &perm);
+        if (rc != PC_OK) return rc;
+    }
+    if (prof) PC_CUDA(ix, cudaEventRecord(L.t1, L.stream));
+    pc_tree T = pc_tree_of(ix);
+    int grid = (int)((m + PC_QUERY_THREADS - 1) / PC_QUERY_THREADS);
+    if (A.kind == PC_Q_NEAREST)
+        pc_nearest_kernel<<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, d_q, m, qstride, perm, d_idx, d_f);
+    else
+        pc_radius_kernel<<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, d_f, d_idx);
+    ix->launches++;
+    PC_CHECK_LAUNCH(ix);
+    if (prof) { PC_CUDA(ix, cudaEventRecord(L.t2, L.stream)); ix->profiled = true; }
+    return PC_OK;
+}
+
+extern "C" int pc_profile_enable(pc_index *ix, int on)
+{
+    if (!ix) return PC_EINVAL;
+    ix->profile = on != 0;
+    ix->profiled = false;
+    return PC_OK;
+}
+
+extern "C" int pc_profile_last_batch(pc_index *ix, float *order_ms, float *search_ms)
+{
+    if (!ix) return PC_EINVAL;
+    if (!ix->profiled) return pc_fail(ix, PC_EINVAL, "pc_profile_last_batch: no profiled PC_DEVICE batch yet");
+    PC_CUDA(ix, cudaSetDevice(ix->device));
+    pc_lane &L = ix->lane[0];
+    PC_CUDA(ix, cudaEventSynchronize(L.t2));
+    float a = 0.f, b = 0.f;
+    PC_CUDA(ix, cudaEventElapsedTime(&a, L.t0, L.t1));
+    PC_CUDA(ix, cudaEventElapsedTime(&b, L.t1, L.t2));
+    if (order_ms) *order_ms = a;
+    if (search_ms) *search_ms = b;
+    return PC_OK;
+}
+
+// PC_HOST: chunked pipeline over the lanes; PC_DEVICE: one batch on the handle's stream
+static int pc_query_dispatch(pc_index *ix, const pc_qargs &A, const float *q, int64_t m, int64_t q_stride, int space,
+                             int32_t *out_idx, float *out_f)
+{
+    PC_CUDA(ix, cudaSetDevice(ix->device));
+    if (m == 0) return PC_OK;
+    const int qs = (int)q_stride;
+    if (space == PC_DEVICE) return pc_run_batch(ix, ix->lane[0], A, q, m, qs, out_idx, out_f);
+
+    // order the side lanes after everything already queued on the handle's stream (e.g. an asynchronous build)
+    PC_CUDA(ix, cudaEventRecord(ix->ev_ready, ix->stream));
+    for (int l = 1; l < PC_PIPE_LANES; l++) PC_CUDA(ix, cudaStreamWaitEvent(ix->lane[l].stream, ix->ev_ready, 0));
+    const int64_t chunk = PC_HOST_CHUNK;
+    int li = 0;
+    for (int64_t off = 0; off < m; off += chunk, li = (li + 1) % PC_PIPE_LANES) {
+        pc_lane &L = ix->lane[li];
+        int64_t c = m - off < chunk ? m - off : chunk;
+        int rc;
+        if ((rc = pc_grow(ix, &L.d_q, &L.q_cap, c * qs, chunk * 4)) != PC_OK) return rc;
+        if (out_idx && (rc = pc_grow(ix, &L.d_i32, &L.i32_cap, c, chunk)) != PC_OK) return rc;
+        if (out_f && (rc = pc_grow(ix, &L.d_f32, &L.f32_cap, c, chunk)) != PC_OK) return rc;
+        PC_CUDA(ix, cudaMemcpyAsync(L.d_q, q + off * qs, (size_t)c * qs * sizeof(float), cudaMemcpyHostToDevice, L.stream));
+        rc = pc_run_batch(ix, L, A, L.d_q, c, qs, out_idx ? L.d_i32 : nullptr, out_f ? L.d_f32 : nullptr);
+        if (rc != PC_OK) return rc;
+        if (out_idx) PC_CUDA(ix, cudaMemcpyAsync(out_idx + off, L.d_i32, (size_t)c * sizeof(int32_t), cudaMemcpyDeviceToHost, L.stream));
+        if (out_f) PC_CUDA(ix, cudaMemcpyAsync(out_f + off, L.d_f32, (size_t)c * sizeof(float), cudaMemcpyDeviceToHost, L.stream));
+    }
+    for (int l = 0; l < PC_PIPE_LANES; l++) PC_CUDA(ix, cudaStreamSynchronize(ix->lane[l].stream));
+    return PC_OK;
+}
+
+static int pc_check_query_args(pc_index *ix, const char *fn, const float *q, int64_t m, int64_t q_stride, int space)
+{
+    if (!ix) return PC_EINVAL;
+    if (m < 0 || (m > 0 && !q) || (q_stride != 3 && q_stride != 4) || (space != PC_HOST && space != PC_DEVICE))
+        return pc_fail(ix, PC_EINVAL, "%s: bad argument (m=%lld stride=%lld space=%d)", fn, (long long)m, (long long)q_stride, space);
+    if (m > ((int64_t)1 << 32) - 1) return pc_fail(ix, PC_EINVAL, "%s: at most 2^32-1 queries per call", fn);
+    return PC_OK;
+}
+
+extern "C" int pc_nearest_batch(pc_index *ix, const float *q_xyz, int64_t m, int64_t q_stride, int space, int flags,
+                                int32_t *out_idx, float *out_d2)
+{
+    int rc = pc_check_query_args(ix, "pc_nearest_batch", q_xyz, m, q_stride, space);
+    if (rc != PC_OK) return rc;
+    pc_qargs A;
+    memset(&A, 0, sizeof A);
+    A.kind = PC_Q_NEAREST; A.flags = flags;
+    return pc_query_dispatch(ix, A, q_xyz, m, q_stride, space, out_idx, out_d2);
+}
+
+static int pc_make_radius_dev(pc_index *ix, const pc_radius_params *p, int flags, pc_radius_dev *R)
+{
+    if (!p || !(p->max_radius == p->max_radius) || !(p->search_margin == p->search_margin))
+        return pc_fail(ix, PC_EINVAL, "pc_radius_params: null or NaN");
+    R->search_margin = p->search_margin; R->max_radius = p->max_radius; R->sample_range = p->sample_range;
+    R->sx = p->start[0]; R->sy = p->start[1]; R->sz = p->start[2];
+    R->bounded = (flags & PC_RADIUS_FULL_NN) ? 0 : 1;
+    R->bound_thr = FLT_MAX;
+    if (R->bounded) {
+        // radius = min(sqrt(d2) - margin, max_radius): every d > max_radius + margin gives max_radius, so the search
+        // may stop there.  1e-6 relative head-room keeps the clamp decision exact in fp64.
+        double bound = (p->max_radius + p->search_margin) * (1.0 + 1e-6);
+        if (bound < 0.0) bound = 0.0;
+        double b2 = bound * bound * (1.0 + 1e-6);
+        float f = (float)b2;
+        f = nextafterf(f, INFINITY) * PC_THR_SLACK;
+        R->bound_thr = f < FLT_MAX ? f : FLT_MAX;
+    }
+    return PC_OK;
+}
+
+extern "C" int pc_radius_batch(pc_index *ix, const float *q_xyz, int64_t m, int64_t q_stride, int space, int flags,
+                               const pc_radius_params *params, float *out_radius, int32_t *out_idx)
+{
+    int rc = pc_check_query_args(ix, "pc_radius_batch", q_xyz, m, q_stride, space);
+    if (rc != PC_OK) return rc;
+    pc_qargs A;
+    memset(&A, 0, sizeof A);
+    A.kind = PC_Q_RADIUS; A.flags = flags;
+    if ((rc = pc_make_radius_dev(ix, params, flags, &A.R)) != PC_OK) return rc;
+    return pc_query_dispatch(ix, A, q_xyz, m, q_stride, space, out_idx, out_radius);
+}
+
+#include "range_host.inl"
+#include "clearance_host.inl"
+#include "comm_host.inl"

@@ -1,0 +1,184 @@
+// radix_sort.cuh -- hand-written stable LSD radix sort of (key, uint32 value) pairs, 8 bits per pass.
+//
+// Replaces the N sequential kd_insert3 calls of the reference (Utils/kdtree/src/kdtree.c:244-251):
+// ordering the cloud along a Morton curve IS the index construction.
+//
+// Per pass three kernels, no host synchronisation:
+//   rs_histogram : per-tile digit histograms (warp-private shared-memory counters)
+//   rs_scan_rows : exclusive scan of each digit's row of tile counts (one CTA per digit)
+//   rs_scatter   : stable rank of every element inside its tile (match_any ballots per warp round,
+//                  warp-level running counters, scan across warps) + global base -> scatter
+// Stability: a warp owns a contiguous slice of the tile and walks it in rounds of 32 consecutive
+// elements, so (warp, round, lane) order is the input order.
+#pragma once
+#include "common.cuh"
+
+#define RS_THREADS 256
+#define RS_WARPS (RS_THREADS / 32)
+#define RS_RADIX 256
+
+template <typename KeyT>
+__device__ __forceinline__ uint32_t rs_digit(KeyT k, int shift)
+{
+    return (uint32_t)(k >> shift) & (RS_RADIX - 1);
+}
+
+// tile_hist layout: [digit][tile] so that a digit's row is contiguous for the scan
+template <typename KeyT, int ITEMS>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_histogram(const KeyT *__restrict__ keys, int64_t n, int shift, uint32_t *__restrict__ tile_hist, int num_tiles)
+{
+    __shared__ uint32_t hist[RS_WARPS][RS_RADIX];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&hist[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * (RS_THREADS * ITEMS);
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        int64_t i = base + (int64_t)r * RS_THREADS + tid;
+        if (i < n) atomicAdd(&hist[warp][rs_digit(keys[i], shift)], 1u);
+    }
+    __syncthreads();
+    uint32_t s = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; w++) s += hist[w][tid];
+    tile_hist[(int64_t)tid * num_tiles + blockIdx.x] = s;
+}
+
+// One CTA per digit: in-place exclusive scan of tile_hist[digit][0..num_tiles), total -> digit_total[digit]
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scan_rows(uint32_t *__restrict__ tile_hist, int num_tiles, uint32_t *__restrict__ digit_total)
+{
+    __shared__ uint32_t warp_sum[RS_WARPS];
+    __shared__ uint32_t carry_s;
+    uint32_t *row = tile_hist + (int64_t)blockIdx.x * num_tiles;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < num_tiles; base += RS_THREADS) {
+        int i = base + tid;
+        uint32_t v = (i < num_tiles) ? row[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(PC_FULL_MASK, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        uint32_t woff = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) if (w < warp) woff += warp_sum[w];
+        uint32_t carry = carry_s;
+        if (i < num_tiles) row[i] = carry + woff + incl - v;
+        __syncthreads();
+        if (tid == RS_THREADS - 1) carry_s = carry + woff + incl;
+        __syncthreads();
+    }
+    if (tid == 0) digit_total[blockIdx.x] = carry_s;
+}
+
+template <typename KeyT, int ITEMS>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_scatter(const KeyT *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+           KeyT *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift,
+           const uint32_t *__restrict__ tile_prefix, int num_tiles, const uint32_t *__restrict__ digit_total)
+{
+    // counter[w][d]: first the running count of digit d seen by warp w, then its output base
+    __shared__ uint32_t counter[RS_WARPS][RS_RADIX + 1];
+    __shared__ uint32_t digit_base[RS_RADIX];
+    __shared__ uint32_t warp_sum[RS_WARPS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < RS_WARPS * (RS_RADIX + 1); i += RS_THREADS) (&counter[0][0])[i] = 0;
+
+    // exclusive scan of the 256 digit totals (every CTA repeats it: 256 values, cheaper than a launch)
+    {
+        uint32_t v = digit_total[tid], incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(PC_FULL_MASK, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        uint32_t woff = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) if (w < warp) woff += warp_sum[w];
+        digit_base[tid] = woff + incl - v;
+    }
+    __syncthreads();
+
+    const int64_t warp_base = (int64_t)blockIdx.x * (RS_THREADS * ITEMS) + (int64_t)warp * (32 * ITEMS);
+    KeyT key[ITEMS];
+    uint32_t val[ITEMS];
+    uint32_t rank[ITEMS];   // rank of the element among equal digits inside this warp's slice
+    uint32_t dig[ITEMS];
+    const uint32_t lt = pc_lanemask_lt();
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        int64_t i = warp_base + r * 32 + lane;
+        bool ok = i < n;
+        key[r] = ok ? keys_in[i] : (KeyT)0;
+        val[r] = ok ? vals_in[i] : 0u;
+        dig[r] = ok ? rs_digit(key[r], shift) : (uint32_t)RS_RADIX;   // bin 256 collects the out-of-range lanes
+    }
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        uint32_t peers = __match_any_sync(PC_FULL_MASK, dig[r]);
+        int leader = __ffs(peers) - 1;
+        uint32_t before = 0;
+        if (lane == leader) {
+            before = counter[warp][dig[r]];
+            counter[warp][dig[r]] = before + __popc(peers);
+        }
+        before = __shfl_sync(PC_FULL_MASK, before, leader);
+        rank[r] = before + __popc(peers & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+    // thread d turns the per-warp counts of digit d into output bases
+    {
+        uint32_t run = digit_base[tid] + tile_prefix[(int64_t)tid * num_tiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) {
+            uint32_t c = counter[w][tid];
+            counter[w][tid] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < ITEMS; r++) {
+        if (dig[r] < RS_RADIX) {
+            uint32_t pos = counter[warp][dig[r]] + rank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = val[r];
+        }
+    }
+}
+
+// Host-side driver.  Sorts n pairs on `stream`; the result ends in (keys_a, vals_a) when the number of
+// passes is even, otherwise in (keys_b, vals_b): the return value says which (0 = a, 1 = b).
+// tile_hist must hold RS_RADIX * num_tiles(n) uint32, digit_total RS_RADIX uint32.
+template <int ITEMS>
+static inline int rs_num_tiles(int64_t n) { return (int)((n + (int64_t)RS_THREADS * ITEMS - 1) / ((int64_t)RS_THREADS * ITEMS)); }
+
+template <typename KeyT, int ITEMS>
+static int rs_sort_pairs(KeyT *keys_a, uint32_t *vals_a, KeyT *keys_b, uint32_t *vals_b, int64_t n,
+                         int begin_bit, int end_bit, uint32_t *tile_hist, uint32_t *digit_total,
+                         cudaStream_t stream, int64_t *launches)
+{
+    if (n <= 0) return 0;
+    const int tiles = rs_num_tiles<ITEMS>(n);
+    int which = 0;
+    for (int shift = begin_bit; shift < end_bit; shift += 8) {
+        KeyT *kin = which ? keys_b : keys_a, *kout = which ? keys_a : keys_b;
+        uint32_t *vin = which ? vals_b : vals_a, *vout = which ? vals_a : vals_b;
+        rs_histogram<KeyT, ITEMS><<<tiles, RS_THREADS, 0, stream>>>(kin, n, shift, tile_hist, tiles);
+        rs_scan_rows<<<RS_RADIX, RS_THREADS, 0, stream>>>(tile_hist, tiles, digit_total);
+        rs_scatter<KeyT, ITEMS><<<tiles, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, n, shift, tile_hist, tiles, digit_total);
+        if (launches) *launches += 3;
+        which ^= 1;
+    }
+    return which;
+}

@@ -1,0 +1,196 @@
+"""GPU parity tests: libpcindex.so (through the C ABI) against the CPU oracle on the same seeded inputs,
+against the committed golden vectors of the unmodified reference, and -- at full BASELINE sizes --
+through size-independent properties."""
+import numpy as np
+import pytest
+
+import oracle
+from pointcloudtraj_b200 import (PC_QUERY_SORTED, PC_QUERY_UNSORTED, PC_RADIUS_BOUNDED, PC_RADIUS_FULL_NN,
+                                 PcRadiusParams, PointCloudIndex, synth)
+from parity import check_lowest_index_everywhere, check_nearest
+
+pytestmark = pytest.mark.gpu
+
+CLEAN_DEMO = dict(search_margin=0.25, max_radius=1.5, sample_range=30.0)     # clean_demo.launch:31-34
+SIMULATION = dict(search_margin=0.0, max_radius=5.0, sample_range=30.0)      # simulation.launch:24-27
+
+
+@pytest.fixture(scope="module")
+def ix():
+    h = PointCloudIndex(max_points=1 << 20, device=0)
+    yield h
+    h.close()
+
+
+def _oracle(pts, seed=0):
+    return oracle.KdOracle().build(pts, np.random.default_rng(seed).permutation(len(pts)))
+
+
+# ---- golden vectors of the unmodified reference ----------------------------------------------------
+@pytest.mark.parametrize("name", ["forest_lattice", "forest_jitter", "uniform"])
+def test_golden_nearest(ix, golden_dir, name):
+    g = np.load(f"{golden_dir}/{name}.npz")
+    ix.build(g["pts"])
+    for flags in (PC_QUERY_UNSORTED, PC_QUERY_SORTED):
+        idx, d2 = ix.nearest(g["q"], flags=flags)
+        check_nearest(g["pts"], g["q"], idx, d2, g["nn_idx"].astype(np.int64), g["nn_d2"])
+
+
+def test_known_answers(ix, golden_dir):
+    z = np.zeros((1, 3), np.float32)
+    # two equidistant points: lowest index (documented tie rule; the reference returns the first inserted)
+    ix.build(np.array([[1, 0, 0], [-1, 0, 0]], np.float32))
+    assert ix.nearest(z)[0].tolist() == [0]
+    ix.build(np.array([[-1, 0, 0], [1, 0, 0]], np.float32))
+    assert ix.nearest(z)[0].tolist() == [0]
+    # three duplicates -> index 0
+    ix.build(np.array([[2, 2, 2]] * 3, np.float32))
+    i, d = ix.nearest(np.array([[2.5, 2, 2]], np.float32))
+    assert i.tolist() == [0] and d.tolist() == [0.25]
+    # query coincident with a point
+    pts = synth.uniform_cloud(1000, seed=5)
+    ix.build(pts)
+    i, d = ix.nearest(pts[123:124])
+    assert i.tolist() == [123] and d.tolist() == [0.0]
+
+
+def test_empty_and_single(ix):
+    q = synth.rrt_queries(100, 5.0, seed=1)
+    ix.build(np.zeros((0, 3), np.float32))
+    assert ix.size == 0
+    i, d = ix.nearest(q)
+    assert (i == -1).all() and np.isinf(d).all()                                  # kd_nearest3 -> NULL
+    P = PcRadiusParams.make(**CLEAN_DEMO)
+    r, i = ix.radius(q, P, want_idx=True)
+    assert (r == np.float32(1.5 - 0.25)).all() and (i == -1).all()                # corridor_finder.cpp:118-120
+    i, d = ix.nearest(np.zeros((0, 3), np.float32))
+    assert i.shape == (0,)
+    one = np.array([[0.5, -0.25, 1.0]], np.float32)
+    ix.build(one)
+    i, d = ix.nearest(q)
+    assert (i == 0).all()
+    ref = oracle.pair_d2(one, q, np.zeros(len(q), np.int64))
+    assert (d == ref.astype(np.float32)).all()
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 8, 9, 15, 16, 17, 63, 64, 65, 255, 257, 1000, 4097])
+def test_small_sizes_every_tree_shape(ix, n):
+    pts = synth.uniform_cloud(n, half=4.0, seed=n)
+    q = synth.rrt_queries(512, 5.0, seed=n + 1, z=(-1.0, 9.0))
+    ix.build(pts)
+    idx, d2 = ix.nearest(q)
+    check_lowest_index_everywhere(pts, q, idx)
+    ridx, rd2 = _oracle(pts).nearest(q)
+    check_nearest(pts, q, idx, d2, ridx, rd2)
+
+
+# ---- seeded clouds vs the oracle (C1-sized) ----------------------------------------------------------
+@pytest.mark.parametrize("variant,lat", [("L", 0.5), ("J", 0.0)])
+def test_forest_200k(ix, variant, lat):
+    pts, half = synth.forest_cloud(200_000, seed=6, variant=variant, return_half=True)
+    q = synth.rrt_queries(100_000, half, seed=0, lattice_frac=lat)
+    ix.build(pts)
+    idx, d2 = ix.nearest(q)
+    ridx, rd2 = _oracle(pts).nearest(q)
+    n_tied = check_nearest(pts, q, idx, d2, ridx, rd2)
+    if variant == "J":
+        assert n_tied == 0 and (idx == ridx).all()       # tie-free: bit-exact indices
+    idx2, d22 = ix.nearest(q, flags=PC_QUERY_UNSORTED)
+    assert (idx2 == idx).all() and (d22 == d2).all()     # batch ordering does not change results
+
+
+def test_uniform_cloud_and_strides(ix):
+    pts = synth.uniform_cloud(150_000, half=20.0, seed=9)
+    q = synth.rrt_queries(50_000, 22.0, seed=10, z=(-1, 9))
+    ix.build(pts)
+    idx, d2 = ix.nearest(q)
+    ridx, rd2 = _oracle(pts).nearest(q)
+    check_nearest(pts, q, idx, d2, ridx, rd2)
+    # pcl::PointXYZ layout: x, y, z, pad at 16-byte stride, for both cloud and queries
+    pts4 = np.concatenate([pts, np.full((len(pts), 1), np.nan, np.float32)], 1)
+    q4 = np.concatenate([q, np.ones((len(q), 1), np.float32)], 1)
+    ix.build(pts4)
+    idx4, d24 = ix.nearest(q4)
+    assert (idx4 == idx).all() and (d24 == d2).all()
+
+
+@pytest.mark.parametrize("params,seed", [(CLEAN_DEMO, 0), (SIMULATION, 1)])
+def test_radius_batch(ix, params, seed):
+    pts, half = synth.forest_cloud(200_000, seed=6, variant="J", return_half=True)
+    q = synth.rrt_queries(60_000, half * 2.5, seed=seed)       # beyond the map: exercises the sensing-range early-out
+    start = (1.0, -2.0, 2.0)
+    ix.build(pts)
+    P = PcRadiusParams.make(start=start, **params)
+    r_ref, i_ref = _oracle(pts).radius_batch(oracle.RadiusParams.make(start=start, **params), q)
+    r32 = r_ref.astype(np.float32)
+    # unbounded search: the index is the true nearest point wherever a query was issued
+    r, i = ix.radius(q, P, flags=PC_RADIUS_FULL_NN, want_idx=True)
+    assert (r == r32).all()
+    assert (i == i_ref).all()
+    # bounded search (default): same radii bit for bit; index only where the radius is not clamped
+    r, i = ix.radius(q, P, flags=PC_RADIUS_BOUNDED, want_idx=True)
+    assert (r == r32).all()
+    clamped = ~(r_ref < params["max_radius"])
+    assert (i[clamped] == -1).all() and (i[~clamped] == i_ref[~clamped]).all()
+    assert (r_ref == params["max_radius"] - params["search_margin"]).any() and clamped.any() and (r_ref < 0).any()
+    col = ix.check_traj_pt_col(q, P)
+    assert (col == (r_ref < 0)).all()                            # checkTrajPtCol, corridor_finder.cpp:412-416
+
+
+def test_device_pointers_match_host(ix):
+    torch = pytest.importorskip("torch")
+    pts, half = synth.forest_cloud(100_000, seed=3, variant="J", return_half=True)
+    q = synth.rrt_queries(70_000, half, seed=4)
+    ix.build(pts)
+    idx_h, d2_h = ix.nearest(q)
+    tp = torch.from_numpy(pts).cuda()
+    tq = torch.from_numpy(q).cuda()
+    h2 = PointCloudIndex(max_points=0, device=0, stream=torch.cuda.current_stream().cuda_stream)
+    h2.build(tp)
+    idx_d, d2_d = h2.nearest(tq)
+    P = PcRadiusParams.make(**CLEAN_DEMO)
+    r_d = h2.radius(tq, P)
+    torch.cuda.synchronize()
+    assert (idx_d.cpu().numpy() == idx_h).all() and (d2_d.cpu().numpy() == d2_h).all()
+    assert (r_d.cpu().numpy() == ix.radius(q, P)).all()
+    h2.close()
+
+
+def test_rebuild_reuses_handle(ix):
+    # LiDAR-stream pattern (C3): the same handle is rebuilt every frame
+    for frame in range(4):
+        pts = synth.uniform_cloud(30_000 + 1000 * frame, half=10.0, seed=100 + frame)
+        q = synth.rrt_queries(5000, 10.0, seed=frame)
+        ix.build(pts)
+        assert ix.size == len(pts)
+        idx, _ = ix.nearest(q)
+        check_lowest_index_everywhere(pts, q, idx)
+
+
+# ---- full-size properties (C2: 1M-point map) ---------------------------------------------------------
+def test_one_million_points_properties(ix):
+    pts, half = synth.forest_cloud(1_000_000, seed=1, variant="J", return_half=True)
+    ix.build(pts)
+    assert ix.size == 1_000_000
+    # (1) every point is its own nearest neighbour at distance 0 (covers every leaf, checks the permutation)
+    sel = np.random.default_rng(0).permutation(len(pts))[:300_000]
+    idx, d2 = ix.nearest(pts[sel])
+    assert (d2 == 0).all()
+    same = idx == sel
+    if not same.all():      # exact duplicates in the cloud: lowest index wins
+        assert (pts[idx[~same]] == pts[sel[~same]]).all() and (idx[~same] < sel[~same]).all()
+    # (2) oracle on a sample, (3) batch order independence, (4) radius == epilogue of nearest
+    q = synth.rrt_queries(200_000, half, seed=7)
+    idx, d2 = ix.nearest(q)
+    sub = slice(0, 20_000)
+    ridx, rd2 = _oracle(pts).nearest(q[sub])
+    check_nearest(pts, q[sub], idx[sub], d2[sub], ridx, rd2)
+    idx_u, d2_u = ix.nearest(q, flags=PC_QUERY_UNSORTED)
+    assert (idx_u == idx).all() and (d2_u == d2).all()
+    P = PcRadiusParams.make(start=(0, 0, 2), **CLEAN_DEMO)
+    r = ix.radius(q, P)
+    exact = oracle.pair_d2(pts, q, idx.astype(np.int64))
+    expect = np.minimum(np.sqrt(exact) - 0.25, 1.5)
+    far = np.sqrt(((q.astype(np.float64) - np.array([0, 0, 2.0])) ** 2).sum(1)) > 31.5
+    expect[far] = 1.25
+    assert (r == expect.astype(np.float32)).all()
