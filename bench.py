@@ -170,6 +170,8 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one explicit non-default stream for everything: the library's kernels, torch's copies and the timing events
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)

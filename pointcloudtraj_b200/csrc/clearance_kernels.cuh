@@ -1,3 +1,131 @@
-// clearance_kernels.cuh -- Bezier sampling fused with the nearest-obstacle query (checkSafeTrajectory).
+// clearance_kernels.cuh -- trajectory clearance: Bezier sampling fused with the nearest-obstacle query and a
+// per-trajectory reduction.  One CTA per trajectory.
+//
+// Replaces checkSafeTrajectory (Planner/src/sim_planning_demo.cpp:729-781), getPosFromBezier (:715-727) and
+// safeRegionRrtStar::checkTrajPtCol (Planner/src/corridor_finder.cpp:412-416).
+//
+// The reference's time walk accumulates `t += 0.02` / `t_accu += 0.02` in doubles, so sample times are the
+// result of REPEATED addition (not k * dt).  To reproduce them bit for bit, thread 0 of the CTA runs the walk
+// sequentially and publishes a schedule of (segment, t) pairs in shared memory, PC_CLR_CHUNK samples at a time;
+// all threads then evaluate the samples of the chunk in parallel.
+// Powers u^j are built by multiplication (p[j] = p[j/2] * p[j - j/2], <= 2 ulp from libm's pow for j <= 12); the
+// position is cast to float32 exactly where radiusSearch does (corridor_finder.cpp:122-125), which absorbs that
+// difference in all but ~1e-8 of the coordinates (DESIGN.md "Clearance tolerance").
 #pragma once
 #include "query_kernels.cuh"
+
+#define PC_CLR_THREADS 128
+#define PC_CLR_CHUNK 512
+#define PC_MAX_ORDER 12
+
+__constant__ double pc_binom[PC_MAX_ORDER + 1][PC_MAX_ORDER + 1];
+
+struct pc_traj_dev { int32_t first_seg, num_seg; double t_now; };
+
+__device__ __forceinline__ void pc_power_table(double u, int n, double *p)
+{
+    p[0] = 1.0;
+    if (n >= 1) p[1] = u;
+    for (int j = 2; j <= n; j++) p[j] = __dmul_rn(p[j >> 1], p[j - (j >> 1)]);
+}
+
+// p = T * sum_j C(n,j) c_j u^j (1-u)^(n-j) per axis, term evaluated left to right, accumulated from 0
+__device__ __forceinline__ void pc_bezier_pos(const double *__restrict__ c, int n, double u, double T, double out[3])
+{
+    double pu[PC_MAX_ORDER + 1], pv[PC_MAX_ORDER + 1];
+    pc_power_table(u, n, pu);
+    pc_power_table(__dsub_rn(1.0, u), n, pv);
+    const int nc = n + 1;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        double acc = 0.0;
+        for (int j = 0; j <= n; j++) {
+            double term = __dmul_rn(__dmul_rn(__dmul_rn(pc_binom[n][j], c[a * nc + j]), pu[j]), pv[n - j]);
+            acc = __dadd_rn(acc, term);
+        }
+        out[a] = __dmul_rn(acc, T);
+    }
+}
+
+__global__ void __launch_bounds__(PC_CLR_THREADS)
+pc_clearance_kernel(pc_tree T, pc_radius_dev R, const pc_traj_dev *__restrict__ traj, int64_t n_traj,
+                    const int32_t *__restrict__ seg_order, const double *__restrict__ seg_T,
+                    const int64_t *__restrict__ seg_coef_off, const double *__restrict__ coef,
+                    double dt, double horizon,
+                    int32_t *__restrict__ out_first_hit, float *__restrict__ out_min_radius, int32_t *__restrict__ out_n_samples)
+{
+    __shared__ double s_t[PC_CLR_CHUNK];
+    __shared__ int32_t s_seg[PC_CLR_CHUNK];
+    __shared__ int s_count, s_done;
+    __shared__ int s_first_hit;
+    __shared__ double s_warp_min[PC_CLR_THREADS / 32];
+
+    const int64_t tr = blockIdx.x;
+    if (tr >= n_traj) return;
+    const pc_traj_dev tj = traj[tr];
+    const int32_t seg0 = tj.first_seg, nseg = tj.num_seg;
+
+    // walk state (thread 0 only), sim_planning_demo.cpp:735-749
+    int i = 0;
+    double tt = 0.0, t_accu = 0.0;
+    if (threadIdx.x == 0) {
+        double t_s = tj.t_now > 0.0 ? tj.t_now : 0.0;
+        for (i = 0; i < nseg; ++i) {
+            if (t_s > seg_T[seg0 + i] && i + 1 < nseg) t_s = __dsub_rn(t_s, seg_T[seg0 + i]);
+            else break;
+        }
+        tt = t_s;
+        s_first_hit = 0x7fffffff;
+    }
+    double my_min = INFINITY;
+    int64_t chunk_base = 0;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            int cnt = 0;
+            while (i < nseg && cnt < PC_CLR_CHUNK) {
+                const double Ti = seg_T[seg0 + i];
+                if (!(tt < Ti)) { i++; tt = 0.0; continue; }
+                t_accu = __dadd_rn(t_accu, dt);
+                if (t_accu > horizon) { i++; tt = 0.0; continue; }
+                s_t[cnt] = tt; s_seg[cnt] = seg0 + i; cnt++;
+                tt = __dadd_rn(tt, dt);
+            }
+            s_count = cnt;
+            s_done = (i >= nseg);
+        }
+        __syncthreads();
+        const int cnt = s_count;
+        for (int k = threadIdx.x; k < cnt; k += PC_CLR_THREADS) {
+            const int32_t sg = s_seg[k];
+            const double Ti = seg_T[sg];
+            double pos[3];
+            pc_bezier_pos(coef + seg_coef_off[sg], seg_order[sg], __ddiv_rn(s_t[k], Ti), Ti, pos);
+            double radius;
+            if (T.n_points == 0 || pc_radius_early_out(pos[0], pos[1], pos[2], R)) {
+                radius = __dsub_rn(R.max_radius, R.search_margin);
+            } else {
+                const float qx = (float)pos[0], qy = (float)pos[1], qz = (float)pos[2];
+                pc_best b; b.d2 = INFINITY; b.idx = -1; b.thr = R.bound_thr;
+                pc_nearest_traverse(T, qx, qy, qz, b);
+                radius = pc_radius_epilogue(b, R);
+            }
+            my_min = fmin(my_min, radius);
+            if (radius < 0.0) atomicMin(&s_first_hit, (int)(chunk_base + k));
+        }
+        chunk_base += cnt;
+        __syncthreads();
+        if (s_done) break;
+    }
+    // block reduction of the minimum radius
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_min = fmin(my_min, __shfl_xor_sync(PC_FULL_MASK, my_min, o));
+    if ((threadIdx.x & 31) == 0) s_warp_min[threadIdx.x >> 5] = my_min;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double mn = s_warp_min[0];
+        for (int w = 1; w < PC_CLR_THREADS / 32; w++) mn = fmin(mn, s_warp_min[w]);
+        if (out_min_radius) out_min_radius[tr] = (float)mn;
+        if (out_first_hit) out_first_hit[tr] = s_first_hit == 0x7fffffff ? -1 : s_first_hit;
+        if (out_n_samples) out_n_samples[tr] = (int32_t)chunk_base;
+    }
+}

@@ -343,7 +343,9 @@ extern "C" int pc_index_build(pc_index *ix, const float *xyz, int64_t n, int64_t
     int64_t cnt = n_leaves;
     for (int lvl0 = 0; lvl0 < top;) {
         int nl = top - lvl0 < PC_UP_LEVELS ? top - lvl0 : PC_UP_LEVELS;
-        int grid = (int)((cnt + 2 + 2 * PC_UP_THREADS - 1) / (2 * PC_UP_THREADS));
+        // one CTA more than the children need: the empty pad node next to the last real node of EVERY produced
+        // level must be written (index cnt_s of level s lives in CTA (cnt_s << s) / 256 <= (cnt + 255) / 256)
+        int grid = (int)((cnt + 2 * PC_UP_THREADS - 1) / (2 * PC_UP_THREADS)) + 1;
         pc_upper_kernel<<<grid, PC_UP_THREADS, 0, st>>>(ix->nodes, P, lvl0, cnt, nl);
         ix->launches++;
         PC_CHECK_LAUNCH(ix);

@@ -1,7 +1,91 @@
+// range_host.inl -- host side of pc_range_batch (included by pc_index.cu).
+
+static int pc_scratch(pc_index *ix, int64_t bytes, void **out)
+{
+    if (bytes > ix->scratch_cap) {
+        if (ix->scratch) { PC_CUDA(ix, cudaFree(ix->scratch)); ix->scratch = nullptr; ix->scratch_cap = 0; }
+        int64_t c = bytes + bytes / 4 + 4096;
+        PC_CUDA(ix, cudaMalloc(&ix->scratch, (size_t)c));
+        ix->scratch_cap = c;
+    }
+    *out = ix->scratch;
+    return PC_OK;
+}
+
+static inline int64_t pc_align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
 extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64_t q_stride, int space,
                               const double *range, int range_is_scalar,
                               int64_t *out_offsets, int32_t *out_idx, int64_t cap)
 {
-    (void)q_xyz; (void)m; (void)q_stride; (void)space; (void)range; (void)range_is_scalar; (void)out_offsets; (void)out_idx; (void)cap;
-    return pc_fail(ix, PC_ENOTIMPL, "pc_range_batch: not implemented yet");
+    int rc = pc_check_query_args(ix, "pc_range_batch", q_xyz, m, q_stride, space);
+    if (rc != PC_OK) return rc;
+    if (!out_offsets || (m > 0 && !range) || cap < 0 || (cap > 0 && !out_idx))
+        return pc_fail(ix, PC_EINVAL, "pc_range_batch: bad argument");
+    PC_CUDA(ix, cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    const int qs = (int)q_stride;
+    const int64_t n_range = range_is_scalar ? 1 : m;
+    const int64_t n_tiles = (m + PC_SCAN_TILE - 1) / PC_SCAN_TILE;
+
+    // device scratch: [queries | ranges | offsets] (PC_HOST only) + counts + tile sums
+    const int64_t b_q = space == PC_HOST ? pc_align_up(m * qs * (int64_t)sizeof(float), 256) : 0;
+    const int64_t b_r = space == PC_HOST ? pc_align_up(n_range * (int64_t)sizeof(double), 256) : 0;
+    const int64_t b_off = space == PC_HOST ? pc_align_up((m + 1) * (int64_t)sizeof(int64_t), 256) : 0;
+    const int64_t b_cnt = pc_align_up((m + 1) * (int64_t)sizeof(int64_t), 256);
+    const int64_t b_tile = pc_align_up((n_tiles + 1) * (int64_t)sizeof(int64_t), 256);
+    void *base = nullptr;
+    if ((rc = pc_scratch(ix, b_q + b_r + b_off + b_cnt + b_tile, &base)) != PC_OK) return rc;
+    char *p = (char *)base;
+    const float *d_q = q_xyz; const double *d_r = range; int64_t *d_off = out_offsets;
+    if (space == PC_HOST) {
+        d_q = (const float *)p; p += b_q;
+        d_r = (const double *)p; p += b_r;
+        d_off = (int64_t *)p; p += b_off;
+        if (m > 0) {
+            PC_CUDA(ix, cudaMemcpyAsync((void *)d_q, q_xyz, (size_t)m * qs * sizeof(float), cudaMemcpyHostToDevice, st));
+            PC_CUDA(ix, cudaMemcpyAsync((void *)d_r, range, (size_t)n_range * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+    }
+    int64_t *d_cnt = (int64_t *)p; p += b_cnt;
+    int64_t *d_tile = (int64_t *)p;
+
+    int64_t total = 0;
+    if (m == 0) {
+        if (space == PC_HOST) out_offsets[0] = 0;
+        else PC_CUDA(ix, cudaMemsetAsync(out_offsets, 0, sizeof(int64_t), st));
+        return PC_OK;
+    }
+    pc_tree T = pc_tree_of(ix);
+    const int grid = (int)((m + PC_QUERY_THREADS - 1) / PC_QUERY_THREADS);
+    pc_range_count_kernel<<<grid, PC_QUERY_THREADS, 0, st>>>(T, d_q, m, qs, d_r, range_is_scalar ? 1 : 0, d_cnt);
+    pc_scan_tile_sums<<<(int)n_tiles, PC_SCAN_THREADS, 0, st>>>(d_cnt, m, d_tile);
+    pc_scan_tile_offsets<<<1, PC_SCAN_THREADS, 0, st>>>(d_tile, n_tiles);
+    pc_scan_write_offsets<<<(int)n_tiles, PC_SCAN_THREADS, 0, st>>>(d_cnt, m, d_tile, d_off);
+    ix->launches += 4;
+    PC_CHECK_LAUNCH(ix);
+    // the total decides whether the lists fit: one 8-byte read-back
+    PC_CUDA(ix, cudaMemcpyAsync(&total, d_off + m, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    if (space == PC_HOST)
+        PC_CUDA(ix, cudaMemcpyAsync(out_offsets, d_off, (size_t)(m + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    PC_CUDA(ix, cudaStreamSynchronize(st));
+    if (!out_idx && cap == 0) return PC_OK;              // offsets only
+    if (total > cap) return pc_fail(ix, PC_ECAP, "pc_range_batch: %lld hits exceed cap %lld", (long long)total, (long long)cap);
+    if (total == 0) return PC_OK;
+
+    int32_t *d_out = out_idx;
+    if (space == PC_HOST) {
+        // the lists are staged in the (idle) lane-0 int32 buffer
+        pc_lane &L = ix->lane[0];
+        if ((rc = pc_grow(ix, &L.d_i32, &L.i32_cap, total)) != PC_OK) return rc;
+        d_out = L.d_i32;
+    }
+    pc_range_fill_kernel<<<grid, PC_QUERY_THREADS, 0, st>>>(T, d_q, m, qs, d_r, range_is_scalar ? 1 : 0, d_off, d_out);
+    ix->launches++;
+    PC_CHECK_LAUNCH(ix);
+    if (space == PC_HOST) {
+        PC_CUDA(ix, cudaMemcpyAsync(out_idx, d_out, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        PC_CUDA(ix, cudaStreamSynchronize(st));
+    }
+    return PC_OK;
 }

@@ -1,3 +1,195 @@
-// range_kernels.cuh -- fixed-radius range queries (kd_nearest_range3).
+// range_kernels.cuh -- fixed-radius range queries: all points with d2 <= range^2.
+//
+// Replaces find_nearest / kd_nearest_range3 (Utils/kdtree/src/kdtree.c:262-293,595-602) and the kd_res_*
+// iteration (kdtree.c:613-650).  The hit test is the reference's inclusive `dist_sq <= SQ(range)` (kdtree.c:273)
+// evaluated in fp64 in its operation order; unlike the reference the far side of a split is never skipped, so a
+// point at exactly `range` is always reported (the reference misses it from one side, kdtree.c:283 -- SURVEY 8c-5).
+// Two passes over the same traversal: count, (scan on the device), fill; every list is then sorted by original
+// index so the output is canonical.
 #pragma once
 #include "query_kernels.cuh"
+
+template <bool FILL>
+__device__ __forceinline__ void pc_range_leaf(const float4 *__restrict__ pts, int64_t first_slot, int64_t n_points,
+                                              float qx, float qy, float qz, double qxd, double qyd, double qzd,
+                                              float thr, double r2, int32_t *__restrict__ out, int64_t &count)
+{
+    float4 p[PC_LEAF];
+#pragma unroll
+    for (int i = 0; i < PC_LEAF; i++) p[i] = __ldg(pts + i);
+#pragma unroll
+    for (int i = 0; i < PC_LEAF; i++) {
+        float dx = p[i].x - qx, dy = p[i].y - qy, dz = p[i].z - qz;
+        float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (d <= thr && first_slot + i < n_points) {           // the tail of the last leaf repeats the last point
+            double e = pc_exact_d2(p[i].x, p[i].y, p[i].z, qxd, qyd, qzd);
+            if (e <= r2) {
+                if (FILL) out[count] = __float_as_int(p[i].w);
+                count++;
+            }
+        }
+    }
+}
+
+template <bool FILL>
+__device__ __forceinline__ int64_t pc_range_traverse(const pc_tree &T, float qx, float qy, float qz, double range,
+                                                     int32_t *__restrict__ out)
+{
+    const double qxd = (double)qx, qyd = (double)qy, qzd = (double)qz;
+    const double r2 = __dmul_rn(range, range);
+    if (!(r2 == r2)) return 0;   // NaN range
+    const float thr = fminf(__fmul_ru(__double2float_ru(r2), PC_THR_SLACK), FLT_MAX);
+    uint32_t stack_node[PC_STACK];
+    int sp = 0;
+    uint32_t node = 1;
+    int64_t count = 0;
+    for (;;) {
+        const float4 *pair = T.nodes + 4ull * node;
+        const float4 lo0 = __ldg(pair), hi0 = __ldg(pair + 1), lo1 = __ldg(pair + 2), hi1 = __ldg(pair + 3);
+        const bool in0 = pc_box_d2(lo0, hi0, qx, qy, qz) <= thr;
+        const bool in1 = pc_box_d2(lo1, hi1, qx, qy, qz) <= thr;
+        const uint32_t c0 = 2u * node;
+        bool descended = false;
+        if (c0 >= T.P) {
+            if (in0) pc_range_leaf<FILL>(T.points + (size_t)(c0 - T.P) * PC_LEAF, (int64_t)(c0 - T.P) * PC_LEAF, T.n_points,
+                                         qx, qy, qz, qxd, qyd, qzd, thr, r2, out, count);
+            if (in1) pc_range_leaf<FILL>(T.points + (size_t)(c0 + 1 - T.P) * PC_LEAF, (int64_t)(c0 + 1 - T.P) * PC_LEAF, T.n_points,
+                                         qx, qy, qz, qxd, qyd, qzd, thr, r2, out, count);
+        } else {
+            if (in0 && in1) { stack_node[sp++] = c0 + 1; node = c0; descended = true; }
+            else if (in0) { node = c0; descended = true; }
+            else if (in1) { node = c0 + 1; descended = true; }
+        }
+        if (descended) continue;
+        if (sp == 0) break;
+        node = stack_node[--sp];
+    }
+    return count;
+}
+
+__global__ void __launch_bounds__(PC_QUERY_THREADS)
+pc_range_count_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstride,
+                      const double *__restrict__ range, int range_is_scalar, int64_t *__restrict__ counts)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const float *qq = q + k * qstride;
+    int64_t c = 0;
+    if (T.n_points > 0) c = pc_range_traverse<false>(T, qq[0], qq[1], qq[2], range[range_is_scalar ? 0 : k], nullptr);
+    counts[k] = c;
+}
+
+// in-place heap sort of one query's list (ascending original index); lists are short (tens to hundreds)
+__device__ __forceinline__ void pc_sort_list(int32_t *__restrict__ a, int64_t n)
+{
+    if (n < 2) return;
+    for (int64_t start = n / 2 - 1; start >= 0; start--) {
+        int64_t root = start;
+        for (;;) {
+            int64_t child = 2 * root + 1;
+            if (child >= n) break;
+            if (child + 1 < n && a[child] < a[child + 1]) child++;
+            if (a[root] >= a[child]) break;
+            int32_t t = a[root]; a[root] = a[child]; a[child] = t;
+            root = child;
+        }
+    }
+    for (int64_t end = n - 1; end > 0; end--) {
+        int32_t t = a[0]; a[0] = a[end]; a[end] = t;
+        int64_t root = 0;
+        for (;;) {
+            int64_t child = 2 * root + 1;
+            if (child >= end) break;
+            if (child + 1 < end && a[child] < a[child + 1]) child++;
+            if (a[root] >= a[child]) break;
+            int32_t u = a[root]; a[root] = a[child]; a[child] = u;
+            root = child;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PC_QUERY_THREADS)
+pc_range_fill_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstride,
+                     const double *__restrict__ range, int range_is_scalar,
+                     const int64_t *__restrict__ offsets, int32_t *__restrict__ out_idx)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= m) return;
+    const int64_t begin = offsets[k], want = offsets[k + 1] - begin;
+    if (want == 0 || T.n_points == 0) return;
+    const float *qq = q + k * qstride;
+    pc_range_traverse<true>(T, qq[0], qq[1], qq[2], range[range_is_scalar ? 0 : k], out_idx + begin);
+    pc_sort_list(out_idx + begin, want);
+}
+
+// ---- exclusive scan of int64 counts into offsets[m + 1] (three small kernels) ---------------------------
+#define PC_SCAN_THREADS 256
+#define PC_SCAN_ITEMS 8
+#define PC_SCAN_TILE (PC_SCAN_THREADS * PC_SCAN_ITEMS)
+
+__device__ __forceinline__ int64_t pc_block_exclusive_scan(int64_t v, int64_t *total)
+{
+    __shared__ int64_t warp_sum[PC_SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int64_t t = __shfl_up_sync(PC_FULL_MASK, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    int64_t woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < PC_SCAN_THREADS / 32; w++) { if (w < warp) woff += warp_sum[w]; tot += warp_sum[w]; }
+    if (total) *total = tot;
+    return woff + incl - v;
+}
+
+__global__ void __launch_bounds__(PC_SCAN_THREADS)
+pc_scan_tile_sums(const int64_t *__restrict__ counts, int64_t m, int64_t *__restrict__ tile_sum)
+{
+    const int64_t base = (int64_t)blockIdx.x * PC_SCAN_TILE + (int64_t)threadIdx.x * PC_SCAN_ITEMS;
+    int64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < PC_SCAN_ITEMS; i++) if (base + i < m) s += counts[base + i];
+    int64_t tot;
+    pc_block_exclusive_scan(s, &tot);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(PC_SCAN_THREADS)
+pc_scan_tile_offsets(int64_t *__restrict__ tile_sum, int64_t n_tiles)
+{
+    __shared__ int64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n_tiles; base += PC_SCAN_THREADS) {
+        int64_t i = base + threadIdx.x;
+        int64_t v = i < n_tiles ? tile_sum[i] : 0, tot;
+        int64_t ex = pc_block_exclusive_scan(v, &tot);
+        int64_t carry = carry_s;
+        if (i < n_tiles) tile_sum[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + tot;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(PC_SCAN_THREADS)
+pc_scan_write_offsets(const int64_t *__restrict__ counts, int64_t m, const int64_t *__restrict__ tile_off,
+                      int64_t *__restrict__ offsets)
+{
+    const int64_t base = (int64_t)blockIdx.x * PC_SCAN_TILE + (int64_t)threadIdx.x * PC_SCAN_ITEMS;
+    int64_t c[PC_SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int i = 0; i < PC_SCAN_ITEMS; i++) { c[i] = base + i < m ? counts[base + i] : 0; s += c[i]; }
+    int64_t run = tile_off[blockIdx.x] + pc_block_exclusive_scan(s, nullptr);
+#pragma unroll
+    for (int i = 0; i < PC_SCAN_ITEMS; i++) {
+        if (base + i < m) offsets[base + i] = run;
+        run += c[i];
+        if (base + i == m - 1) offsets[m] = run;
+    }
+}

@@ -28,6 +28,8 @@ class PointCloudIndex:
         ``torch.cuda.current_stream().cuda_stream`` to order the calls with torch work."""
         self._L = L.load()
         h = C.c_void_p()
+        if stream is not None and int(stream) == 0:
+            stream = 1      # cudaStreamLegacy: NULL means "create a private stream" in the C ABI
         rc = self._L.pc_index_create(C.byref(h), int(device), int(max_points), C.c_void_p(stream or 0))
         if rc != L.PC_OK:
             raise L.PcError(rc, self._L.pc_last_error(None).decode())
