@@ -303,7 +303,7 @@ def run_b200(args):
                 "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(args),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "pc_radius_kernel", "kernel_ms": k_ms,
+                             "traffic": None, "kernel": "pc_query_packet_kernel<RADIUS>", "kernel_ms": k_ms,
                              "batch_order_ms": float(np.mean(order_ms)),
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                              "algorithmic_bytes_per_query": BYTES_PER_QUERY},

@@ -84,9 +84,9 @@ typedef struct pc_traj {
 /* device-side layout of a built index (for inspection and for replication across GPUs) */
 typedef struct pc_index_view {
     int64_t n_points;      /* points in the cloud                                           */
-    int64_t n_leaves;      /* ceil(n_points / 8)                                            */
+    int64_t n_leaves;      /* ceil(n_points / 2)                                            */
     int64_t leaf_base;     /* P: power of two >= max(2, n_leaves); node ids are [1, 2P)      */
-    const void *points;    /* float4[8 * n_leaves]: x, y, z, original index (int bits)      */
+    const void *points;    /* float4[2 * n_leaves]: x, y, z, original index (int bits); = nodes + 4P */
     const void *nodes;     /* float4[4 * P]: node i -> lo = nodes[2i], hi = nodes[2i+1]      */
     float bbox_lo[3], bbox_hi[3];
 } pc_index_view;

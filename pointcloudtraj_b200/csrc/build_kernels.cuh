@@ -1,12 +1,13 @@
 // build_kernels.cuh -- index construction kernels (bbox, Morton keys, leaf gather, bounding-box tree).
 //
-// Index layout in HBM (all float4, 16-byte aligned, see DESIGN.md "Data layout"):
-//   points[8 * n_leaves] : the cloud in Morton order, (x, y, z, original index as int bits); the tail of the
-//                          last leaf repeats the last real point so leaf scans need no bounds check
-//   nodes[4 * P]         : implicit complete binary tree in heap numbering over P = 2^k >= n_leaves leaf
-//                          slots; node i owns nodes[2i] = box min (xyz), nodes[2i+1] = box max (xyz);
-//                          children 2i, 2i+1 are adjacent (one aligned 64-byte pair); leaf j is node P + j;
-//                          unused slots hold the empty box (min = +inf, max = -inf)
+// Index layout in HBM: ONE float4 array, P = 2^k >= max(2, ceil(n / 2)) leaf slots, heap numbering (root = node 1,
+// children of i are 2i and 2i+1, leaf j is node P + j):
+//   boxes  tree[0 .. 4P)  : node i's box is tree[2i] = min (xyz), tree[2i+1] = max (xyz); the boxes of the two children
+//                           of i are therefore the aligned 64-byte record tree[4i .. 4i+3]
+//   points tree[4P .. 6P) : leaf j holds points[2j], points[2j+1] in Morton order, (x, y, z, original index as int
+//                           bits); when n is odd the last slot repeats the last real point
+// A traversal step loads the record of the node it visits: a box pair (64 B) or a leaf's two points (32 B).
+// Unused box slots hold the empty box (min = +inf, max = -inf).
 // replaces struct kdtree / struct kdnode / struct kdhyperrect (Utils/kdtree/src/kdtree.c:56-80) and
 // hyperrect_extend (kdtree.c:729-741).
 #pragma once

@@ -4,7 +4,9 @@
 #include <stdint.h>
 #include <float.h>
 
-#define PC_LEAF 8            // points per leaf = one 128-byte line of float4
+#ifndef PC_LEAF
+#define PC_LEAF 4            // points per leaf (power of two); build with -DPC_LEAF=n to change (scripts/sweep.py)
+#endif
 #define PC_FULL_MASK 0xffffffffu
 
 // ---- monotone float <-> uint mapping (for atomicMin/atomicMax on floats) -------------------------

@@ -36,6 +36,7 @@ struct pc_lane {
     uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr; int64_t sort_cap = 0;
     uint32_t *tile_hist = nullptr; int64_t hist_cap = 0;
     uint32_t *digit_total = nullptr;
+    unsigned long long *counter = nullptr;                   // work counter of the persistent query kernel
     cudaEvent_t done = nullptr;
     cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr;   // profiling: batch start / ordered / searched
 };
@@ -56,8 +57,9 @@ struct pc_index {
     uint32_t *vals_a = nullptr, *vals_b = nullptr;
     uint32_t *tile_hist = nullptr; int64_t hist_cap = 0;
     uint32_t *digit_total = nullptr;
-    float4 *points = nullptr; int64_t points_cap = 0;
-    float4 *nodes = nullptr; int64_t nodes_cap = 0;
+    float4 *tree = nullptr; int64_t tree_cap = 0;   // one allocation: boxes [0, 4P) then leaf records [4P, 6P)
+    float4 *points = nullptr;                       // = tree + 4P of the current build
+    float4 *nodes = nullptr;                        // = tree
     cudaEvent_t ev_b0 = nullptr, ev_b1 = nullptr, ev_ready = nullptr;
     bool build_timed = false;
 
@@ -68,6 +70,10 @@ struct pc_index {
 
     int64_t launches = 0;
     bool profile = false, profiled = false;
+    // tuning knobs (environment: PC_QUERY_KERNEL, PC_SORT_BITS, PC_MIN_IDLE), see DESIGN.md "Query kernel variants"
+    int query_kernel = 3;     // 1 = one thread per query, 2 = persistent warps with lane refill, 3 = warp packets (ordered batches)
+    int sort_bits = 24;       // radix-sorted key width of the batch ordering pass (0 = never order)
+    int min_idle = 8;         // persistent kernel: refill once this many lanes are idle
     char err[256] = "";
 };
 
@@ -127,7 +133,8 @@ static int pc_reserve_cloud(pc_index *ix, int64_t n)
     int64_t cap = n;
     // free the old arena
     cudaFree(ix->d_xyz); cudaFree(ix->keys_a); cudaFree(ix->keys_b); cudaFree(ix->vals_a); cudaFree(ix->vals_b);
-    cudaFree(ix->points); cudaFree(ix->nodes); cudaFree(ix->tile_hist);
+    cudaFree(ix->tree); cudaFree(ix->tile_hist);
+    ix->tree = nullptr; ix->tree_cap = 0;
     ix->d_xyz = nullptr; ix->keys_a = ix->keys_b = nullptr; ix->vals_a = ix->vals_b = nullptr;
     ix->points = ix->nodes = nullptr; ix->tile_hist = nullptr; ix->cap = 0; ix->hist_cap = 0;
     ix->key_bytes = pc_key_bits_per_axis(cap) > 10 ? 8 : 4;
@@ -138,10 +145,8 @@ static int pc_reserve_cloud(pc_index *ix, int64_t n)
     PC_CUDA(ix, cudaMalloc((void **)&ix->vals_b, (size_t)cap * sizeof(uint32_t)));
     int64_t leaves = (cap + PC_LEAF - 1) / PC_LEAF;
     int64_t P = pc_pow2_ge(leaves);
-    ix->points_cap = (leaves + 1) * PC_LEAF;
-    ix->nodes_cap = 4 * P;
-    PC_CUDA(ix, cudaMalloc((void **)&ix->points, (size_t)ix->points_cap * sizeof(float4)));
-    PC_CUDA(ix, cudaMalloc((void **)&ix->nodes, (size_t)ix->nodes_cap * sizeof(float4)));
+    ix->tree_cap = 4 * P + PC_LEAF * P;
+    PC_CUDA(ix, cudaMalloc((void **)&ix->tree, (size_t)ix->tree_cap * sizeof(float4)));
     ix->hist_cap = (int64_t)RS_RADIX * (rs_num_tiles<8>(cap) + 1);
     PC_CUDA(ix, cudaMalloc((void **)&ix->tile_hist, (size_t)ix->hist_cap * sizeof(uint32_t)));
     ix->cap = cap;
@@ -168,6 +173,9 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         TRY(cudaGetDeviceProperties(&prop, device));
         if (prop.major < 10) { rc = pc_fail(nullptr, PC_ECUDA, "pc_index_create: device is sm_%d%d, this library is built for sm_100a only", prop.major, prop.minor); break; }
         ix->sm_count = prop.multiProcessorCount;
+        if (const char *v = getenv("PC_QUERY_KERNEL")) { int b_ = atoi(v); ix->query_kernel = (b_ >= 1 && b_ <= 3) ? b_ : 3; }
+        if (const char *v = getenv("PC_SORT_BITS")) { int b_ = atoi(v); ix->sort_bits = b_ <= 0 ? 0 : (b_ <= 16 ? 16 : (b_ <= 24 ? 24 : 32)); }
+        if (const char *v = getenv("PC_MIN_IDLE")) { int b_ = atoi(v); ix->min_idle = b_ < 1 ? 1 : (b_ > 32 ? 32 : b_); }
         if (cuda_stream) { ix->stream = (cudaStream_t)cuda_stream; ix->own_stream = false; }
         else { TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking)); ix->own_stream = true; }
         TRY(cudaEventCreate(&ix->ev_b0));
@@ -184,6 +192,7 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
             TRY(cudaEventCreate(&ix->lane[l].t1));
             TRY(cudaEventCreate(&ix->lane[l].t2));
             TRY(cudaMalloc((void **)&ix->lane[l].digit_total, RS_RADIX * sizeof(uint32_t)));
+            TRY(cudaMalloc((void **)&ix->lane[l].counter, 2 * sizeof(unsigned long long)));
         }
         if (rc != PC_OK) break;
 #undef TRY
@@ -207,7 +216,7 @@ extern "C" void pc_index_destroy(pc_index *ix)
         if (L.stream && L.own_stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
         cudaFree(L.d_q); cudaFree(L.d_i32); cudaFree(L.d_f32);
         cudaFree(L.keys_a); cudaFree(L.keys_b); cudaFree(L.vals_a); cudaFree(L.vals_b);
-        cudaFree(L.tile_hist); cudaFree(L.digit_total);
+        cudaFree(L.tile_hist); cudaFree(L.digit_total); cudaFree(L.counter);
         if (L.done) cudaEventDestroy(L.done);
         if (L.t0) cudaEventDestroy(L.t0);
         if (L.t1) cudaEventDestroy(L.t1);
@@ -215,7 +224,7 @@ extern "C" void pc_index_destroy(pc_index *ix)
     }
     cudaFree(ix->d_xyz); cudaFree(ix->d_bbox); cudaFree(ix->keys_a); cudaFree(ix->keys_b);
     cudaFree(ix->vals_a); cudaFree(ix->vals_b); cudaFree(ix->tile_hist); cudaFree(ix->digit_total);
-    cudaFree(ix->points); cudaFree(ix->nodes); cudaFree(ix->scratch);
+    cudaFree(ix->tree); cudaFree(ix->scratch);
     if (ix->ev_b0) cudaEventDestroy(ix->ev_b0);
     if (ix->ev_b1) cudaEventDestroy(ix->ev_b1);
     if (ix->ev_ready) cudaEventDestroy(ix->ev_ready);
@@ -331,6 +340,8 @@ extern "C" int pc_index_build(pc_index *ix, const float *xyz, int64_t n, int64_t
 
     const int64_t n_leaves = (n + PC_LEAF - 1) / PC_LEAF;
     const int64_t P = pc_pow2_ge(n_leaves);
+    ix->nodes = ix->tree;
+    ix->points = ix->tree + 4 * P;
     {
         int64_t slots = (n_leaves + 1) * PC_LEAF;
         int grid = (int)((slots + PC_BUILD_THREADS - 1) / PC_BUILD_THREADS);
@@ -394,7 +405,18 @@ static pc_tree pc_tree_of(const pc_index *ix)
 }
 
 // Morton-order a device-resident batch on lane L: returns the permutation (device pointer) in *perm
-static int pc_sort_queries(pc_index *ix, pc_lane &L, const float *d_q, int64_t m, int qstride, const uint32_t **perm)
+enum pc_qkind { PC_Q_NEAREST, PC_Q_RADIUS };
+
+struct pc_qargs {
+    pc_qkind kind;
+    pc_radius_dev R;
+    int flags;
+};
+
+// Morton-order a device-resident batch on lane L: *perm = permutation (device), L.counter[1] = number of leading
+// entries that still need a search (radius batches answer the sensing-range early-outs in this pass)
+static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const float *d_q, int64_t m, int qstride,
+                           int32_t *d_idx, float *d_f, const uint32_t **perm)
 {
     if (m > L.sort_cap) {
         int64_t c = m;
@@ -409,12 +431,18 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const float *d_q, int64_t m
     int64_t need_hist = (int64_t)RS_RADIX * (rs_num_tiles<16>(m) + 1);
     int rc = pc_grow(ix, &L.tile_hist, &L.hist_cap, need_hist);
     if (rc != PC_OK) return rc;
-    // keep the top 16 of the 30 Morton bits: 2 radix passes, cells of ~1/40 of the cloud's extent
-    const int drop = 14;
-    pc_query_key_kernel<<<(int)((m + 255) / 256), 256, 0, L.stream>>>(d_q, m, qstride, ix->d_bbox, drop, L.keys_a, L.vals_a);
+    // sort_bits (16 / 24 / 32) = radix-sorted key width: the top sort_bits - 1 Morton bits plus one bit for the
+    // "already answered" key that sends early-outs to the end
+    const int bits = ix->sort_bits;
+    const int drop = 31 - bits > 0 ? 31 - bits : 0;
+    const int grid = (int)((m + 255) / 256);
+    if (A.kind == PC_Q_RADIUS)
+        pc_query_key_kernel<PC_KIND_RADIUS><<<grid, 256, 0, L.stream>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1);
+    else
+        pc_query_key_kernel<PC_KIND_NEAREST><<<grid, 256, 0, L.stream>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1);
     ix->launches++;
     PC_CHECK_LAUNCH(ix);
-    int which = rs_sort_pairs<uint32_t, 16>(L.keys_a, L.vals_a, L.keys_b, L.vals_b, m, 0, 16, L.tile_hist, L.digit_total, L.stream, &ix->launches);
+    int which = rs_sort_pairs<uint32_t, 16>(L.keys_a, L.vals_a, L.keys_b, L.vals_b, m, 0, bits, L.tile_hist, L.digit_total, L.stream, &ix->launches);
     PC_CHECK_LAUNCH(ix);
     *perm = which ? L.vals_b : L.vals_a;
     return PC_OK;
@@ -422,19 +450,11 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const float *d_q, int64_t m
 
 static bool pc_want_sort(const pc_index *ix, int flags, int64_t m)
 {
-    if (ix->n == 0) return false;
+    if (ix->n == 0 || ix->sort_bits == 0) return false;
     if (flags & PC_QUERY_SORTED) return true;
     if (flags & PC_QUERY_UNSORTED) return false;
     return m >= PC_SORT_MIN_BATCH;
 }
-
-enum pc_qkind { PC_Q_NEAREST, PC_Q_RADIUS };
-
-struct pc_qargs {
-    pc_qkind kind;
-    pc_radius_dev R;
-    int flags;
-};
 
 // run one device-resident batch on lane L
 static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float *d_q, int64_t m, int qstride,
@@ -442,19 +462,40 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
 {
     if (m == 0) return PC_OK;
     const uint32_t *perm = nullptr;
+    const unsigned long long *m_eff = nullptr;
     const bool prof = ix->profile && &L == &ix->lane[0];
     if (prof) PC_CUDA(ix, cudaEventRecord(L.t0, L.stream));
+    // counter[0]: work counter of the persistent kernel, counter[1]: queries that need a search after the ordering pass
+    PC_CUDA(ix, cudaMemsetAsync(L.counter, 0, 2 * sizeof(unsigned long long), L.stream));
     if (pc_want_sort(ix, A.flags, m)) {
-        int rc = pc_sort_queries(ix, L, d_q, m, qstride, &perm);
+        int rc = pc_sort_queries(ix, L, A, d_q, m, qstride, d_idx, d_f, &perm);
         if (rc != PC_OK) return rc;
+        m_eff = L.counter + 1;
     }
     if (prof) PC_CUDA(ix, cudaEventRecord(L.t1, L.stream));
     pc_tree T = pc_tree_of(ix);
-    int grid = (int)((m + PC_QUERY_THREADS - 1) / PC_QUERY_THREADS);
-    if (A.kind == PC_Q_NEAREST)
-        pc_nearest_kernel<<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, d_q, m, qstride, perm, d_idx, d_f);
-    else
-        pc_radius_kernel<<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, d_f, d_idx);
+    const int64_t want = (m + PC_QUERY_THREADS - 1) / PC_QUERY_THREADS;
+    if (ix->query_kernel == 3 && perm) {
+        // Morton-ordered batch: one warp walks the tree once for its 32 neighbouring queries
+        const int grid = (int)want;
+        if (A.kind == PC_Q_NEAREST)
+            pc_query_packet_kernel<PC_KIND_NEAREST><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
+        else
+            pc_query_packet_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
+    } else if (ix->query_kernel != 2) {
+        const int grid = (int)want;
+        if (A.kind == PC_Q_NEAREST)
+            pc_query_simple_kernel<PC_KIND_NEAREST><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
+        else
+            pc_query_simple_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
+    } else {
+        // persistent grid: up to 8 CTAs of 4 warps per SM (<= 64 registers/thread), fewer when the batch is small
+        const int grid = (int)(want < (int64_t)ix->sm_count * 8 ? want : (int64_t)ix->sm_count * 8);
+        if (A.kind == PC_Q_NEAREST)
+            pc_query_persist_kernel<PC_KIND_NEAREST><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f, L.counter, ix->min_idle);
+        else
+            pc_query_persist_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f, L.counter, ix->min_idle);
+    }
     ix->launches++;
     PC_CHECK_LAUNCH(ix);
     if (prof) { PC_CUDA(ix, cudaEventRecord(L.t2, L.stream)); ix->profiled = true; }

@@ -1,9 +1,8 @@
-// query_kernels.cuh -- exact nearest / radius / range queries: one thread per query, near-first
-// descent of the bounding-box tree with a short per-thread stack.
+// query_kernels.cuh -- exact nearest / radius queries: near-first descent of the bounding-box tree with a short
+// per-thread stack, one query per lane.
 //
-// Replaces kd_nearest_i / kd_nearest3 (Utils/kdtree/src/kdtree.c:345-457,493-500), find_nearest /
-// kd_nearest_range3 (kdtree.c:262-293,595-602) and the epilogue of safeRegionRrtStar::radiusSearch
-// (Planner/src/corridor_finder.cpp:113-133).
+// Replaces kd_nearest_i / kd_nearest3 (Utils/kdtree/src/kdtree.c:345-457,493-500) and the epilogue of
+// safeRegionRrtStar::radiusSearch (Planner/src/corridor_finder.cpp:113-133).
 //
 // Exactness: boxes and points are filtered in fp32 against `thr`, an upper bound of the current best fp64
 // distance inflated by 2^-20 (fp32 evaluation error of d2 is < 2^-22 relative, so no candidate whose fp64
@@ -18,8 +17,8 @@
 #define PC_THR_SLACK 1.00000095367431640625f   // 1 + 2^-20
 
 struct pc_tree {
-    const float4 *__restrict__ nodes;
-    const float4 *__restrict__ points;
+    const float4 *__restrict__ nodes;    // boxes: node i -> nodes[2i] (min), nodes[2i+1] (max)
+    const float4 *__restrict__ points;   // leaf j -> points[PC_LEAF * j ..]
     int64_t n_points;
     uint32_t P;            // leaf base (power of two >= 2)
 };
@@ -53,30 +52,39 @@ struct pc_best {
     float thr;     // fp32 filter threshold (inclusive)
 };
 
-__device__ __forceinline__ void pc_scan_leaf(const float4 *__restrict__ pts, float qx, float qy, float qz,
-                                             double qxd, double qyd, double qzd, pc_best &b)
+__device__ __forceinline__ void pc_consider(const float4 p, float d, float qx, float qy, float qz, pc_best &b)
 {
-    float4 p[PC_LEAF];
-#pragma unroll
-    for (int i = 0; i < PC_LEAF; i++) p[i] = __ldg(pts + i);
-#pragma unroll
-    for (int i = 0; i < PC_LEAF; i++) {
-        float dx = p[i].x - qx, dy = p[i].y - qy, dz = p[i].z - qz;
-        float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        if (d <= b.thr) {
-            double e = pc_exact_d2(p[i].x, p[i].y, p[i].z, qxd, qyd, qzd);
-            int32_t id = __float_as_int(p[i].w);
-            if (e < b.d2 || (e == b.d2 && (uint32_t)id < (uint32_t)b.idx)) {
-                b.d2 = e; b.idx = id; b.thr = fminf(b.thr, pc_thr_from(e));
-            }
+    if (d <= b.thr) {
+        const double e = pc_exact_d2(p.x, p.y, p.z, (double)qx, (double)qy, (double)qz);
+        const int32_t id = __float_as_int(p.w);
+        if (e < b.d2 || (e == b.d2 && (uint32_t)id < (uint32_t)b.idx)) {
+            b.d2 = e; b.idx = id; b.thr = fminf(b.thr, pc_thr_from(e));
         }
     }
 }
 
-// Core traversal.  On entry b holds the initial bound (d2 = +inf, idx = -1, thr = bound).
+__device__ __forceinline__ void pc_scan_leaf(const float4 *__restrict__ pts, float qx, float qy, float qz, pc_best &b)
+{
+    float4 p[PC_LEAF];
+    float d[PC_LEAF];
+#pragma unroll
+    for (int i = 0; i < PC_LEAF; i++) p[i] = __ldg(pts + i);
+    float dmin = FLT_MAX;
+#pragma unroll
+    for (int i = 0; i < PC_LEAF; i++) {
+        const float dx = p[i].x - qx, dy = p[i].y - qy, dz = p[i].z - qz;
+        d[i] = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        dmin = fminf(dmin, d[i]);
+    }
+    if (dmin <= b.thr) {          // one branch for the whole leaf: after the first leaves almost never taken
+#pragma unroll
+        for (int i = 0; i < PC_LEAF; i++) pc_consider(p[i], d[i], qx, qy, qz, b);
+    }
+}
+
+// Core traversal of one query by one thread.  On entry b holds the initial bound (d2 = +inf, idx = -1, thr = bound).
 __device__ __forceinline__ void pc_nearest_traverse(const pc_tree &T, float qx, float qy, float qz, pc_best &b)
 {
-    const double qxd = (double)qx, qyd = (double)qy, qzd = (double)qz;
     uint32_t stack_node[PC_STACK];
     float stack_d[PC_STACK];
     int sp = 0;
@@ -94,8 +102,8 @@ __device__ __forceinline__ void pc_nearest_traverse(const pc_tree &T, float qx, 
         bool descended = false;
         if (c0 >= T.P) {
             // children are leaves
-            if (dn <= b.thr) pc_scan_leaf(T.points + (size_t)(cn - T.P) * PC_LEAF, qx, qy, qz, qxd, qyd, qzd, b);
-            if (df <= b.thr) pc_scan_leaf(T.points + (size_t)(cf - T.P) * PC_LEAF, qx, qy, qz, qxd, qyd, qzd, b);
+            if (dn <= b.thr) pc_scan_leaf(T.points + (size_t)(cn - T.P) * PC_LEAF, qx, qy, qz, b);
+            if (df <= b.thr) pc_scan_leaf(T.points + (size_t)(cf - T.P) * PC_LEAF, qx, qy, qz, b);
         } else {
             if (df <= b.thr) { stack_node[sp] = cf; stack_d[sp] = df; sp++; }
             if (dn <= b.thr) { node = cn; descended = true; }
@@ -111,23 +119,7 @@ __device__ __forceinline__ void pc_nearest_traverse(const pc_tree &T, float qx, 
     }
 }
 
-// ---- kernels ----------------------------------------------------------------------------------------
-// perm (nullable): process query perm[t] in slot t (Morton-ordered batches); results go to the original slot.
-__global__ void __launch_bounds__(PC_QUERY_THREADS)
-pc_nearest_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstride, const uint32_t *__restrict__ perm,
-                  int32_t *__restrict__ out_idx, float *__restrict__ out_d2)
-{
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m) return;
-    int64_t k = perm ? (int64_t)perm[t] : t;
-    const float *qq = q + k * qstride;
-    float qx = qq[0], qy = qq[1], qz = qq[2];
-    pc_best b; b.d2 = INFINITY; b.idx = -1; b.thr = FLT_MAX;
-    if (T.n_points > 0) pc_nearest_traverse(T, qx, qy, qz, b);
-    if (out_idx) out_idx[k] = b.idx;
-    if (out_d2) out_d2[k] = (float)b.d2;
-}
-
+// ---- radiusSearch pieces ------------------------------------------------------------------------------
 struct pc_radius_dev {
     double search_margin, max_radius, sample_range;
     double sx, sy, sz;
@@ -152,39 +144,270 @@ __device__ __forceinline__ bool pc_radius_early_out(double px, double py, double
     return __dsqrt_rn(s) > __dadd_rn(R.sample_range, R.max_radius);
 }
 
-__global__ void __launch_bounds__(PC_QUERY_THREADS)
-pc_radius_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, int64_t m, int qstride,
-                 const uint32_t *__restrict__ perm, float *__restrict__ out_radius, int32_t *__restrict__ out_idx)
+#define PC_KIND_NEAREST 0
+#define PC_KIND_RADIUS 1
+
+// result of a query that needs no search: empty cloud (kd_nearest3 -> NULL; corridor_finder.cpp:118-120) or outside the
+// sensing range (corridor_finder.cpp:115-116)
+template <int KIND>
+__device__ __forceinline__ void pc_write_trivial(const pc_radius_dev &R, uint32_t k, int32_t *out_idx, float *out_f)
 {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= m) return;
-    int64_t k = perm ? (int64_t)perm[t] : t;
-    const float *qq = q + k * qstride;
-    float qx = qq[0], qy = qq[1], qz = qq[2];
-    double radius;
-    int32_t idx = -1;
-    if (T.n_points == 0 || pc_radius_early_out((double)qx, (double)qy, (double)qz, R)) {
-        radius = __dsub_rn(R.max_radius, R.search_margin);
-    } else {
-        pc_best b; b.d2 = INFINITY; b.idx = -1; b.thr = R.bound_thr;
-        pc_nearest_traverse(T, qx, qy, qz, b);
-        radius = pc_radius_epilogue(b, R);
-        idx = (R.bounded && !(radius < R.max_radius)) ? -1 : b.idx;
-    }
-    if (out_radius) out_radius[k] = (float)radius;
-    if (out_idx) out_idx[k] = idx;
+    if (out_idx) out_idx[k] = -1;
+    if (out_f) out_f[k] = (KIND == PC_KIND_RADIUS) ? (float)__dsub_rn(R.max_radius, R.search_margin) : INFINITY;
 }
 
-// Morton keys of a query batch in the index's frame, keeping only the top bits (coarse cells are enough to make
-// the lanes of a warp walk the same part of the tree)
+template <int KIND>
+__device__ __forceinline__ void pc_write_result(const pc_radius_dev &R, const pc_best &b, uint32_t k, int32_t *out_idx, float *out_f)
+{
+    if (KIND == PC_KIND_RADIUS) {
+        const double radius = pc_radius_epilogue(b, R);
+        if (out_f) out_f[k] = (float)radius;
+        if (out_idx) out_idx[k] = (R.bounded && !(radius < R.max_radius)) ? -1 : b.idx;
+    } else {
+        if (out_idx) out_idx[k] = b.idx;
+        if (out_f) out_f[k] = (float)b.d2;
+    }
+}
+
+// ---- variant 1: one thread per query, exit when done ----------------------------------------------------
+// perm (nullable): process query perm[t] in slot t (Morton-ordered batches); results go to the original slot.
+// m_eff (nullable): device-side number of leading entries of perm that need a search (the rest were answered by the
+// ordering pass).
+template <int KIND>
+__global__ void __launch_bounds__(PC_QUERY_THREADS)
+pc_query_simple_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, int64_t m, int qstride,
+                       const uint32_t *__restrict__ perm, const unsigned long long *__restrict__ m_eff,
+                       int32_t *__restrict__ out_idx, float *__restrict__ out_f)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= m || (m_eff && t >= (int64_t)*m_eff)) return;
+    const uint32_t k = perm ? perm[t] : (uint32_t)t;
+    const float *qq = q + (size_t)k * qstride;
+    const float qx = qq[0], qy = qq[1], qz = qq[2];
+    bool search = T.n_points > 0;
+    if (KIND == PC_KIND_RADIUS && search && !m_eff && pc_radius_early_out((double)qx, (double)qy, (double)qz, R)) search = false;
+    if (!search) { pc_write_trivial<KIND>(R, k, out_idx, out_f); return; }
+    pc_best b; b.d2 = INFINITY; b.idx = -1; b.thr = (KIND == PC_KIND_RADIUS) ? R.bound_thr : FLT_MAX;
+    pc_nearest_traverse(T, qx, qy, qz, b);
+    pc_write_result<KIND>(R, b, k, out_idx, out_f);
+}
+
+// ---- variant 2: persistent warps, lanes refilled as their query finishes -----------------------------------
+// A query walks a data-dependent number of tree nodes, so "one thread per query, exit when done" leaves most lanes
+// of a warp idle while the longest query of the 32 finishes (measured: 5.7 of 32 lanes active, profiles/r1_full_v1*).
+// Here every warp owns a running window of the (Morton-ordered) batch, taken PC_Q_CHUNK queries at a time from a
+// global counter and staged in shared memory; finished lanes park their result and, once `min_idle` lanes are
+// parked, write the results and take the next queries of the window.  Every loop iteration performs ONE traversal
+// step per lane: load the record of the node to visit (a pair of child boxes, or the points of a leaf) and process it.
+#define PC_Q_CHUNK 128
+
+template <int KIND>
+__global__ void __launch_bounds__(PC_QUERY_THREADS, 8)
+pc_query_persist_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, int64_t m, int qstride,
+                        const uint32_t *__restrict__ perm, const unsigned long long *__restrict__ m_eff,
+                        int32_t *__restrict__ out_idx, float *__restrict__ out_f,
+                        unsigned long long *__restrict__ counter, int min_idle)
+{
+    __shared__ float4 s_q[PC_QUERY_THREADS / 32][PC_Q_CHUNK];   // staged window: x, y, z, caller slot (int bits)
+    const uint32_t lt = pc_lanemask_lt();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long m_search = m_eff ? (long long)*m_eff : (long long)m;
+    uint32_t stack_node[PC_STACK];
+    float stack_d[PC_STACK];
+    int sp = 0;
+    // warp-uniform window [cur, end) of the batch; s_q[warp][j] holds query win0 + j
+    long long cur = 0, end = 0, win0 = 0;
+    bool exhausted = false;
+    // per-lane query state
+    bool has_q = false, parked = false;   // parked: finished, result not yet written
+    uint32_t node = 0;          // node to visit next; 0 = take the next one from the stack
+    uint32_t k = 0;             // slot of the query in the caller's arrays
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    pc_best b; b.d2 = INFINITY; b.idx = -1; b.thr = FLT_MAX;
+
+    for (;;) {
+        uint32_t idle = __ballot_sync(PC_FULL_MASK, !has_q);
+        if (__popc(idle) >= min_idle) {
+            // parked lanes write their results (the epilogue is deferred to here so that it runs for many lanes at once)
+            if (parked) { pc_write_result<KIND>(R, b, k, out_idx, out_f); parked = false; }
+            // hand queries to the idle lanes; queries that need no search are answered on the spot, so keep going
+            // until the idle lanes hold real work or the batch is used up
+            for (;;) {
+                if (cur == end && !exhausted) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(counter, (unsigned long long)PC_Q_CHUNK);
+                    base = __shfl_sync(PC_FULL_MASK, base, 0);
+                    if (base >= (unsigned long long)m_search) {
+                        exhausted = true;
+                    } else {
+                        win0 = cur = (long long)base;
+                        end = cur + PC_Q_CHUNK < m_search ? cur + PC_Q_CHUNK : m_search;
+                        __syncwarp();
+                        for (int j = lane; j < (int)(end - cur); j += 32) {
+                            const long long t = cur + j;
+                            const uint32_t kk = perm ? perm[t] : (uint32_t)t;
+                            const float *qq = q + (size_t)kk * qstride;
+                            s_q[warp][j] = make_float4(qq[0], qq[1], qq[2], __uint_as_float(kk));
+                        }
+                        __syncwarp();
+                    }
+                }
+                const int avail = (int)(end - cur);
+                const int want = __popc(idle);
+                const int rank = __popc(idle & lt);
+                if (!has_q && rank < avail) {
+                    const float4 v = s_q[warp][(int)(cur - win0) + rank];
+                    qx = v.x; qy = v.y; qz = v.z; k = __float_as_uint(v.w);
+                    bool search = T.n_points > 0;
+                    if (KIND == PC_KIND_RADIUS && search && !m_eff && pc_radius_early_out((double)qx, (double)qy, (double)qz, R)) search = false;
+                    if (search) {
+                        has_q = true; node = 1; sp = 0;
+                        b.d2 = INFINITY; b.idx = -1; b.thr = (KIND == PC_KIND_RADIUS) ? R.bound_thr : FLT_MAX;
+                    } else {
+                        pc_write_trivial<KIND>(R, k, out_idx, out_f);
+                    }
+                }
+                cur += want < avail ? want : avail;
+                idle = __ballot_sync(PC_FULL_MASK, !has_q);
+                if (exhausted || __popc(idle) < min_idle) break;
+            }
+            if (exhausted && idle == PC_FULL_MASK) break;
+        }
+        // ---- one traversal step --------------------------------------------------------------------------
+        if (has_q) {
+            if (node >= T.P) {
+                pc_scan_leaf(T.points + (size_t)(node - T.P) * PC_LEAF, qx, qy, qz, b);
+                node = 0;
+            } else {
+                const float4 *pair = T.nodes + 4ull * node;
+                const float4 lo0 = __ldg(pair), hi0 = __ldg(pair + 1), lo1 = __ldg(pair + 2), hi1 = __ldg(pair + 3);
+                const float d0 = pc_box_d2(lo0, hi0, qx, qy, qz);
+                const float d1 = pc_box_d2(lo1, hi1, qx, qy, qz);
+                const uint32_t c0 = 2u * node;
+                const bool first0 = d0 <= d1;
+                const uint32_t cn = first0 ? c0 : c0 + 1, cf = first0 ? c0 + 1 : c0;
+                const float dn = fminf(d0, d1), df = fmaxf(d0, d1);
+                if (df <= b.thr) { stack_node[sp] = cf; stack_d[sp] = df; sp++; }
+                node = dn <= b.thr ? cn : 0;
+            }
+            if (node == 0) {
+                while (sp > 0 && stack_d[sp - 1] > b.thr) sp--;          // drop entries the shrinking bound has pruned
+                if (sp == 0) { has_q = false; parked = true; }
+                else node = stack_node[--sp];
+            }
+        }
+    }
+}
+
+// ---- variant 3: warp packets ---------------------------------------------------------------------------------
+// After the ordering pass the 32 queries of a warp lie in one small Morton cell, so their searches visit almost the
+// same nodes.  The warp therefore walks the tree ONCE for all 32 queries: one shared stack (kept in registers, entry i
+// in lane i, read back with a shuffle), every node record loaded once at a warp-uniform address, each lane testing its
+// own query against it; a subtree is entered when ANY lane still needs it (ballot), the nearer child is chosen by
+// majority vote.  Control flow is warp-uniform, so all 32 lanes are active at every step and there is no per-lane
+// stack in local memory; the price is that a lane also visits nodes only its neighbours needed.
+template <int KIND>
+__global__ void __launch_bounds__(PC_QUERY_THREADS)
+pc_query_packet_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, int64_t m, int qstride,
+                       const uint32_t *__restrict__ perm, const unsigned long long *__restrict__ m_eff,
+                       int32_t *__restrict__ out_idx, float *__restrict__ out_f)
+{
+    const int lane = threadIdx.x & 31;
+    const long long m_search = m_eff ? (long long)*m_eff : (long long)m;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t - lane >= m_search) return;                       // whole warp past the end
+    bool valid = t < m_search;
+    uint32_t k = 0;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    pc_best b; b.d2 = INFINITY; b.idx = -1; b.thr = -1.0f;  // thr < 0: this lane needs nothing
+    if (valid) {
+        k = perm ? perm[t] : (uint32_t)t;
+        const float *qq = q + (size_t)k * qstride;
+        qx = qq[0]; qy = qq[1]; qz = qq[2];
+        bool search = T.n_points > 0;
+        if (KIND == PC_KIND_RADIUS && search && !m_eff && pc_radius_early_out((double)qx, (double)qy, (double)qz, R)) search = false;
+        if (search) b.thr = (KIND == PC_KIND_RADIUS) ? R.bound_thr : FLT_MAX;
+        else { pc_write_trivial<KIND>(R, k, out_idx, out_f); valid = false; }
+    }
+    if (__ballot_sync(PC_FULL_MASK, valid) == 0) return;
+
+    // warp stack: entry i lives in lane i -- node id and the smallest box distance any interested lane had when it
+    // was pushed (float bits; distances are >= 0 so the unsigned order is the float order)
+    uint32_t my_entry = 0, my_dmin = 0;
+    int sp = 0;
+    uint32_t node = 1;
+    // largest threshold of any lane: an entry whose dmin exceeds it is needed by nobody any more
+    uint32_t wmax = __reduce_max_sync(PC_FULL_MASK, b.thr < 0.f ? 0u : __float_as_uint(b.thr));
+    for (;;) {
+        const float4 *pair = T.nodes + 4ull * node;
+        const float4 lo0 = __ldg(pair), hi0 = __ldg(pair + 1), lo1 = __ldg(pair + 2), hi1 = __ldg(pair + 3);
+        const float d0 = pc_box_d2(lo0, hi0, qx, qy, qz);
+        const float d1 = pc_box_d2(lo1, hi1, qx, qy, qz);
+        const bool want0 = d0 <= b.thr, want1 = d1 <= b.thr;
+        const uint32_t w0 = __ballot_sync(PC_FULL_MASK, want0);
+        const uint32_t w1 = __ballot_sync(PC_FULL_MASK, want1);
+        const uint32_t c0 = 2u * node;
+        bool pop = true;
+        if (w0 | w1) {
+            // the child most interested lanes are nearer to goes first
+            const uint32_t pref0 = __ballot_sync(PC_FULL_MASK, d0 <= d1) & (w0 | w1);
+            const bool first0 = w1 == 0 || (w0 != 0 && 2 * __popc(pref0) >= __popc(w0 | w1));
+            const uint32_t cn = first0 ? c0 : c0 + 1, cf = first0 ? c0 + 1 : c0;
+            const bool both = w0 != 0 && w1 != 0;
+            if (c0 >= T.P) {
+                pc_scan_leaf(T.points + (size_t)(cn - T.P) * PC_LEAF, qx, qy, qz, b);
+                if (both && __ballot_sync(PC_FULL_MASK, (first0 ? d1 : d0) <= b.thr))
+                    pc_scan_leaf(T.points + (size_t)(cf - T.P) * PC_LEAF, qx, qy, qz, b);
+                wmax = __reduce_max_sync(PC_FULL_MASK, b.thr < 0.f ? 0u : __float_as_uint(b.thr));
+            } else {
+                if (both) {
+                    const float df = first0 ? d1 : d0;
+                    const bool wantf = first0 ? want1 : want0;
+                    const uint32_t dmin = __reduce_min_sync(PC_FULL_MASK, wantf ? __float_as_uint(df) : 0x7f800000u);
+                    if (lane == sp) { my_entry = cf; my_dmin = dmin; }
+                    sp++;
+                }
+                node = cn;
+                pop = false;
+            }
+        }
+        if (pop) {
+            bool found = false;
+            while (sp > 0) {
+                sp--;
+                if (__shfl_sync(PC_FULL_MASK, my_dmin, sp) <= wmax) { node = __shfl_sync(PC_FULL_MASK, my_entry, sp); found = true; break; }
+            }
+            if (!found) break;
+        }
+    }
+    if (valid) pc_write_result<KIND>(R, b, k, out_idx, out_f);
+}
+
+// ---- ordering pass of a batch --------------------------------------------------------------------------
+// Morton key of every query in the index's frame (top `30 - drop_bits` bits), so that the lanes of a warp walk the
+// same part of the tree.  For radius batches the sensing-range early-out (corridor_finder.cpp:115-116) is evaluated
+// here, once, coalesced: such queries get their result now and the largest key, and n_search counts the others --
+// after the sort they are exactly the first n_search entries of the permutation.
+template <int KIND>
 __global__ void __launch_bounds__(256)
 pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const uint32_t *__restrict__ bbox, int drop_bits,
-                    uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+                    pc_radius_dev R, int32_t *__restrict__ out_idx, float *__restrict__ out_f,
+                    uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, unsigned long long *__restrict__ n_search)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const pc_frame f = pc_make_frame(bbox, 10);
-    const float *p = q + i * qstride;
-    keys[i] = pc_morton30(p[0], p[1], p[2], f) >> drop_bits;
-    vals[i] = (uint32_t)i;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool search = false;
+    if (i < m) {
+        const pc_frame f = pc_make_frame(bbox, 10);
+        const float *p = q + i * qstride;
+        const float x = p[0], y = p[1], z = p[2];
+        search = true;
+        if (KIND == PC_KIND_RADIUS && pc_radius_early_out((double)x, (double)y, (double)z, R)) {
+            search = false;
+            pc_write_trivial<KIND>(R, (uint32_t)i, out_idx, out_f);
+        }
+        keys[i] = search ? (pc_morton30(x, y, z, f) >> drop_bits) : (0x3fffffffu >> drop_bits) + 1u;
+        vals[i] = (uint32_t)i;
+    }
+    const int n = __syncthreads_count(search);
+    if (threadIdx.x == 0 && n) atomicAdd(n_search, (unsigned long long)n);
 }
