@@ -178,32 +178,47 @@ def run_b200(args):
     M = args.queries
     start = (0.0, 0.0, 2.0)
 
-    # the cloud: generated on rank 0, replicated with one NCCL broadcast, indexed on every rank
+    # the cloud lives on rank 0 only: rank 0 builds the index, ONE ncclBroadcast (pc_index_broadcast) replicates the
+    # built index into every rank's handle; after that no collective is on the data path
+    stream = torch.cuda.current_stream().cuda_stream
+    ix = PointCloudIndex(max_points=N_POINTS, device=local, stream=stream)
+    meta = torch.zeros(1, dtype=torch.float64, device=dev)
+    build_ms = []
+    t_pts = None
     if rank == 0:
         pts, half = make_cloud()
         t_pts = torch.from_numpy(pts).to(dev)
-        meta = torch.tensor([half], dtype=torch.float64, device=dev)
-    else:
-        t_pts = torch.empty((N_POINTS, 3), dtype=torch.float32, device=dev)
-        meta = torch.zeros(1, dtype=torch.float64, device=dev)
+        meta[0] = half
+        for _ in range(5):
+            ix.build(t_pts)
+            build_ms.append(ix.last_build_ms())
     bcast_ms = 0.0
     if world > 1:
+        from pointcloudtraj_b200.dist import Replicator
+        rep = Replicator(rank, world, local)
+        dist.broadcast(meta, 0)
+        rep.broadcast(ix, 0)                      # warm-up (NCCL channel setup)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.barrier()
+        torch.cuda.synchronize()
         e0.record()
-        dist.broadcast(t_pts, 0)
-        dist.broadcast(meta, 0)
+        rep.broadcast(ix, 0)
         e1.record()
         torch.cuda.synchronize()
         bcast_ms = e0.elapsed_time(e1)
+        assert ix.size == N_POINTS
     half = float(meta.item())
-
-    stream = torch.cuda.current_stream().cuda_stream
-    ix = PointCloudIndex(max_points=N_POINTS, device=local, stream=stream)
-    build_ms = []
-    for _ in range(5):
-        ix.build(t_pts)
-        build_ms.append(ix.last_build_ms())
+    replica_ok = None
+    if world > 1:
+        # every rank answers the same probe batch against its replica; all answers must equal rank 0's
+        probe = torch.from_numpy(synth.rrt_queries(200_000, half, seed=7)).to(dev)
+        pi, pd = ix.nearest(probe)
+        ref_i, ref_d = pi.clone(), pd.clone()
+        dist.broadcast(ref_i, 0)
+        dist.broadcast(ref_d, 0)
+        ok = torch.tensor([int(bool((pi == ref_i).all().item() and (pd == ref_d).all().item()))], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        replica_ok = bool(ok.item())
     P = PcRadiusParams.make(start=start, **PARAMS)
 
     # per-rank query batch (weak scaling: every GPU answers its own M queries per step)
@@ -281,14 +296,16 @@ def run_b200(args):
     e2e_val = world * M * e2e_steps / float(t.item())
     same = bool((r_pin.to(dev) == t_r).all().item())
 
-    # C3: index rebuild of a 300k-point frame (ms/frame), device-resident frame
-    frame = t_pts[:FRAME_POINTS].contiguous()
-    ixf = PointCloudIndex(max_points=FRAME_POINTS, device=local, stream=stream)
-    fms = []
-    for _ in range(12):
-        ixf.build(frame)
-        fms.append(ixf.last_build_ms())
-    ixf.close()
+    # C3: index rebuild of a 300k-point frame (ms/frame), device-resident frame (rank 0 holds the cloud)
+    fms = [0.0] * 12
+    if rank == 0:
+        frame = t_pts[:FRAME_POINTS].contiguous()
+        ixf = PointCloudIndex(max_points=FRAME_POINTS, device=local, stream=stream)
+        fms = []
+        for _ in range(12):
+            ixf.build(frame)
+            fms.append(ixf.last_build_ms())
+        ixf.close()
 
     if rank == 0:
         peaks = {}
@@ -311,9 +328,10 @@ def run_b200(args):
                         "steps": e2e_steps, "matches_device_result": same},
                 "gpu_launches": launches, "clocks": clocks,
                 "index_build_ms_per_frame": {"points": FRAME_POINTS, "median": float(np.median(fms[2:])), "min": float(min(fms))},
-                "index_build_ms_1M": float(np.median(build_ms[1:])), "broadcast_ms": bcast_ms}
+                "index_build_ms_1M": float(np.median(build_ms[1:])), "index_broadcast_ms": bcast_ms,
+                "replicas_match_root": replica_ok}
         if not args.no_cpu_baseline and world == 1:
-            cb, r_cpu = cpu_baseline(t_pts.cpu().numpy(), q_host, start, args.cpu_sample)
+            cb, r_cpu = cpu_baseline(pts, q_host, start, args.cpu_sample)
             cb["gpu_matches_cpu_sample"] = bool((r_cpu.astype(np.float32) == t_r[: len(r_cpu)].cpu().numpy()).all())
             line["cpu_baseline"] = cb
         print(json.dumps(line))
