@@ -1,0 +1,122 @@
+// pc_corridor.hpp -- header-only C++14 mirror of the CLOUD-FACING members of safeRegionRrtStar
+// (Planner/include/pointcloudTraj/corridor_finder.h:17-150, Planner/src/corridor_finder.cpp) over the C ABI of
+// pc_index.h.  Same member names, argument meaning and return values; the per-sample members get batched
+// overloads, which is what the planner's loops call after the switch.
+//
+//   setParam        corridor_finder.cpp:17-23      safety_margin, search_margin, max_radius, sample_range
+//   setStartPt      corridor_finder.cpp:43-50      refreshes start_pt (the centre of the sensing-range early-out)
+//   setPt           corridor_finder.cpp:52-91      only its effect on radiusSearch: start_pt and sample_range = local_range (:87)
+//   setInput        corridor_finder.cpp:93-99      full index rebuild per cloud message; empty cloud -> cloud_empty
+//   radiusSearch    corridor_finder.cpp:113-133    early-outs, float32 cast of the point, 1-NN, min(sqrt(d2) - search_margin, max_radius)
+//   checkTrajPtCol  corridor_finder.cpp:412-416    radiusSearch(pt) < 0
+//   checkSafeTrajectory  Planner/src/sim_planning_demo.cpp:729-781 (a free function there; it only needs the cloud)
+//
+// No Eigen/PCL/ROS dependency: points are plain double[3] / float arrays (pcl::PointXYZ is x,y,z,pad float32 =
+// stride 4; Eigen::Vector3d::data() is double[3]).
+#ifndef PC_CORRIDOR_HPP_
+#define PC_CORRIDOR_HPP_
+
+#include <cmath>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "pc_index.h"
+
+namespace pc {
+
+class SafeRegionCloud {
+public:
+    explicit SafeRegionCloud(int device = 0, int64_t max_points = 0, void *cuda_stream = nullptr)
+    {
+        if (pc_index_create(&ix_, device, max_points, cuda_stream) != PC_OK)
+            throw std::runtime_error(std::string("pc_index_create: ") + pc_last_error(nullptr));
+        params_.search_margin = 0.0; params_.max_radius = 0.0; params_.sample_range = 0.0;
+        params_.start[0] = params_.start[1] = params_.start[2] = 0.0;
+    }
+    ~SafeRegionCloud() { pc_index_destroy(ix_); }
+    SafeRegionCloud(const SafeRegionCloud &) = delete;
+    SafeRegionCloud &operator=(const SafeRegionCloud &) = delete;
+
+    void setParam(double safety_margin_, double search_margin_, double max_radius_, double sample_range_)
+    {
+        safety_margin = safety_margin_;
+        params_.search_margin = search_margin_;
+        params_.max_radius = max_radius_;
+        params_.sample_range = sample_range_;
+    }
+    void setStartPt(const double startPt[3]) { for (int a = 0; a < 3; a++) params_.start[a] = startPt[a]; }
+    void setPt(const double startPt[3], double local_range) { setStartPt(startPt); params_.sample_range = local_range; }
+
+    // cloud: n points, stride_floats = 3 (packed) or 4 (pcl::PointXYZ); host memory.  Returns PC_OK or an error code.
+    int setInput(const float *xyz, int64_t n, int64_t stride_floats = 4)
+    {
+        cloud_empty = (n == 0);
+        return pc_index_build(ix_, xyz, n, stride_floats, PC_HOST);
+    }
+
+    // one point, as in the reference (double in, double out).  Latency-bound: prefer the batch overload.
+    double radiusSearch(const double search_Pt[3])
+    {
+        // the reference tests the sensing range on the double point BEFORE the float32 cast (corridor_finder.cpp:115-125)
+        const double dx = search_Pt[0] - params_.start[0], dy = search_Pt[1] - params_.start[1], dz = search_Pt[2] - params_.start[2];
+        if (std::sqrt(dx * dx + dy * dy + dz * dz) > params_.sample_range + params_.max_radius) return params_.max_radius - params_.search_margin;
+        if (cloud_empty) return params_.max_radius - params_.search_margin;
+        const float q[3] = { (float)search_Pt[0], (float)search_Pt[1], (float)search_Pt[2] };
+        pc_radius_params p = params_;
+        p.sample_range = -1.0;                      // already decided above
+        float r = 0.f;
+        check(pc_radius_batch(ix_, q, 1, 3, PC_HOST, PC_QUERY_UNSORTED, &p, &r, nullptr));
+        return (double)r;
+    }
+
+    // m points (float32, stride 3 or 4, host memory) -> out_radius[m] (and the nearest point's index, nullable)
+    int radiusSearch(const float *pts, int64_t m, int64_t stride_floats, float *out_radius, int32_t *out_idx = nullptr)
+    {
+        return pc_radius_batch(ix_, pts, m, stride_floats, PC_HOST, PC_QUERY_AUTO, &params_, out_radius, out_idx);
+    }
+
+    bool checkTrajPtCol(const double pt[3]) { return radiusSearch(pt) < 0.0; }
+
+    int checkTrajPtCol(const float *pts, int64_t m, int64_t stride_floats, std::vector<uint8_t> &collides)
+    {
+        std::vector<float> r((size_t)m);
+        int rc = radiusSearch(pts, m, stride_floats, r.data());
+        if (rc != PC_OK) return rc;
+        collides.resize((size_t)m);
+        for (int64_t k = 0; k < m; k++) collides[(size_t)k] = r[(size_t)k] < 0.f;
+        return PC_OK;
+    }
+
+    // checkSafeTrajectory for a batch of piecewise Bezier trajectories (layout: pc_clearance_batch in pc_index.h).
+    // first_hit[t] >= 0  <=>  the reference's checkSafeTrajectory(stop_time) returns true for trajectory t.
+    int checkSafeTrajectory(const std::vector<pc_traj> &traj, const std::vector<int32_t> &seg_order, const std::vector<double> &seg_T,
+                            const std::vector<int64_t> &seg_coef_off, const std::vector<double> &coef, double stop_time,
+                            std::vector<int32_t> &first_hit, std::vector<float> *min_radius = nullptr, double dt = 0.02)
+    {
+        first_hit.resize(traj.size());
+        if (min_radius) min_radius->resize(traj.size());
+        return pc_clearance_batch(ix_, traj.data(), (int64_t)traj.size(), seg_order.data(), seg_T.data(), seg_coef_off.data(),
+                                  (int64_t)seg_order.size(), coef.data(), (int64_t)coef.size(), PC_HOST, dt, stop_time, &params_,
+                                  first_hit.data(), min_radius ? min_radius->data() : nullptr, nullptr);
+    }
+
+    pc_index *handle() { return ix_; }
+    const pc_radius_params &params() const { return params_; }
+    const char *lastError() const { return pc_last_error(ix_); }
+
+    double safety_margin = 0.0;     // kept for the planner's own node rejection (corridor_finder.cpp:732), unused here
+    bool cloud_empty = true;
+
+private:
+    void check(int rc) const
+    {
+        if (rc != PC_OK) throw std::runtime_error(std::string("pcindex: ") + pc_last_error(ix_));
+    }
+    pc_index *ix_ = nullptr;
+    pc_radius_params params_;
+};
+
+}  // namespace pc
+#endif  // PC_CORRIDOR_HPP_

@@ -612,3 +612,4 @@ extern "C" int pc_radius_batch(pc_index *ix, const float *q_xyz, int64_t m, int6
 #include "range_host.inl"
 #include "clearance_host.inl"
 #include "comm_host.inl"
+#include "kd_compat.inl"
