@@ -71,7 +71,7 @@ struct pc_index {
     int64_t launches = 0;
     bool profile = false, profiled = false;
     // tuning knobs (environment: PC_QUERY_KERNEL, PC_SORT_BITS, PC_MIN_IDLE), see DESIGN.md "Query kernel variants"
-    int query_kernel = 3;     // 1 = one thread per query, 2 = persistent warps with lane refill, 3 = warp packets (ordered batches)
+    int query_kernel = 3;     // 1 = thread per query, 2 = persistent lane refill, 3 = warp packets (ordered batches)
     int sort_bits = 24;       // radix-sorted key width of the batch ordering pass (0 = never order)
     int min_idle = 8;         // persistent kernel: refill once this many lanes are idle
     char err[256] = "";
@@ -475,7 +475,7 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
     if (prof) PC_CUDA(ix, cudaEventRecord(L.t1, L.stream));
     pc_tree T = pc_tree_of(ix);
     const int64_t want = (m + PC_QUERY_THREADS - 1) / PC_QUERY_THREADS;
-    if (ix->query_kernel == 3 && perm) {
+    if (ix->query_kernel >= 3 && perm) {
         // Morton-ordered batch: one warp walks the tree once for its 32 neighbouring queries
         const int grid = (int)want;
         if (A.kind == PC_Q_NEAREST)

@@ -306,6 +306,11 @@ pc_query_persist_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q,
 // own query against it; a subtree is entered when ANY lane still needs it (ballot), the nearer child is chosen by
 // majority vote.  Control flow is warp-uniform, so all 32 lanes are active at every step and there is no per-lane
 // stack in local memory; the price is that a lane also visits nodes only its neighbours needed.
+// Tried and dropped (profiles/r1_sweep3*, r1_sweep4*): rejecting stale stack entries with a per-entry minimum
+// distance and __reduce_min/max_sync (3 % slower: entries are rarely stale), and a "wide" variant that tests the 32
+// descendants five levels down against the packet's bounding box, one per lane (40 % slower: one lane whose
+// search radius stays at the bound keeps the whole packet's bound large, so far too many leaves survive the
+// conservative test and need a per-query re-test).
 template <int KIND>
 __global__ void __launch_bounds__(PC_QUERY_THREADS)
 pc_query_packet_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, int64_t m, int qstride,
@@ -331,21 +336,16 @@ pc_query_packet_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, 
     }
     if (__ballot_sync(PC_FULL_MASK, valid) == 0) return;
 
-    // warp stack: entry i lives in lane i -- node id and the smallest box distance any interested lane had when it
-    // was pushed (float bits; distances are >= 0 so the unsigned order is the float order)
-    uint32_t my_entry = 0, my_dmin = 0;
+    uint32_t my_entry = 0;      // warp stack: entry i lives in lane i
     int sp = 0;
     uint32_t node = 1;
-    // largest threshold of any lane: an entry whose dmin exceeds it is needed by nobody any more
-    uint32_t wmax = __reduce_max_sync(PC_FULL_MASK, b.thr < 0.f ? 0u : __float_as_uint(b.thr));
     for (;;) {
         const float4 *pair = T.nodes + 4ull * node;
         const float4 lo0 = __ldg(pair), hi0 = __ldg(pair + 1), lo1 = __ldg(pair + 2), hi1 = __ldg(pair + 3);
         const float d0 = pc_box_d2(lo0, hi0, qx, qy, qz);
         const float d1 = pc_box_d2(lo1, hi1, qx, qy, qz);
-        const bool want0 = d0 <= b.thr, want1 = d1 <= b.thr;
-        const uint32_t w0 = __ballot_sync(PC_FULL_MASK, want0);
-        const uint32_t w1 = __ballot_sync(PC_FULL_MASK, want1);
+        const uint32_t w0 = __ballot_sync(PC_FULL_MASK, d0 <= b.thr);
+        const uint32_t w1 = __ballot_sync(PC_FULL_MASK, d1 <= b.thr);
         const uint32_t c0 = 2u * node;
         bool pop = true;
         if (w0 | w1) {
@@ -358,26 +358,16 @@ pc_query_packet_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, 
                 pc_scan_leaf(T.points + (size_t)(cn - T.P) * PC_LEAF, qx, qy, qz, b);
                 if (both && __ballot_sync(PC_FULL_MASK, (first0 ? d1 : d0) <= b.thr))
                     pc_scan_leaf(T.points + (size_t)(cf - T.P) * PC_LEAF, qx, qy, qz, b);
-                wmax = __reduce_max_sync(PC_FULL_MASK, b.thr < 0.f ? 0u : __float_as_uint(b.thr));
             } else {
-                if (both) {
-                    const float df = first0 ? d1 : d0;
-                    const bool wantf = first0 ? want1 : want0;
-                    const uint32_t dmin = __reduce_min_sync(PC_FULL_MASK, wantf ? __float_as_uint(df) : 0x7f800000u);
-                    if (lane == sp) { my_entry = cf; my_dmin = dmin; }
-                    sp++;
-                }
+                if (both) { if (lane == sp) my_entry = cf; sp++; }
                 node = cn;
                 pop = false;
             }
         }
         if (pop) {
-            bool found = false;
-            while (sp > 0) {
-                sp--;
-                if (__shfl_sync(PC_FULL_MASK, my_dmin, sp) <= wmax) { node = __shfl_sync(PC_FULL_MASK, my_entry, sp); found = true; break; }
-            }
-            if (!found) break;
+            if (sp == 0) break;
+            sp--;
+            node = __shfl_sync(PC_FULL_MASK, my_entry, sp);
         }
     }
     if (valid) pc_write_result<KIND>(R, b, k, out_idx, out_f);

@@ -196,3 +196,33 @@ def test_one_million_points_properties(ix):
     far = np.sqrt(((q.astype(np.float64) - np.array([0, 0, 2.0])) ** 2).sum(1)) > 31.5
     expect[far] = 1.25
     assert (r == expect.astype(np.float32)).all()
+
+
+def test_five_million_points_64bit_keys():
+    """C4-sized cloud: above 4 Mi points the build switches to 63-bit Morton keys (uint64 radix sort, 5 passes)."""
+    pts, half = synth.forest_cloud(5_000_000, seed=2, variant="J", return_half=True)
+    h = PointCloudIndex(max_points=len(pts), device=0)
+    try:
+        h.build(pts)
+        assert h.size == len(pts)
+        v = h.view()
+        assert v.n_leaves == (len(pts) + 3) // 4 and v.leaf_base >= v.n_leaves
+        assert np.allclose(np.array(v.bbox_lo[:]), pts.min(0)) and np.allclose(np.array(v.bbox_hi[:]), pts.max(0))
+        sel = np.random.default_rng(1).permutation(len(pts))[:400_000]
+        idx, d2 = h.nearest(pts[sel])
+        assert (d2 == 0).all() and (idx == sel).all()            # every sampled point finds itself
+        q = synth.rrt_queries(300_000, half, seed=3)
+        idx, d2 = h.nearest(q)
+        bi, bd, ties = oracle.brute_nearest(pts, q[:1500])       # independent fp64 brute force
+        assert (idx[:1500] == bi).all() and (d2[:1500] == bd.astype(np.float32)).all()
+        idx_u, d2_u = h.nearest(q, flags=PC_QUERY_UNSORTED)
+        assert (idx_u == idx).all() and (d2_u == d2).all()
+        P = PcRadiusParams.make(start=(0, 0, 2), **SIMULATION)
+        r = h.radius(q, P, flags=PC_RADIUS_FULL_NN)
+        exact = oracle.pair_d2(pts, q, idx.astype(np.int64))
+        expect = np.minimum(np.sqrt(exact) - 0.0, 5.0)
+        far = np.sqrt(((q.astype(np.float64) - np.array([0, 0, 2.0])) ** 2).sum(1)) > 35.0
+        expect[far] = 5.0
+        assert (r == expect.astype(np.float32)).all()
+    finally:
+        h.close()
