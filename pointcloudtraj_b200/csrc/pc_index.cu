@@ -21,7 +21,7 @@
 
 #define PC_VERSION_STRING "pcindex 0.1 (sm_100a)"
 #define PC_PIPE_LANES 3                 // concurrent H2D / kernel / D2H chunks for PC_HOST calls
-#define PC_HOST_CHUNK (1 << 20)         // queries per pipelined chunk
+#define PC_HOST_CHUNK (1 << 21)         // queries per pipelined chunk (scripts/e2e_sweep.py: 2 Mi is the optimum for 10 M batches)
 #define PC_SORT_MIN_BATCH (1 << 15)     // PC_QUERY_AUTO sorts batches at least this large
 
 static thread_local char g_create_error[256] = "";
@@ -74,6 +74,7 @@ struct pc_index {
     int query_kernel = 3;     // 1 = thread per query, 2 = persistent lane refill, 3 = warp packets (ordered batches)
     int sort_bits = 24;       // radix-sorted key width of the batch ordering pass (0 = never order)
     int min_idle = 8;         // persistent kernel: refill once this many lanes are idle
+    int64_t host_chunk = PC_HOST_CHUNK;   // PC_HOST calls: queries per pipelined chunk (PC_HOST_CHUNK_QUERIES)
     char err[256] = "";
 };
 
@@ -175,6 +176,7 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         ix->sm_count = prop.multiProcessorCount;
         if (const char *v = getenv("PC_QUERY_KERNEL")) { int b_ = atoi(v); ix->query_kernel = (b_ >= 1 && b_ <= 3) ? b_ : 3; }
         if (const char *v = getenv("PC_SORT_BITS")) { int b_ = atoi(v); ix->sort_bits = b_ <= 0 ? 0 : (b_ <= 16 ? 16 : (b_ <= 24 ? 24 : 32)); }
+        if (const char *v = getenv("PC_HOST_CHUNK_QUERIES")) { long long b_ = atoll(v); if (b_ >= 1024) ix->host_chunk = b_; }
         if (const char *v = getenv("PC_MIN_IDLE")) { int b_ = atoi(v); ix->min_idle = b_ < 1 ? 1 : (b_ > 32 ? 32 : b_); }
         if (cuda_stream) { ix->stream = (cudaStream_t)cuda_stream; ix->own_stream = false; }
         else { TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking)); ix->own_stream = true; }
@@ -537,7 +539,7 @@ static int pc_query_dispatch(pc_index *ix, const pc_qargs &A, const float *q, in
     // order the side lanes after everything already queued on the handle's stream (e.g. an asynchronous build)
     PC_CUDA(ix, cudaEventRecord(ix->ev_ready, ix->stream));
     for (int l = 1; l < PC_PIPE_LANES; l++) PC_CUDA(ix, cudaStreamWaitEvent(ix->lane[l].stream, ix->ev_ready, 0));
-    const int64_t chunk = PC_HOST_CHUNK;
+    const int64_t chunk = ix->host_chunk;
     int li = 0;
     for (int64_t off = 0; off < m; off += chunk, li = (li + 1) % PC_PIPE_LANES) {
         pc_lane &L = ix->lane[li];

@@ -20,11 +20,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def build_variant(leaf):
-    out = os.path.join(ROOT, "gpurun_out", f"libpcindex_leaf{leaf}.so")
+def build_variant(leaf, defs=""):
+    tag = defs.replace("-D", "").replace("=", "").replace(" ", "_")
+    out = os.path.join(ROOT, "gpurun_out", f"libpcindex_leaf{leaf}{tag}.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     cmd = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", f"-DPC_LEAF={leaf}", "-o", out,
+           "-Xcompiler", "-fPIC", "-shared", f"-DPC_LEAF={leaf}"] + defs.split() + ["-o", out,
            os.path.join(ROOT, "pointcloudtraj_b200", "csrc", "pc_index.cu"), "-lcudart", "-ldl"]
     subprocess.run(cmd, check=True, capture_output=True)
     return out
@@ -38,6 +39,7 @@ def main():
     ap.add_argument("--bits", default="16,24,32")
     ap.add_argument("--idle", default="4,8,16")
     ap.add_argument("--reps", type=int, default=4)
+    ap.add_argument("--defs", default="", help="extra nvcc -D flags, e.g. '-DPC_PACKET_ORDER=0'")
     args = ap.parse_args()
     import torch
     from pointcloudtraj_b200 import _lib, synth
@@ -59,7 +61,7 @@ def main():
     print(f"# {M} queries, 1M-point forest J; times in ms (median of {args.reps}); r = pc_radius_batch, n = pc_nearest_batch")
     print(f"{'leaf':>4s} {'kern':>4s} {'bits':>4s} {'idle':>4s} {'build':>7s} {'r_order':>8s} {'r_search':>9s} {'r_Gq/s':>7s} {'n_order':>8s} {'n_search':>9s} {'n_Gq/s':>7s} ok")
     for leaf in [int(v) for v in args.leaves.split(",")]:
-        path = build_variant(leaf)
+        path = build_variant(leaf, args.defs)
         _lib._lib = None
         _lib.LIB_PATH = path
         L = _lib.load()
