@@ -27,7 +27,10 @@
  * arguments live in that space.  PC_DEVICE calls are asynchronous on the handle's stream (call
  * pc_index_sync or synchronise the stream you passed to pc_index_create); PC_HOST calls return
  * when the results are in the caller's host buffers (pinned buffers from pc_host_alloc make the
- * copies asynchronous and pipelined with the kernels).
+ * copies asynchronous and pipelined with the kernels).  PC_HOST_ASYNC calls (pinned host buffers) only enqueue the
+ * batch -- copy in, kernels, copy out -- on one of three internal streams in turn and return; results are valid after
+ * pc_index_sync.  Back-to-back PC_HOST_ASYNC batches overlap their PCIe copies with each other's kernels; the caller
+ * must give every batch in flight its own buffers.
  *
  * Exactness contract (DESIGN.md "Tie rule"): out_idx is the point that minimises the reference's
  * fp64 expression d2 = ((px-qx)^2 + (py-qy)^2) + (pz-qz)^2 (float32 inputs widened to double,
@@ -53,6 +56,7 @@ extern "C" {
 
 #define PC_HOST   0
 #define PC_DEVICE 1
+#define PC_HOST_ASYNC 2   /* pc_nearest_batch / pc_radius_batch only: host buffers (pinned), the call returns at once */
 
 /* flags for pc_radius_batch / pc_clearance_batch */
 #define PC_RADIUS_BOUNDED   0  /* default: search only within max_radius + search_margin (exact for the radius) */

@@ -95,22 +95,33 @@ pc_clearance_kernel(pc_tree T, pc_radius_dev R, const pc_traj_dev *__restrict__ 
         }
         __syncthreads();
         const int cnt = s_count;
-        for (int k = threadIdx.x; k < cnt; k += PC_CLR_THREADS) {
-            const int32_t sg = s_seg[k];
-            const double Ti = seg_T[sg];
-            double pos[3];
-            pc_bezier_pos(coef + seg_coef_off[sg], seg_order[sg], __ddiv_rn(s_t[k], Ti), Ti, pos);
-            double radius;
-            if (T.n_points == 0 || pc_radius_early_out(pos[0], pos[1], pos[2], R)) {
-                radius = __dsub_rn(R.max_radius, R.search_margin);
-            } else {
-                const float qx = (float)pos[0], qy = (float)pos[1], qz = (float)pos[2];
-                pc_best b; b.d2 = INFINITY; b.idx = -1; b.thr = R.bound_thr;
-                pc_nearest_traverse(T, qx, qy, qz, b);
-                radius = pc_radius_epilogue(b, R);
+        // a warp takes 32 CONSECUTIVE samples: they are a few centimetres apart, i.e. an ideal packet
+        for (int base = (threadIdx.x >> 5) * 32; base < cnt; base += PC_CLR_THREADS) {
+            const int k = base + (threadIdx.x & 31);
+            const bool have = k < cnt;
+            double radius = INFINITY;
+            pc_best b; b.d2 = INFINITY; b.idx = -1; b.thr = -1.0f;
+            float qx = 0.f, qy = 0.f, qz = 0.f;
+            bool search = false;
+            if (have) {
+                const int32_t sg = s_seg[k];
+                const double Ti = seg_T[sg];
+                double pos[3];
+                pc_bezier_pos(coef + seg_coef_off[sg], seg_order[sg], __ddiv_rn(s_t[k], Ti), Ti, pos);
+                if (T.n_points == 0 || pc_radius_early_out(pos[0], pos[1], pos[2], R)) {
+                    radius = __dsub_rn(R.max_radius, R.search_margin);
+                } else {
+                    qx = (float)pos[0]; qy = (float)pos[1]; qz = (float)pos[2];
+                    search = qx == qx && qy == qy && qz == qz;
+                    if (search) b.thr = R.bound_thr;
+                }
             }
-            my_min = fmin(my_min, radius);
-            if (radius < 0.0) atomicMin(&s_first_hit, (int)(chunk_base + k));
+            pc_packet_traverse(T, qx, qy, qz, b, threadIdx.x & 31);
+            if (have) {
+                if (search || !(radius < INFINITY)) radius = pc_radius_epilogue(b, R);
+                my_min = fmin(my_min, radius);
+                if (radius < 0.0) atomicMin(&s_first_hit, (int)(chunk_base + k));
+            }
         }
         chunk_base += cnt;
         __syncthreads();

@@ -141,5 +141,6 @@ extern "C" int pc_index_broadcast(pc_index *ix, pc_comm *c, int root)
         if ((int64_t)(bytes / sizeof(float4)) > ix->tree_cap) return pc_fail(ix, PC_ENOMEM, "pc_index_broadcast: arena too small");
         PC_NCCL(ix, g_nccl.Broadcast(ix->tree, ix->tree, bytes, 0 /* ncclInt8 */, root, c->nccl, st));
     }
+    PC_CUDA(ix, cudaEventRecord(ix->ev_ready, st));
     return PC_OK;
 }

@@ -76,6 +76,36 @@ __device__ __forceinline__ uint32_t pc_morton30(float x, float y, float z, const
     return pc_spread10(cx) | (pc_spread10(cy) << 1) | (pc_spread10(cz) << 2);
 }
 
+// 30-bit Hilbert index of a 10-bit cell (Skilling's transpose algorithm): consecutive indices are always adjacent
+// cells, unlike the Morton curve whose octant jumps put far-apart cells next to each other
+__device__ __forceinline__ uint32_t pc_hilbert30_cells(uint32_t x, uint32_t y, uint32_t z)
+{
+    uint32_t X[3] = { x, y, z };
+    const uint32_t M = 1u << 9;
+#pragma unroll
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {
+        const uint32_t P = Q - 1;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            if (X[i] & Q) X[0] ^= P;
+            else { const uint32_t t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+        }
+    }
+    X[1] ^= X[0];
+    X[2] ^= X[1];
+    uint32_t t = 0;
+#pragma unroll
+    for (uint32_t Q = M; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
+    X[0] ^= t; X[1] ^= t; X[2] ^= t;
+    return (pc_spread10(X[0]) << 2) | (pc_spread10(X[1]) << 1) | pc_spread10(X[2]);
+}
+
+__device__ __forceinline__ uint32_t pc_hilbert30(float x, float y, float z, const pc_frame &f)
+{
+    return pc_hilbert30_cells(pc_cell_coord(x, f.lo[0], f.inv_cell, f.max_cell), pc_cell_coord(y, f.lo[1], f.inv_cell, f.max_cell),
+                              pc_cell_coord(z, f.lo[2], f.inv_cell, f.max_cell));
+}
+
 __device__ __forceinline__ uint64_t pc_morton63(float x, float y, float z, const pc_frame &f)
 {
     uint64_t cx = pc_cell_coord(x, f.lo[0], f.inv_cell, f.max_cell);

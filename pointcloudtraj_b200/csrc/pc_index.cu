@@ -74,6 +74,7 @@ struct pc_index {
     int query_kernel = 3;     // 1 = thread per query, 2 = persistent lane refill, 3 = warp packets (ordered batches)
     int sort_bits = 24;       // radix-sorted key width of the batch ordering pass (0 = never order)
     int min_idle = 8;         // persistent kernel: refill once this many lanes are idle
+    int next_lane = 0;        // PC_HOST_ASYNC: lane of the next batch
     int64_t host_chunk = PC_HOST_CHUNK;   // PC_HOST calls: queries per pipelined chunk (PC_HOST_CHUNK_QUERIES)
     char err[256] = "";
 };
@@ -239,6 +240,7 @@ extern "C" int pc_index_sync(pc_index *ix)
     if (!ix) return PC_EINVAL;
     PC_CUDA(ix, cudaSetDevice(ix->device));
     PC_CUDA(ix, cudaStreamSynchronize(ix->stream));
+    for (int l = 1; l < PC_PIPE_LANES; l++) PC_CUDA(ix, cudaStreamSynchronize(ix->lane[l].stream));   // PC_HOST_ASYNC batches
     return PC_OK;
 }
 
@@ -309,6 +311,8 @@ extern "C" int pc_index_build(pc_index *ix, const float *xyz, int64_t n, int64_t
         if (rc != PC_OK) return rc;
     }
     cudaStream_t st = ix->stream;
+    // batches still in flight on the side lanes (PC_HOST_ASYNC) read the tree this build is about to overwrite
+    for (int l = 1; l < PC_PIPE_LANES; l++) PC_CUDA(ix, cudaStreamWaitEvent(st, ix->lane[l].done, 0));
     const int stride = (int)stride_floats;
     const float *src = xyz;
     if (space == PC_HOST) {
@@ -366,6 +370,7 @@ extern "C" int pc_index_build(pc_index *ix, const float *xyz, int64_t n, int64_t
         lvl0 += nl;
     }
     PC_CUDA(ix, cudaEventRecord(ix->ev_b1, st));
+    PC_CUDA(ix, cudaEventRecord(ix->ev_ready, st));
     ix->n = n; ix->n_leaves = n_leaves; ix->P = P; ix->build_timed = true;
     if (space == PC_HOST) PC_CUDA(ix, cudaStreamSynchronize(st));
     return PC_OK;
@@ -536,9 +541,24 @@ static int pc_query_dispatch(pc_index *ix, const pc_qargs &A, const float *q, in
     const int qs = (int)q_stride;
     if (space == PC_DEVICE) return pc_run_batch(ix, ix->lane[0], A, q, m, qs, out_idx, out_f);
 
-    // order the side lanes after everything already queued on the handle's stream (e.g. an asynchronous build)
-    PC_CUDA(ix, cudaEventRecord(ix->ev_ready, ix->stream));
+    // order the side lanes after the last (possibly still running) index build / broadcast on the handle's stream
     for (int l = 1; l < PC_PIPE_LANES; l++) PC_CUDA(ix, cudaStreamWaitEvent(ix->lane[l].stream, ix->ev_ready, 0));
+    if (space == PC_HOST_ASYNC) {
+        // the whole batch on the next lane, no wait: consecutive calls overlap their H2D / kernels / D2H
+        pc_lane &L = ix->lane[ix->next_lane];
+        ix->next_lane = (ix->next_lane + 1) % PC_PIPE_LANES;
+        int rc;
+        if ((rc = pc_grow(ix, &L.d_q, &L.q_cap, m * qs)) != PC_OK) return rc;
+        if (out_idx && (rc = pc_grow(ix, &L.d_i32, &L.i32_cap, m)) != PC_OK) return rc;
+        if (out_f && (rc = pc_grow(ix, &L.d_f32, &L.f32_cap, m)) != PC_OK) return rc;
+        PC_CUDA(ix, cudaMemcpyAsync(L.d_q, q, (size_t)m * qs * sizeof(float), cudaMemcpyHostToDevice, L.stream));
+        rc = pc_run_batch(ix, L, A, L.d_q, m, qs, out_idx ? L.d_i32 : nullptr, out_f ? L.d_f32 : nullptr);
+        if (rc != PC_OK) return rc;
+        if (out_idx) PC_CUDA(ix, cudaMemcpyAsync(out_idx, L.d_i32, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, L.stream));
+        if (out_f) PC_CUDA(ix, cudaMemcpyAsync(out_f, L.d_f32, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, L.stream));
+        PC_CUDA(ix, cudaEventRecord(L.done, L.stream));      // a later rebuild must wait for this batch
+        return PC_OK;
+    }
     const int64_t chunk = ix->host_chunk;
     int li = 0;
     for (int64_t off = 0; off < m; off += chunk, li = (li + 1) % PC_PIPE_LANES) {
@@ -561,7 +581,7 @@ static int pc_query_dispatch(pc_index *ix, const pc_qargs &A, const float *q, in
 static int pc_check_query_args(pc_index *ix, const char *fn, const float *q, int64_t m, int64_t q_stride, int space)
 {
     if (!ix) return PC_EINVAL;
-    if (m < 0 || (m > 0 && !q) || (q_stride != 3 && q_stride != 4) || (space != PC_HOST && space != PC_DEVICE))
+    if (m < 0 || (m > 0 && !q) || (q_stride != 3 && q_stride != 4) || (space != PC_HOST && space != PC_DEVICE && space != PC_HOST_ASYNC))
         return pc_fail(ix, PC_EINVAL, "%s: bad argument (m=%lld stride=%lld space=%d)", fn, (long long)m, (long long)q_stride, space);
     if (m > ((int64_t)1 << 32) - 1) return pc_fail(ix, PC_EINVAL, "%s: at most 2^32-1 queries per call", fn);
     return PC_OK;

@@ -13,6 +13,9 @@
 #include "build_kernels.cuh"
 
 #define PC_QUERY_THREADS 128
+#ifndef PC_QUERY_CURVE
+#define PC_QUERY_CURVE 1     // batch ordering curve: 0 = Morton, 1 = Hilbert
+#endif
 #ifndef PC_PACKET_ORDER
 #define PC_PACKET_ORDER 0
 #endif
@@ -314,31 +317,11 @@ pc_query_persist_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q,
 // descendants five levels down against the packet's bounding box, one per lane (40 % slower: one lane whose
 // search radius stays at the bound keeps the whole packet's bound large, so far too many leaves survive the
 // conservative test and need a per-query re-test).
-template <int KIND>
-__global__ void __launch_bounds__(PC_QUERY_THREADS)
-pc_query_packet_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, int64_t m, int qstride,
-                       const uint32_t *__restrict__ perm, const unsigned long long *__restrict__ m_eff,
-                       int32_t *__restrict__ out_idx, float *__restrict__ out_f)
+// The packet walk itself: must be called by all 32 lanes of a warp, converged; lanes without a query pass
+// b.thr < 0 and take part in the votes only.
+__device__ __forceinline__ void pc_packet_traverse(const pc_tree &T, float qx, float qy, float qz, pc_best &b, int lane)
 {
-    const int lane = threadIdx.x & 31;
-    const long long m_search = m_eff ? (long long)*m_eff : (long long)m;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t - lane >= m_search) return;                       // whole warp past the end
-    bool valid = t < m_search;
-    uint32_t k = 0;
-    float qx = 0.f, qy = 0.f, qz = 0.f;
-    pc_best b; b.d2 = INFINITY; b.idx = -1; b.thr = -1.0f;  // thr < 0: this lane needs nothing
-    if (valid) {
-        k = perm ? perm[t] : (uint32_t)t;
-        const float *qq = q + (size_t)k * qstride;
-        qx = qq[0]; qy = qq[1]; qz = qq[2];
-        bool search = T.n_points > 0;
-        if (KIND == PC_KIND_RADIUS && search && !m_eff && pc_radius_early_out((double)qx, (double)qy, (double)qz, R)) search = false;
-        if (search) b.thr = (KIND == PC_KIND_RADIUS) ? R.bound_thr : FLT_MAX;
-        else { pc_write_trivial<KIND>(R, k, out_idx, out_f); valid = false; }
-    }
-    if (__ballot_sync(PC_FULL_MASK, valid) == 0) return;
-
+    if (__ballot_sync(PC_FULL_MASK, b.thr >= 0.f) == 0) return;
     uint32_t my_entry = 0;      // warp stack: entry i lives in lane i
     int sp = 0;
     uint32_t node = 1;
@@ -379,6 +362,32 @@ pc_query_packet_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, 
             node = __shfl_sync(PC_FULL_MASK, my_entry, sp);
         }
     }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(PC_QUERY_THREADS)
+pc_query_packet_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, int64_t m, int qstride,
+                       const uint32_t *__restrict__ perm, const unsigned long long *__restrict__ m_eff,
+                       int32_t *__restrict__ out_idx, float *__restrict__ out_f)
+{
+    const int lane = threadIdx.x & 31;
+    const long long m_search = m_eff ? (long long)*m_eff : (long long)m;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t - lane >= m_search) return;                       // whole warp past the end
+    bool valid = t < m_search;
+    uint32_t k = 0;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    pc_best b; b.d2 = INFINITY; b.idx = -1; b.thr = -1.0f;  // thr < 0: this lane needs nothing
+    if (valid) {
+        k = perm ? perm[t] : (uint32_t)t;
+        const float *qq = q + (size_t)k * qstride;
+        qx = qq[0]; qy = qq[1]; qz = qq[2];
+        bool search = T.n_points > 0;
+        if (KIND == PC_KIND_RADIUS && search && !m_eff && pc_radius_early_out((double)qx, (double)qy, (double)qz, R)) search = false;
+        if (search) b.thr = (KIND == PC_KIND_RADIUS) ? R.bound_thr : FLT_MAX;
+        else { pc_write_trivial<KIND>(R, k, out_idx, out_f); valid = false; }
+    }
+    pc_packet_traverse(T, qx, qy, qz, b, lane);
     if (valid) pc_write_result<KIND>(R, b, k, out_idx, out_f);
 }
 
@@ -404,7 +413,12 @@ pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
             search = false;
             pc_write_trivial<KIND>(R, (uint32_t)i, out_idx, out_f);
         }
-        keys[i] = search ? (pc_morton30(x, y, z, f) >> drop_bits) : (0x3fffffffu >> drop_bits) + 1u;
+#if PC_QUERY_CURVE == 1
+        const uint32_t cell_key = pc_hilbert30(x, y, z, f);
+#else
+        const uint32_t cell_key = pc_morton30(x, y, z, f);
+#endif
+        keys[i] = search ? (cell_key >> drop_bits) : (0x3fffffffu >> drop_bits) + 1u;
         vals[i] = (uint32_t)i;
     }
     const int n = __syncthreads_count(search);

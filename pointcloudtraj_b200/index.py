@@ -133,6 +133,16 @@ class PointCloudIndex:
         self._check(self._L.pc_radius_batch(self._h, p, m, stride, space, flags, C.byref(params), pr, pi))
         return (r, idx) if want_idx else r
 
+    def radius_async(self, q_pinned, out_pinned, params: L.PcRadiusParams, flags=L.PC_RADIUS_BOUNDED):
+        """PC_HOST_ASYNC radius batch: q_pinned / out_pinned are numpy views of PINNED host memory (float32 (m,3|4) and
+        float32 (m,)); the call only enqueues the batch, results are valid after sync().  Give every batch in flight
+        its own buffers."""
+        if q_pinned.dtype != np.float32 or q_pinned.ndim != 2 or not q_pinned.flags.c_contiguous:
+            raise TypeError("q_pinned: contiguous float32 (m, 3|4)")
+        m, stride = q_pinned.shape
+        self._check(self._L.pc_radius_batch(self._h, C.c_void_p(q_pinned.ctypes.data), m, stride, L.PC_HOST_ASYNC, flags,
+                                            C.byref(params), C.c_void_p(out_pinned.ctypes.data), C.c_void_p(0)))
+
     def check_traj_pt_col(self, pts, params: L.PcRadiusParams):
         """safeRegionRrtStar::checkTrajPtCol (corridor_finder.cpp:412-416): radiusSearch(pt) < 0."""
         return self.radius(pts, params) < 0

@@ -226,3 +226,21 @@ def test_five_million_points_64bit_keys():
         assert (r == expect.astype(np.float32)).all()
     finally:
         h.close()
+
+
+def test_async_host_batches_match_blocking_calls(ix):
+    """PC_HOST_ASYNC: batches enqueued back to back on the internal streams, one wait; same results as blocking calls,
+    and a rebuild issued while batches are in flight waits for them."""
+    torch = pytest.importorskip("torch")
+    pts, half = synth.forest_cloud(120_000, seed=5, variant="J", return_half=True)
+    ix.build(pts)
+    P = PcRadiusParams.make(start=(0, 0, 2), **CLEAN_DEMO)
+    batches = [torch.from_numpy(synth.rrt_queries(90_000 + 1000 * k, half, seed=20 + k)).pin_memory() for k in range(5)]
+    outs = [torch.full((len(b),), -7.0).pin_memory() for b in batches]
+    for b, o in zip(batches, outs):
+        ix.radius_async(b.numpy(), o.numpy(), P)
+    ix.build(pts[::-1].copy())                     # must not disturb the batches still in flight
+    ix.sync()
+    ix.build(pts)
+    for b, o in zip(batches, outs):
+        assert (o.numpy() == ix.radius(b.numpy(), P)).all()
