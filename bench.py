@@ -31,6 +31,9 @@ CLOUD_SEED = 1
 PARAMS = dict(search_margin=0.25, max_radius=1.5, sample_range=30.0)   # clean_demo.launch:31-34
 BYTES_PER_QUERY = 16            # algorithmic: 12 B query (xyz float32) in + 4 B radius out
 FRAME_POINTS = 300_000          # C3 frame for the build-ms metric
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on the default workload, from the
+# `ncu --set full` capture summarised in profiles/r1_full_final.txt (547.9 MB + 105.4 MB); re-measure when the kernel changes
+NCU_TRAFFIC_BYTES = {10_000_000: 653_369_856}
 
 
 def parse():
@@ -341,7 +344,8 @@ def run_b200(args):
                 "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(args),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": None, "kernel": "pc_query_packet_kernel<RADIUS>", "kernel_ms": k_ms,
+                             "traffic": NCU_TRAFFIC_BYTES.get(M), "traffic_source": "profiles/r1_full_final.txt (ncu --set full, bytes per launch)",
+                             "kernel": "pc_query_packet_kernel<RADIUS>", "kernel_ms": k_ms,
                              "batch_order_ms": float(np.mean(order_ms)),
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                              "algorithmic_bytes_per_query": BYTES_PER_QUERY},
