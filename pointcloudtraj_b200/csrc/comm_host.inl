@@ -134,6 +134,8 @@ extern "C" int pc_index_broadcast(pc_index *ix, pc_comm *c, int root)
         ix->nodes = ix->tree;
         ix->points = ix->tree + 4 * h.P;
         if (h.n > 0) PC_CUDA(ix, cudaMemcpyAsync(ix->d_bbox, h.bbox, sizeof h.bbox, cudaMemcpyHostToDevice, st));
+        memcpy(ix->h_bbox, h.bbox, sizeof h.bbox);
+        ix->bbox_from_bcast = h.n > 0;
     }
     if (h.n > 0) {
         // boxes [0, 4P) and the leaf records [4P, 4P + PC_LEAF * n_leaves) are one contiguous span of the tree array

@@ -61,7 +61,9 @@ struct pc_index {
     float4 *points = nullptr;                       // = tree + 4P of the current build
     float4 *nodes = nullptr;                        // = tree
     cudaEvent_t ev_b0 = nullptr, ev_b1 = nullptr, ev_ready = nullptr;
+    uint32_t *h_bbox = nullptr;                      // pinned host copy of d_bbox, valid once ev_b1 has completed
     bool build_timed = false;
+    bool bbox_from_bcast = false;                    // h_bbox was filled by pc_index_broadcast (receiver side)
 
     pc_lane lane[PC_PIPE_LANES];
 
@@ -73,6 +75,7 @@ struct pc_index {
     // tuning knobs (environment: PC_QUERY_KERNEL, PC_SORT_BITS, PC_MIN_IDLE), see DESIGN.md "Query kernel variants"
     int query_kernel = 3;     // 1 = thread per query, 2 = persistent lane refill, 3 = warp packets (ordered batches)
     int sort_bits = 24;       // radix-sorted key width of the batch ordering pass (0 = never order)
+    bool sort_bits_auto = true;   // no PC_SORT_BITS in the environment: pick 24 or 32 from the batch density
     int min_idle = 8;         // persistent kernel: refill once this many lanes are idle
     int next_lane = 0;        // PC_HOST_ASYNC: lane of the next batch
     int64_t host_chunk = PC_HOST_CHUNK;   // PC_HOST calls: queries per pipelined chunk (PC_HOST_CHUNK_QUERIES)
@@ -176,7 +179,7 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         if (prop.major < 10) { rc = pc_fail(nullptr, PC_ECUDA, "pc_index_create: device is sm_%d%d, this library is built for sm_100a only", prop.major, prop.minor); break; }
         ix->sm_count = prop.multiProcessorCount;
         if (const char *v = getenv("PC_QUERY_KERNEL")) { int b_ = atoi(v); ix->query_kernel = (b_ >= 1 && b_ <= 3) ? b_ : 3; }
-        if (const char *v = getenv("PC_SORT_BITS")) { int b_ = atoi(v); ix->sort_bits = b_ <= 0 ? 0 : (b_ <= 16 ? 16 : (b_ <= 24 ? 24 : 32)); }
+        if (const char *v = getenv("PC_SORT_BITS")) { ix->sort_bits_auto = false; int b_ = atoi(v); ix->sort_bits = b_ <= 0 ? 0 : (b_ <= 16 ? 16 : (b_ <= 24 ? 24 : 32)); }
         if (const char *v = getenv("PC_HOST_CHUNK_QUERIES")) { long long b_ = atoll(v); if (b_ >= 1024) ix->host_chunk = b_; }
         if (const char *v = getenv("PC_MIN_IDLE")) { int b_ = atoi(v); ix->min_idle = b_ < 1 ? 1 : (b_ > 32 ? 32 : b_); }
         if (cuda_stream) { ix->stream = (cudaStream_t)cuda_stream; ix->own_stream = false; }
@@ -185,6 +188,7 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         TRY(cudaEventCreate(&ix->ev_b1));
         TRY(cudaEventCreateWithFlags(&ix->ev_ready, cudaEventDisableTiming));
         TRY(cudaMalloc((void **)&ix->d_bbox, 8 * sizeof(uint32_t)));
+        TRY(cudaHostAlloc((void **)&ix->h_bbox, 8 * sizeof(uint32_t), cudaHostAllocDefault));
         TRY(cudaMalloc((void **)&ix->digit_total, RS_RADIX * sizeof(uint32_t)));
         for (int l = 0; l < PC_PIPE_LANES; l++) {
             // lane 0 shares the handle's stream (PC_DEVICE calls are ordered on it); the others overlap copies
@@ -225,6 +229,7 @@ extern "C" void pc_index_destroy(pc_index *ix)
         if (L.t1) cudaEventDestroy(L.t1);
         if (L.t2) cudaEventDestroy(L.t2);
     }
+    if (ix->h_bbox) cudaFreeHost(ix->h_bbox);
     cudaFree(ix->d_xyz); cudaFree(ix->d_bbox); cudaFree(ix->keys_a); cudaFree(ix->keys_b);
     cudaFree(ix->vals_a); cudaFree(ix->vals_b); cudaFree(ix->tile_hist); cudaFree(ix->digit_total);
     cudaFree(ix->tree); cudaFree(ix->scratch);
@@ -369,9 +374,10 @@ extern "C" int pc_index_build(pc_index *ix, const float *xyz, int64_t n, int64_t
         for (int s = 0; s < nl; s++) cnt = (cnt + 1) >> 1;
         lvl0 += nl;
     }
+    PC_CUDA(ix, cudaMemcpyAsync(ix->h_bbox, ix->d_bbox, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PC_CUDA(ix, cudaEventRecord(ix->ev_b1, st));
     PC_CUDA(ix, cudaEventRecord(ix->ev_ready, st));
-    ix->n = n; ix->n_leaves = n_leaves; ix->P = P; ix->build_timed = true;
+    ix->n = n; ix->n_leaves = n_leaves; ix->P = P; ix->build_timed = true; ix->bbox_from_bcast = false;
     if (space == PC_HOST) PC_CUDA(ix, cudaStreamSynchronize(st));
     return PC_OK;
 }
@@ -438,9 +444,23 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
     int64_t need_hist = (int64_t)RS_RADIX * (rs_num_tiles<16>(m) + 1);
     int rc = pc_grow(ix, &L.tile_hist, &L.hist_cap, need_hist);
     if (rc != PC_OK) return rc;
-    // sort_bits (16 / 24 / 32) = radix-sorted key width: the top sort_bits - 1 Morton bits plus one bit for the
+    // sort_bits (16 / 24 / 32) = radix-sorted key width: the top sort_bits - 1 curve bits plus one bit for the
     // "already answered" key that sends early-outs to the end
-    const int bits = ix->sort_bits;
+    int bits = ix->sort_bits;
+    if (ix->sort_bits_auto && ((ix->build_timed && cudaEventQuery(ix->ev_b1) == cudaSuccess) || ix->bbox_from_bcast)) {
+        // 24 bits (8 per axis) order the batch well when its cells hold a handful of queries; a batch that is dense
+        // relative to the cloud's extent (large maps) needs the full 30-bit curve.  Estimated from the cloud's bounding
+        // box; if the build has not finished yet (no host copy of the box) the default stays.
+        float ext[3], emax = 0.f, vol = 1.f;
+        for (int a = 0; a < 3; a++) {
+            ext[a] = pc_ordered_to_float(ix->h_bbox[3 + a]) - pc_ordered_to_float(ix->h_bbox[a]);
+            emax = ext[a] > emax ? ext[a] : emax;
+        }
+        for (int a = 0; a < 3; a++) vol *= ext[a] > emax / 256.f ? ext[a] : emax / 256.f;
+        const float cell = emax / 256.f;
+        const double per_cell = vol > 0.f ? (double)m * cell * cell * cell / vol : 0.0;
+        bits = per_cell > 16.0 ? 32 : 24;
+    }
     const int drop = 31 - bits > 0 ? 31 - bits : 0;
     const int grid = (int)((m + 255) / 256);
     if (A.kind == PC_Q_RADIUS)

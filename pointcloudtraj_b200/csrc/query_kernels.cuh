@@ -16,6 +16,9 @@
 #ifndef PC_QUERY_CURVE
 #define PC_QUERY_CURVE 1     // batch ordering curve: 0 = Morton, 1 = Hilbert
 #endif
+#ifndef PC_PREFETCH_PUSH
+#define PC_PREFETCH_PUSH 0
+#endif
 #ifndef PC_PACKET_ORDER
 #define PC_PACKET_ORDER 0
 #endif
@@ -351,7 +354,15 @@ __device__ __forceinline__ void pc_packet_traverse(const pc_tree &T, float qx, f
                 if (both && __ballot_sync(PC_FULL_MASK, (first0 ? d1 : d0) <= b.thr))
                     pc_scan_leaf(T.points + (size_t)(cf - T.P) * PC_LEAF, qx, qy, qz, b);
             } else {
-                if (both) { if (lane == sp) my_entry = cf; sp++; }
+                if (both) {
+                    if (lane == sp) my_entry = cf;
+                    sp++;
+#if PC_PREFETCH_PUSH
+                    // the far child will be visited later: start pulling its record towards L2 now (matters when the
+                    // index is larger than L2 and a visit would otherwise wait for HBM)
+                    if (lane == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(T.nodes + 4ull * cf));
+#endif
+                }
                 node = cn;
                 pop = false;
             }

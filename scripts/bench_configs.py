@@ -80,7 +80,12 @@ def c1_like(name, n_pts, n_q, seed):
     for _ in range(5):
         ix.radius(q, P)
     host_ms = (time.perf_counter() - t0) / 5 * 1e3
+    # fixed-radius range queries (kd_nearest_range3), r = 1 m, host buffers, wall clock incl. both passes and copies
+    t0 = time.perf_counter()
+    off, lst = ix.range(q, 1.0)
+    range_ms = (time.perf_counter() - t0) * 1e3
     print(json.dumps({"config": name, "points": n_pts, "queries": n_q, "index_build_ms": build_ms,
+                      "range_r1_ms_host_buffers": range_ms, "range_r1_qps": n_q / range_ms * 1e3, "range_r1_mean_hits": float(off[-1]) / n_q,
                       "nearest_ms": nn_ms, "nearest_qps": n_q / nn_ms * 1e3, "radius_ms": rad_ms, "radius_qps": n_q / rad_ms * 1e3,
                       "radius_host_buffers_ms": host_ms, "parity_spot_check": brute_check(t_pts, t_q, idx, d2)}))
     ix.close()
