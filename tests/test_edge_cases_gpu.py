@@ -1,0 +1,111 @@
+"""GPU edge cases: degenerate clouds, far / non-finite queries, argument validation, error reporting."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from pointcloudtraj_b200 import (PC_QUERY_SORTED, PC_QUERY_UNSORTED, PC_RADIUS_FULL_NN, PcError, PcRadiusParams,
+                                 PointCloudIndex, synth)
+from pointcloudtraj_b200 import _lib as L
+from parity import check_lowest_index_everywhere
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ix():
+    h = PointCloudIndex(max_points=0, device=0)      # grows on demand: exercises the arena re-allocation path
+    yield h
+    h.close()
+
+
+def test_all_points_identical(ix):
+    pts = np.tile(np.array([[1.5, -2.0, 0.75]], np.float32), (5000, 1))
+    q = synth.rrt_queries(40_000, 4.0, seed=1)
+    ix.build(pts)
+    for flags in (PC_QUERY_UNSORTED, PC_QUERY_SORTED):
+        idx, d2 = ix.nearest(q, flags=flags)
+        assert (idx == 0).all()                                  # 5000 exact ties: lowest index
+        assert (d2 == oracle.pair_d2(pts, q, np.zeros(len(q), np.int64)).astype(np.float32)).all()
+    off, lst = ix.range(q[:50], 100.0)
+    assert (np.diff(off) == 5000).all() and (lst[:5000] == np.arange(5000)).all()
+
+
+def test_collinear_and_planar_clouds(ix):
+    rng = np.random.default_rng(3)
+    line = np.zeros((20_000, 3), np.float32)
+    line[:, 0] = rng.uniform(-50, 50, len(line))                  # all on the x axis: boxes degenerate in y and z
+    plane = np.zeros((20_000, 3), np.float32)
+    plane[:, :2] = rng.uniform(-5, 5, (len(plane), 2))
+    q = synth.rrt_queries(33_000, 6.0, seed=2, z=(-3, 3))
+    for pts in (line, plane):
+        ix.build(pts)
+        idx, d2 = ix.nearest(q)
+        check_lowest_index_everywhere(pts, q[:3000], idx[:3000])
+        bi, bd, _ = oracle.brute_nearest(pts, q[:3000])
+        assert (d2[:3000] == bd.astype(np.float32)).all()
+
+
+def test_far_and_huge_queries(ix):
+    pts = synth.uniform_cloud(10_000, half=5.0, seed=4)
+    ix.build(pts)
+    q = np.array([[1e6, 0, 0], [-1e6, 1e6, -1e6], [0, 0, 1e9], [3e4, -3e4, 2.0]], np.float32)
+    q = np.concatenate([q, synth.rrt_queries(40_000, 5.0, seed=5)])      # mixed into an ordered batch
+    idx, d2 = ix.nearest(q)
+    bi, bd, _ = oracle.brute_nearest(pts, q[:64])
+    assert (idx[:64] == bi).all() and (d2[:64] == bd.astype(np.float32)).all()
+    P = PcRadiusParams.make(0.25, 1.5, -1.0, (0, 0, 0))                   # sensing-range early-out disabled
+    r = ix.radius(q[:4], P)
+    assert (r == np.float32(1.5)).all()                                   # far from everything: clamped
+
+
+def test_non_finite_queries_do_not_poison_their_neighbours(ix):
+    pts = synth.uniform_cloud(20_000, half=5.0, seed=6)
+    ix.build(pts)
+    q = synth.rrt_queries(50_000, 5.0, seed=7)
+    ref_idx, ref_d2 = ix.nearest(q)
+    bad = q.copy()
+    rows = np.arange(0, len(q), 97)
+    bad[rows, 0] = np.nan
+    bad[rows[::2], 1] = np.inf
+    idx, d2 = ix.nearest(bad)
+    good = np.ones(len(q), bool)
+    good[rows] = False
+    assert (idx[good] == ref_idx[good]).all() and (d2[good] == ref_d2[good]).all()
+    assert (idx[rows[1::2]] == -1).all()                                   # NaN query: no neighbour (documented)
+
+
+def test_argument_validation_and_error_strings(ix):
+    lib = ix._L
+    pts = synth.uniform_cloud(100, seed=1)
+    ix.build(pts)
+    q = synth.rrt_queries(10, 5.0, seed=1)
+    out = np.empty(10, np.int32)
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    assert lib.pc_nearest_batch(ix._h, vp(q), 10, 5, 0, 0, vp(out), None) == L.PC_EINVAL         # stride must be 3 or 4
+    assert b"stride" in lib.pc_last_error(ix._h)
+    assert lib.pc_nearest_batch(ix._h, vp(q), -1, 3, 0, 0, vp(out), None) == L.PC_EINVAL
+    assert lib.pc_nearest_batch(ix._h, None, 10, 3, 0, 0, vp(out), None) == L.PC_EINVAL
+    assert lib.pc_nearest_batch(ix._h, vp(q), 10, 3, 7, 0, vp(out), None) == L.PC_EINVAL         # unknown memory space
+    assert lib.pc_index_build(ix._h, vp(pts), 100, 2, 0) == L.PC_EINVAL
+    assert lib.pc_radius_batch(ix._h, vp(q), 10, 3, 0, 0, None, vp(out), None) == L.PC_EINVAL      # params required
+    assert lib.pc_nearest_batch(ix._h, vp(q), 0, 3, 0, 0, None, None) == L.PC_OK                   # empty batch is legal
+    assert ix.size == 100                                                                         # failed calls changed nothing
+    h = C.c_void_p()
+    assert lib.pc_index_create(C.byref(h), 99, 10, None) == L.PC_EINVAL                            # no such device
+    with pytest.raises(PcError):
+        ix.clearance([0, 1], [4], [-1.0], [0, 15], np.zeros(15), PcRadiusParams.make())            # T <= 0
+
+
+def test_arena_growth_and_shrink(ix):
+    sizes = [10, 70_000, 300, 2_100_000, 5]
+    for n in sizes:
+        pts = synth.uniform_cloud(n, half=6.0, seed=n)
+        q = synth.rrt_queries(2000, 6.0, seed=n + 1)
+        ix.build(pts)
+        idx, _ = ix.nearest(q)
+        check_lowest_index_everywhere(pts, q[:300], idx[:300])
+    P = PcRadiusParams.make(0.25, 1.5, 30.0, (0, 0, 2))
+    r, i = ix.radius(q, P, flags=PC_RADIUS_FULL_NN, want_idx=True)
+    assert (i == idx).all()
