@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "pc_nearest_batch", "pc_radius_batch", "pc_range_batch", "pc_clearance_batch",
     "pc_host_alloc", "pc_host_free",
     "pc_comm_unique_id", "pc_comm_init", "pc_comm_destroy", "pc_index_broadcast", "pc_shard_range",
-    "pc_launch_count", "pc_profile_enable", "pc_profile_last_batch",
+    "pc_launch_count", "pc_profile_enable", "pc_profile_last_batch", "pc_batch_shard",
 ]
 
 
@@ -104,6 +104,7 @@ def load():
     L.pc_shard_range.restype = None
     L.pc_launch_count.argtypes = [vp, i32]
     L.pc_launch_count.restype = i64
+    L.pc_batch_shard.argtypes = [vp, i32, i32]
     L.pc_profile_enable.argtypes = [vp, i32]
     L.pc_profile_last_batch.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     _lib = L

@@ -37,6 +37,7 @@ struct pc_lane {
     uint32_t *tile_hist = nullptr; int64_t hist_cap = 0;
     uint32_t *digit_total = nullptr;
     unsigned long long *counter = nullptr;                   // work counter of the persistent query kernel
+    uint32_t *shard_hist = nullptr; int64_t shard_cap = 0;   // pc_batch_shard: curve histogram + the rank's bin range
     cudaEvent_t done = nullptr;
     cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr;   // profiling: batch start / ordered / searched
 };
@@ -78,6 +79,7 @@ struct pc_index {
     bool sort_bits_auto = true;   // no PC_SORT_BITS in the environment: pick 24 or 32 from the batch density
     int min_idle = 8;         // persistent kernel: refill once this many lanes are idle
     int next_lane = 0;        // PC_HOST_ASYNC: lane of the next batch
+    int shard_rank = 0, shard_n = 1;   // pc_batch_shard
     int64_t host_chunk = PC_HOST_CHUNK;   // PC_HOST calls: queries per pipelined chunk (PC_HOST_CHUNK_QUERIES)
     char err[256] = "";
 };
@@ -223,7 +225,7 @@ extern "C" void pc_index_destroy(pc_index *ix)
         if (L.stream && L.own_stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
         cudaFree(L.d_q); cudaFree(L.d_i32); cudaFree(L.d_f32);
         cudaFree(L.keys_a); cudaFree(L.keys_b); cudaFree(L.vals_a); cudaFree(L.vals_b);
-        cudaFree(L.tile_hist); cudaFree(L.digit_total); cudaFree(L.counter);
+        cudaFree(L.tile_hist); cudaFree(L.digit_total); cudaFree(L.counter); cudaFree(L.shard_hist);
         if (L.done) cudaEventDestroy(L.done);
         if (L.t0) cudaEventDestroy(L.t0);
         if (L.t1) cudaEventDestroy(L.t1);
@@ -444,8 +446,8 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
     int64_t need_hist = (int64_t)RS_RADIX * (rs_num_tiles<16>(m) + 1);
     int rc = pc_grow(ix, &L.tile_hist, &L.hist_cap, need_hist);
     if (rc != PC_OK) return rc;
-    // sort_bits (16 / 24 / 32) = radix-sorted key width: the top sort_bits - 1 curve bits plus one bit for the
-    // "already answered" key that sends early-outs to the end
+    // sort_bits (16 / 24 / 32) = radix-sorted key width = how many of the top curve bits order the batch; queries that
+    // need no search (sensing-range early-outs) are answered by the key kernel and never enter the sort
     int bits = ix->sort_bits;
     if (ix->sort_bits_auto && ((ix->build_timed && cudaEventQuery(ix->ev_b1) == cudaSuccess) || ix->bbox_from_bcast)) {
         // 24 bits (8 per axis) order the batch well when its cells hold a handful of queries; a batch that is dense
@@ -461,15 +463,34 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
         const double per_cell = vol > 0.f ? (double)m * cell * cell * cell / vol : 0.0;
         bits = per_cell > 16.0 ? 32 : 24;
     }
-    const int drop = 31 - bits > 0 ? 31 - bits : 0;
+    const int drop = 30 - bits > 0 ? 30 - bits : 0;     // 24-bit sort = top 24 curve bits, 32-bit sort = all 30
     const int grid = (int)((m + 255) / 256);
-    if (A.kind == PC_Q_RADIUS)
+    if (ix->shard_n > 1) {
+        // spatial sharding: this rank answers its own stretch of the Hilbert curve (see query_kernels.cuh)
+        const int drop_s = 30 - bits > 0 ? 30 - bits : 0;
+        uint32_t *key_full = L.keys_b;                       // free until the first radix pass writes to it
+        uint32_t *hist = nullptr;
+        if ((rc = pc_grow(ix, &L.shard_hist, &L.shard_cap, PC_SHARD_BINS + 8)) != PC_OK) return rc;
+        hist = L.shard_hist;
+        PC_CUDA(ix, cudaMemsetAsync(hist, 0, (PC_SHARD_BINS + 8) * sizeof(uint32_t), L.stream));
+        const int pgrid = (int)(grid < ix->sm_count * 8 ? grid : ix->sm_count * 8);
+        if (A.kind == PC_Q_RADIUS)
+            pc_shard_key_kernel<PC_KIND_RADIUS><<<pgrid, 256, 0, L.stream>>>(d_q, m, qstride, ix->d_bbox, A.R, d_idx, d_f, key_full, hist);
+        else
+            pc_shard_key_kernel<PC_KIND_NEAREST><<<pgrid, 256, 0, L.stream>>>(d_q, m, qstride, ix->d_bbox, A.R, d_idx, d_f, key_full, hist);
+        pc_shard_split_kernel<<<1, 1024, 0, L.stream>>>(hist, ix->shard_rank, ix->shard_n, hist + PC_SHARD_BINS);
+        pc_shard_select_kernel<<<grid, 256, 0, L.stream>>>(key_full, m, hist + PC_SHARD_BINS, drop_s, L.keys_a, L.vals_a, L.counter + 1);
+        ix->launches += 3;
+        PC_CHECK_LAUNCH(ix);
+    } else if (A.kind == PC_Q_RADIUS)
         pc_query_key_kernel<PC_KIND_RADIUS><<<grid, 256, 0, L.stream>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1);
     else
         pc_query_key_kernel<PC_KIND_NEAREST><<<grid, 256, 0, L.stream>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1);
-    ix->launches++;
+    if (ix->shard_n <= 1) ix->launches++;
     PC_CHECK_LAUNCH(ix);
-    int which = rs_sort_pairs<uint32_t, 16>(L.keys_a, L.vals_a, L.keys_b, L.vals_b, m, 0, bits, L.tile_hist, L.digit_total, L.stream, &ix->launches);
+    // only the L.counter[1] compacted entries (device-side count <= m) are sorted
+    int which = rs_sort_pairs<uint32_t, 16>(L.keys_a, L.vals_a, L.keys_b, L.vals_b, m, 0, bits, L.tile_hist, L.digit_total, L.stream,
+                                            &ix->launches, L.counter + 1);
     PC_CHECK_LAUNCH(ix);
     *perm = which ? L.vals_b : L.vals_a;
     return PC_OK;
@@ -478,6 +499,7 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
 static bool pc_want_sort(const pc_index *ix, int flags, int64_t m)
 {
     if (ix->n == 0 || ix->sort_bits == 0) return false;
+    if (ix->shard_n > 1) return true;          // the share is selected by the ordering pass
     if (flags & PC_QUERY_SORTED) return true;
     if (flags & PC_QUERY_UNSORTED) return false;
     return m >= PC_SORT_MIN_BATCH;
@@ -529,6 +551,14 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
     return PC_OK;
 }
 
+extern "C" int pc_batch_shard(pc_index *ix, int rank, int n_ranks)
+{
+    if (!ix || n_ranks < 1 || rank < 0 || rank >= n_ranks) return pc_fail(ix, PC_EINVAL, "pc_batch_shard: bad argument");
+    ix->shard_rank = rank;
+    ix->shard_n = n_ranks;
+    return PC_OK;
+}
+
 extern "C" int pc_profile_enable(pc_index *ix, int on)
 {
     if (!ix) return PC_EINVAL;
@@ -572,6 +602,10 @@ static int pc_query_dispatch(pc_index *ix, const pc_qargs &A, const float *q, in
         if (out_idx && (rc = pc_grow(ix, &L.d_i32, &L.i32_cap, m)) != PC_OK) return rc;
         if (out_f && (rc = pc_grow(ix, &L.d_f32, &L.f32_cap, m)) != PC_OK) return rc;
         PC_CUDA(ix, cudaMemcpyAsync(L.d_q, q, (size_t)m * qs * sizeof(float), cudaMemcpyHostToDevice, L.stream));
+        if (ix->shard_n > 1) {
+            if (out_idx) PC_CUDA(ix, cudaMemcpyAsync(L.d_i32, out_idx, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, L.stream));
+            if (out_f) PC_CUDA(ix, cudaMemcpyAsync(L.d_f32, out_f, (size_t)m * sizeof(float), cudaMemcpyHostToDevice, L.stream));
+        }
         rc = pc_run_batch(ix, L, A, L.d_q, m, qs, out_idx ? L.d_i32 : nullptr, out_f ? L.d_f32 : nullptr);
         if (rc != PC_OK) return rc;
         if (out_idx) PC_CUDA(ix, cudaMemcpyAsync(out_idx, L.d_i32, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, L.stream));
@@ -589,6 +623,11 @@ static int pc_query_dispatch(pc_index *ix, const pc_qargs &A, const float *q, in
         if (out_idx && (rc = pc_grow(ix, &L.d_i32, &L.i32_cap, c, chunk)) != PC_OK) return rc;
         if (out_f && (rc = pc_grow(ix, &L.d_f32, &L.f32_cap, c, chunk)) != PC_OK) return rc;
         PC_CUDA(ix, cudaMemcpyAsync(L.d_q, q + off * qs, (size_t)c * qs * sizeof(float), cudaMemcpyHostToDevice, L.stream));
+        if (ix->shard_n > 1) {
+            // entries of other ranks' queries must come back untouched: stage the caller's current output contents
+            if (out_idx) PC_CUDA(ix, cudaMemcpyAsync(L.d_i32, out_idx + off, (size_t)c * sizeof(int32_t), cudaMemcpyHostToDevice, L.stream));
+            if (out_f) PC_CUDA(ix, cudaMemcpyAsync(L.d_f32, out_f + off, (size_t)c * sizeof(float), cudaMemcpyHostToDevice, L.stream));
+        }
         rc = pc_run_batch(ix, L, A, L.d_q, c, qs, out_idx ? L.d_i32 : nullptr, out_f ? L.d_f32 : nullptr);
         if (rc != PC_OK) return rc;
         if (out_idx) PC_CUDA(ix, cudaMemcpyAsync(out_idx + off, L.d_i32, (size_t)c * sizeof(int32_t), cudaMemcpyDeviceToHost, L.stream));

@@ -413,8 +413,12 @@ pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
                     pc_radius_dev R, int32_t *__restrict__ out_idx, float *__restrict__ out_f,
                     uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, unsigned long long *__restrict__ n_search)
 {
+    __shared__ uint32_t s_warp[8];
+    __shared__ unsigned long long s_base;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     bool search = false;
+    uint32_t key = 0;
     if (i < m) {
         const pc_frame f = pc_make_frame(bbox, 10);
         const float *p = q + i * qstride;
@@ -425,13 +429,116 @@ pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
             pc_write_trivial<KIND>(R, (uint32_t)i, out_idx, out_f);
         }
 #if PC_QUERY_CURVE == 1
-        const uint32_t cell_key = pc_hilbert30(x, y, z, f);
+        key = pc_hilbert30(x, y, z, f) >> drop_bits;
 #else
-        const uint32_t cell_key = pc_morton30(x, y, z, f);
+        key = pc_morton30(x, y, z, f) >> drop_bits;
 #endif
-        keys[i] = search ? (cell_key >> drop_bits) : (0x3fffffffu >> drop_bits) + 1u;
-        vals[i] = (uint32_t)i;
     }
-    const int n = __syncthreads_count(search);
-    if (threadIdx.x == 0 && n) atomicAdd(n_search, (unsigned long long)n);
+    // compact the queries that still need a search: only those are sorted and searched.  One atomic per CTA; the slot a
+    // query lands in depends on CTA scheduling, which changes the composition of packets but never a result.
+    const uint32_t mask = __ballot_sync(PC_FULL_MASK, search);
+    if (lane == 0) s_warp[warp] = __popc(mask);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < 8; w++) { const uint32_t c = s_warp[w]; s_warp[w] = tot; tot += c; }
+        s_base = tot ? atomicAdd(n_search, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    if (search) {
+        const unsigned long long pos = s_base + s_warp[warp] + __popc(mask & pc_lanemask_lt());
+        keys[pos] = key;
+        vals[pos] = (uint32_t)i;
+    }
+}
+
+// ---- spatial sharding of one batch across ranks (pc_batch_shard) -------------------------------------------------
+// Every rank receives the SAME batch and answers the queries of its own stretch of the Hilbert curve, so that a rank's
+// share is as dense in space as the whole batch (a contiguous slice of a random batch would be n_ranks times sparser,
+// and sparse packets walk more of the tree).  Three small kernels replace the key kernel:
+//   pc_shard_key_kernel   : curve key of every query (early-outs answered by every rank), 4096-bin histogram of the top
+//                           12 curve bits
+//   pc_shard_split_kernel : prefix over the bins -> the bin range whose cumulative count is nearest to this rank's
+//                           equal share (a pure function of the histogram: all ranks compute the same partition)
+//   pc_shard_select_kernel: compact the queries whose bin lies in the range
+#define PC_SHARD_BINS 4096
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+pc_shard_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const uint32_t *__restrict__ bbox,
+                    pc_radius_dev R, int32_t *__restrict__ out_idx, float *__restrict__ out_f,
+                    uint32_t *__restrict__ key_full, uint32_t *__restrict__ hist)
+{
+    __shared__ uint32_t s_hist[PC_SHARD_BINS];
+    for (int b = threadIdx.x; b < PC_SHARD_BINS; b += blockDim.x) s_hist[b] = 0;
+    __syncthreads();
+    const pc_frame f = pc_make_frame(bbox, 10);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        const float *p = q + i * qstride;
+        const float x = p[0], y = p[1], z = p[2];
+        uint32_t key = 0xffffffffu;                                   // no search needed
+        if (KIND == PC_KIND_RADIUS && pc_radius_early_out((double)x, (double)y, (double)z, R)) {
+            pc_write_trivial<KIND>(R, (uint32_t)i, out_idx, out_f);
+        } else {
+            key = pc_hilbert30(x, y, z, f);
+            atomicAdd(&s_hist[key >> 18], 1u);
+        }
+        key_full[i] = key;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < PC_SHARD_BINS; b += blockDim.x)
+        if (s_hist[b]) atomicAdd(&hist[b], s_hist[b]);
+}
+
+// one CTA of 1024 threads; range[0], range[1] = first and one-past-last bin owned by `rank`
+__global__ void __launch_bounds__(1024)
+pc_shard_split_kernel(const uint32_t *__restrict__ hist, int rank, int n_ranks, uint32_t *__restrict__ range)
+{
+    __shared__ unsigned long long s_cum[PC_SHARD_BINS + 1];
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int b = 0; b < PC_SHARD_BINS; b++) { s_cum[b] = run; run += hist[b]; }
+        s_cum[PC_SHARD_BINS] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        const int r = rank + (int)threadIdx.x;                          // boundary r: bins [0, cut_r) go to ranks < r
+        const unsigned long long total = s_cum[PC_SHARD_BINS];
+        uint32_t cut = r <= 0 ? 0u : (r >= n_ranks ? (uint32_t)PC_SHARD_BINS : 0u);
+        if (r > 0 && r < n_ranks) {
+            const unsigned long long target = total * (unsigned long long)r / (unsigned long long)n_ranks;
+            int lo = 0, hi = PC_SHARD_BINS;                             // first bin boundary with cumulative count >= target
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_cum[mid] < target) lo = mid + 1; else hi = mid; }
+            cut = (uint32_t)lo;
+        }
+        range[threadIdx.x] = cut;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pc_shard_select_kernel(const uint32_t *__restrict__ key_full, int64_t m, const uint32_t *__restrict__ range, int drop_bits,
+                       uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, unsigned long long *__restrict__ n_search)
+{
+    __shared__ uint32_t s_warp[8];
+    __shared__ unsigned long long s_base;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t key = 0xffffffffu;
+    if (i < m) key = key_full[i];
+    const uint32_t bin = key >> 18;
+    const bool mine = key != 0xffffffffu && bin >= range[0] && bin < range[1];
+    const uint32_t mask = __ballot_sync(PC_FULL_MASK, mine);
+    if (lane == 0) s_warp[warp] = __popc(mask);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < 8; w++) { const uint32_t c = s_warp[w]; s_warp[w] = tot; tot += c; }
+        s_base = tot ? atomicAdd(n_search, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    if (mine) {
+        const unsigned long long pos = s_base + s_warp[warp] + __popc(mask & pc_lanemask_lt());
+        keys[pos] = key >> drop_bits;
+        vals[pos] = (uint32_t)i;
+    }
 }

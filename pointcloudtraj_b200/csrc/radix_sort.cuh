@@ -26,8 +26,10 @@ __device__ __forceinline__ uint32_t rs_digit(KeyT k, int shift)
 // tile_hist layout: [digit][tile] so that a digit's row is contiguous for the scan
 template <typename KeyT, int ITEMS>
 __global__ void __launch_bounds__(RS_THREADS)
-rs_histogram(const KeyT *__restrict__ keys, int64_t n, int shift, uint32_t *__restrict__ tile_hist, int num_tiles)
+rs_histogram(const KeyT *__restrict__ keys, int64_t n, const unsigned long long *__restrict__ n_dev, int shift,
+             uint32_t *__restrict__ tile_hist, int num_tiles)
 {
+    if (n_dev && (int64_t)*n_dev < n) n = (int64_t)*n_dev;     // element count known only on the device (<= host bound)
     __shared__ uint32_t hist[RS_WARPS][RS_RADIX];
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < RS_WARPS * RS_RADIX; i += RS_THREADS) (&hist[0][0])[i] = 0;
@@ -81,9 +83,11 @@ rs_scan_rows(uint32_t *__restrict__ tile_hist, int num_tiles, uint32_t *__restri
 template <typename KeyT, int ITEMS>
 __global__ void __launch_bounds__(RS_THREADS)
 rs_scatter(const KeyT *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-           KeyT *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift,
-           const uint32_t *__restrict__ tile_prefix, int num_tiles, const uint32_t *__restrict__ digit_total)
+           KeyT *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, const unsigned long long *__restrict__ n_dev,
+           int shift, const uint32_t *__restrict__ tile_prefix, int num_tiles, const uint32_t *__restrict__ digit_total)
 {
+    if (n_dev && (int64_t)*n_dev < n) n = (int64_t)*n_dev;
+    if ((int64_t)blockIdx.x * (RS_THREADS * ITEMS) >= n) return;   // tile past the device-side count
     // counter[w][d]: first the running count of digit d seen by warp w, then its output base
     __shared__ uint32_t counter[RS_WARPS][RS_RADIX + 1];
     __shared__ uint32_t digit_base[RS_RADIX];
@@ -166,7 +170,7 @@ static inline int rs_num_tiles(int64_t n) { return (int)((n + (int64_t)RS_THREAD
 template <typename KeyT, int ITEMS>
 static int rs_sort_pairs(KeyT *keys_a, uint32_t *vals_a, KeyT *keys_b, uint32_t *vals_b, int64_t n,
                          int begin_bit, int end_bit, uint32_t *tile_hist, uint32_t *digit_total,
-                         cudaStream_t stream, int64_t *launches)
+                         cudaStream_t stream, int64_t *launches, const unsigned long long *n_dev = nullptr)
 {
     if (n <= 0) return 0;
     const int tiles = rs_num_tiles<ITEMS>(n);
@@ -174,9 +178,9 @@ static int rs_sort_pairs(KeyT *keys_a, uint32_t *vals_a, KeyT *keys_b, uint32_t 
     for (int shift = begin_bit; shift < end_bit; shift += 8) {
         KeyT *kin = which ? keys_b : keys_a, *kout = which ? keys_a : keys_b;
         uint32_t *vin = which ? vals_b : vals_a, *vout = which ? vals_a : vals_b;
-        rs_histogram<KeyT, ITEMS><<<tiles, RS_THREADS, 0, stream>>>(kin, n, shift, tile_hist, tiles);
+        rs_histogram<KeyT, ITEMS><<<tiles, RS_THREADS, 0, stream>>>(kin, n, n_dev, shift, tile_hist, tiles);
         rs_scan_rows<<<RS_RADIX, RS_THREADS, 0, stream>>>(tile_hist, tiles, digit_total);
-        rs_scatter<KeyT, ITEMS><<<tiles, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, n, shift, tile_hist, tiles, digit_total);
+        rs_scatter<KeyT, ITEMS><<<tiles, RS_THREADS, 0, stream>>>(kin, vin, kout, vout, n, n_dev, shift, tile_hist, tiles, digit_total);
         if (launches) *launches += 3;
         which ^= 1;
     }

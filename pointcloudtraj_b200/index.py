@@ -70,13 +70,17 @@ class PointCloudIndex:
             raise TypeError(f"{name}: expected float32 (n, 3|4)")
         return C.c_void_p(a.ctypes.data), a.shape[0], a.shape[1], L.PC_HOST, a, False
 
+    NOT_MINE_IDX = -2 ** 31        # shard mode: pre-fill of entries owned by other ranks (float outputs: NaN)
+
     def _out(self, m, dtype, torch_mode, ref=None):
+        shard = getattr(self, "_shard_n", 1) > 1
+        fill = (self.NOT_MINE_IDX if dtype == np.int32 else float("nan")) if shard else None
         if torch_mode:
             import torch
             tdt = {np.int32: torch.int32, np.float32: torch.float32, np.int64: torch.int64}[dtype]
-            t = torch.empty(m, dtype=tdt, device=ref.device)
+            t = torch.empty(m, dtype=tdt, device=ref.device) if fill is None else torch.full((m,), fill, dtype=tdt, device=ref.device)
             return t, C.c_void_p(t.data_ptr())
-        a = np.empty(m, dtype=dtype)
+        a = np.empty(m, dtype=dtype) if fill is None else np.full(m, fill, dtype=dtype)
         return a, C.c_void_p(a.ctypes.data)
 
     # ---- index ------------------------------------------------------------------------------------
@@ -106,6 +110,11 @@ class PointCloudIndex:
 
     def launches(self, reset=False):
         return int(self._L.pc_launch_count(self._h, 1 if reset else 0))
+
+    def batch_shard(self, rank=0, n_ranks=1):
+        """Spatial sharding (pc_batch_shard): every rank passes the same batch, each answers its stretch of the curve."""
+        self._check(self._L.pc_batch_shard(self._h, int(rank), int(n_ranks)))
+        self._shard_n = int(n_ranks)
 
     def profile(self, on=True):
         self._check(self._L.pc_profile_enable(self._h, 1 if on else 0))

@@ -156,7 +156,7 @@ def c4():
     ix.close()
 
 
-def c5(n_pts, n_q):
+def c5(n_pts, n_q, shard):
     import torch.distributed as dist
     from pointcloudtraj_b200.dist import Replicator, env_rank, shard_range
     rank, world, local = env_rank()
@@ -193,14 +193,28 @@ def c5(n_pts, n_q):
         e0.record(); rep.broadcast(ix, 0); e1.record(); torch.cuda.synchronize()
         bcast_ms = e0.elapsed_time(e1)
     half, side = float(meta[0]), int(meta[1])
-    b, e = shard_range(n_q, rank, world)
-    g = torch.Generator(device=dev).manual_seed(1000 + rank)
     ext = torch.tensor([2 * half * side, 2 * half * side, 3.4], device=dev)
     lo = torch.tensor([-half, -half, 0.6], device=dev)
-    q = (torch.rand((e - b, 3), device=dev, generator=g) * ext + lo).contiguous()
+    answered = n_q
+    if shard == "spatial" and world > 1:
+        # every rank holds the SAME batch and answers its own stretch of the Hilbert curve (pc_batch_shard)
+        g = torch.Generator(device=dev).manual_seed(1000)
+        q = (torch.rand((n_q, 3), device=dev, generator=g) * ext + lo).contiguous()
+        ix.batch_shard(rank, world)
+    else:
+        # every rank answers a contiguous slice of the batch (pc_shard_range)
+        b, e = shard_range(n_q, rank, world)
+        g = torch.Generator(device=dev).manual_seed(1000 + rank)
+        q = (torch.rand((e - b, 3), device=dev, generator=g) * ext + lo).contiguous()
     if world > 1:
         dist.barrier()
     nn_ms, _ = timed(lambda: ix.nearest(q), reps=3, warm=1)
+    if shard == "spatial" and world > 1:
+        idx_all, _ = ix.nearest(q)
+        cnt = (idx_all != PointCloudIndex.NOT_MINE_IDX).sum().to(torch.float64)
+        dist.all_reduce(cnt)
+        answered = int(cnt.item())
+        ix.batch_shard(0, 1)
     t = torch.tensor([nn_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -209,6 +223,7 @@ def c5(n_pts, n_q):
         torch.cuda.synchronize()
         ok = brute_check(t_pts, q[:4096], idx, d2, 24)
         print(json.dumps({"config": "c5_scaling", "n_gpus": world, "points": n_pts, "queries_total": n_q, "scaling": "strong",
+                          "sharding": shard if world > 1 else "none", "queries_answered_over_ranks": answered,
                           "index_build_ms": build_ms, "index_broadcast_ms": bcast_ms,
                           "index_bytes": int(ix.view().leaf_base * 64 + ix.view().n_leaves * 64),
                           "nearest_ms_max_over_ranks": float(t.item()), "nearest_qps": n_q / float(t.item()) * 1e3,
@@ -224,6 +239,7 @@ if __name__ == "__main__":
     ap.add_argument("config", choices=["c1", "c2small", "c3", "c4", "c5"])
     ap.add_argument("--points", type=int, default=100_000_000)
     ap.add_argument("--queries", type=int, default=100_000_000)
+    ap.add_argument("--shard", default="spatial", choices=["spatial", "contiguous"])
     a = ap.parse_args()
     if a.config == "c1":
         c1_like("c1_200k_points_100k_queries", 200_000, 100_000, 6)
@@ -234,4 +250,4 @@ if __name__ == "__main__":
     elif a.config == "c4":
         c4()
     else:
-        c5(a.points, a.queries)
+        c5(a.points, a.queries, a.shard)

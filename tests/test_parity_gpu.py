@@ -244,3 +244,40 @@ def test_async_host_batches_match_blocking_calls(ix):
     ix.build(pts)
     for b, o in zip(batches, outs):
         assert (o.numpy() == ix.radius(b.numpy(), P)).all()
+
+
+@pytest.mark.parametrize("n_ranks", [2, 8])
+def test_spatial_batch_sharding(ix, n_ranks):
+    """pc_batch_shard: every rank gets the same batch and answers its stretch of the Hilbert curve.  Emulated on one GPU
+    by switching the rank of one handle: every query is answered by exactly one rank, with the unsharded result, and
+    the shares are balanced."""
+    pts, half = synth.forest_cloud(200_000, seed=6, variant="J", return_half=True)
+    q = synth.rrt_queries(400_000, half, seed=11)
+    P = PcRadiusParams.make(start=(0, 0, 2), **CLEAN_DEMO)
+    ix.build(pts)
+    ref_idx, ref_d2 = ix.nearest(q)
+    ref_r = ix.radius(q, P)
+    owners = np.zeros(len(q), np.int32)
+    shares = []
+    got_idx = np.full(len(q), -9, np.int32)
+    got_r = np.full(len(q), np.nan, np.float32)
+    try:
+        for r in range(n_ranks):
+            ix.batch_shard(r, n_ranks)
+            idx, d2 = ix.nearest(q)
+            mine = idx != PointCloudIndex.NOT_MINE_IDX
+            assert (np.isnan(d2) == ~mine).all()
+            owners += mine
+            shares.append(int(mine.sum()))
+            got_idx[mine] = idx[mine]
+            assert (d2[mine] == ref_d2[mine]).all()
+            rad = ix.radius(q, P)
+            have = ~np.isnan(rad)
+            got_r[have] = rad[have]
+    finally:
+        ix.batch_shard(0, 1)
+    assert (owners == 1).all()                                       # a partition of the batch
+    assert (got_idx == ref_idx).all() and (got_r == ref_r).all()
+    assert max(shares) <= 1.25 * len(q) / n_ranks                     # balanced along the curve
+    idx, _ = ix.nearest(q)
+    assert (idx == ref_idx).all()                                     # sharding switched off again
