@@ -37,7 +37,6 @@ struct pc_lane {
     uint32_t *tile_hist = nullptr; int64_t hist_cap = 0;
     uint32_t *digit_total = nullptr;
     unsigned long long *counter = nullptr;                   // work counter of the persistent query kernel
-    uint32_t *shard_hist = nullptr; int64_t shard_cap = 0;   // pc_batch_shard: curve histogram + the rank's bin range
     cudaEvent_t done = nullptr;
     cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr;   // profiling: batch start / ordered / searched
 };
@@ -225,7 +224,7 @@ extern "C" void pc_index_destroy(pc_index *ix)
         if (L.stream && L.own_stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
         cudaFree(L.d_q); cudaFree(L.d_i32); cudaFree(L.d_f32);
         cudaFree(L.keys_a); cudaFree(L.keys_b); cudaFree(L.vals_a); cudaFree(L.vals_b);
-        cudaFree(L.tile_hist); cudaFree(L.digit_total); cudaFree(L.counter); cudaFree(L.shard_hist);
+        cudaFree(L.tile_hist); cudaFree(L.digit_total); cudaFree(L.counter);
         if (L.done) cudaEventDestroy(L.done);
         if (L.t0) cudaEventDestroy(L.t0);
         if (L.t1) cudaEventDestroy(L.t1);
@@ -449,6 +448,7 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
     // sort_bits (16 / 24 / 32) = radix-sorted key width = how many of the top curve bits order the batch; queries that
     // need no search (sensing-range early-outs) are answered by the key kernel and never enter the sort
     int bits = ix->sort_bits;
+    int shard_level = 5;                                  // curve cells per axis = 2^level dealt to the ranks (pc_batch_shard)
     if (ix->sort_bits_auto && ((ix->build_timed && cudaEventQuery(ix->ev_b1) == cudaSuccess) || ix->bbox_from_bcast)) {
         // 24 bits (8 per axis) order the batch well when its cells hold a handful of queries; a batch that is dense
         // relative to the cloud's extent (large maps) needs the full 30-bit curve.  Estimated from the cloud's bounding
@@ -462,31 +462,24 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
         const float cell = emax / 256.f;
         const double per_cell = vol > 0.f ? (double)m * cell * cell * cell / vol : 0.0;
         bits = per_cell > 16.0 ? 32 : 24;
+        // pc_batch_shard: the finest curve cells (<= 128 per axis) that still hold ~512 queries each
+        if (vol > 0.f) {
+            shard_level = 2;
+            for (int lv = 7; lv >= 2; lv--) {
+                const double c = emax / (double)(1 << lv);
+                double v = 1.0;
+                for (int a = 0; a < 3; a++) v *= ext[a] > c ? ext[a] : c;
+                if ((double)m * c * c * c / v >= 512.0) { shard_level = lv; break; }
+            }
+        }
     }
     const int drop = 30 - bits > 0 ? 30 - bits : 0;     // 24-bit sort = top 24 curve bits, 32-bit sort = all 30
     const int grid = (int)((m + 255) / 256);
-    if (ix->shard_n > 1) {
-        // spatial sharding: this rank answers its own stretch of the Hilbert curve (see query_kernels.cuh)
-        const int drop_s = 30 - bits > 0 ? 30 - bits : 0;
-        uint32_t *key_full = L.keys_b;                       // free until the first radix pass writes to it
-        uint32_t *hist = nullptr;
-        if ((rc = pc_grow(ix, &L.shard_hist, &L.shard_cap, PC_SHARD_BINS + 8)) != PC_OK) return rc;
-        hist = L.shard_hist;
-        PC_CUDA(ix, cudaMemsetAsync(hist, 0, (PC_SHARD_BINS + 8) * sizeof(uint32_t), L.stream));
-        const int pgrid = (int)(grid < ix->sm_count * 8 ? grid : ix->sm_count * 8);
-        if (A.kind == PC_Q_RADIUS)
-            pc_shard_key_kernel<PC_KIND_RADIUS><<<pgrid, 256, 0, L.stream>>>(d_q, m, qstride, ix->d_bbox, A.R, d_idx, d_f, key_full, hist);
-        else
-            pc_shard_key_kernel<PC_KIND_NEAREST><<<pgrid, 256, 0, L.stream>>>(d_q, m, qstride, ix->d_bbox, A.R, d_idx, d_f, key_full, hist);
-        pc_shard_split_kernel<<<1, 1024, 0, L.stream>>>(hist, ix->shard_rank, ix->shard_n, hist + PC_SHARD_BINS);
-        pc_shard_select_kernel<<<grid, 256, 0, L.stream>>>(key_full, m, hist + PC_SHARD_BINS, drop_s, L.keys_a, L.vals_a, L.counter + 1);
-        ix->launches += 3;
-        PC_CHECK_LAUNCH(ix);
-    } else if (A.kind == PC_Q_RADIUS)
-        pc_query_key_kernel<PC_KIND_RADIUS><<<grid, 256, 0, L.stream>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1);
+    if (A.kind == PC_Q_RADIUS)
+        pc_query_key_kernel<PC_KIND_RADIUS><<<grid, 256, 0, L.stream>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n, 30 - 3 * shard_level);
     else
-        pc_query_key_kernel<PC_KIND_NEAREST><<<grid, 256, 0, L.stream>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1);
-    if (ix->shard_n <= 1) ix->launches++;
+        pc_query_key_kernel<PC_KIND_NEAREST><<<grid, 256, 0, L.stream>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n, 30 - 3 * shard_level);
+    ix->launches++;
     PC_CHECK_LAUNCH(ix);
     // only the L.counter[1] compacted entries (device-side count <= m) are sorted
     int which = rs_sort_pairs<uint32_t, 16>(L.keys_a, L.vals_a, L.keys_b, L.vals_b, m, 0, bits, L.tile_hist, L.digit_total, L.stream,

@@ -405,13 +405,14 @@ pc_query_packet_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, 
 // ---- ordering pass of a batch --------------------------------------------------------------------------
 // Morton key of every query in the index's frame (top `30 - drop_bits` bits), so that the lanes of a warp walk the
 // same part of the tree.  For radius batches the sensing-range early-out (corridor_finder.cpp:115-116) is evaluated
-// here, once, coalesced: such queries get their result now and the largest key, and n_search counts the others --
-// after the sort they are exactly the first n_search entries of the permutation.
+// here, once, coalesced: such queries get their result now; the others are compacted into (key, slot) pairs and
+// n_search counts them -- only those are sorted and searched.
 template <int KIND>
 __global__ void __launch_bounds__(256)
 pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const uint32_t *__restrict__ bbox, int drop_bits,
                     pc_radius_dev R, int32_t *__restrict__ out_idx, float *__restrict__ out_f,
-                    uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, unsigned long long *__restrict__ n_search)
+                    uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, unsigned long long *__restrict__ n_search,
+                    int shard_rank, int shard_n, int shard_shift)
 {
     __shared__ uint32_t s_warp[8];
     __shared__ unsigned long long s_base;
@@ -429,10 +430,17 @@ pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
             pc_write_trivial<KIND>(R, (uint32_t)i, out_idx, out_f);
         }
 #if PC_QUERY_CURVE == 1
-        key = pc_hilbert30(x, y, z, f) >> drop_bits;
+        key = pc_hilbert30(x, y, z, f);
 #else
-        key = pc_morton30(x, y, z, f) >> drop_bits;
+        key = pc_morton30(x, y, z, f);
 #endif
+        // pc_batch_shard: the cells of the curve at a batch-dependent level are dealt to the ranks by a hash of the cell
+        // index.  A rank's share is then as dense in space as the whole batch (dense packets) and spread over the whole map
+        // (equal cost per rank).  Measured on C5 with 8 GPUs: array slices 37 ms; contiguous stretches of the curve 41 ms
+        // and round-robin 32^3 cells 43 ms (both unbalanced: 18..42 ms per rank -- on a flat map the low bits of the cell
+        // index encode the z layer); hashed cells: see profiles/r1_c5_strong_scaling.jsonl.
+        if (shard_n > 1 && (int)((((key >> shard_shift) * 2654435761u) >> 15) % (uint32_t)shard_n) != shard_rank) search = false;
+        key >>= drop_bits;
     }
     // compact the queries that still need a search: only those are sorted and searched.  One atomic per CTA; the slot a
     // query lands in depends on CTA scheduling, which changes the composition of packets but never a result.
@@ -448,97 +456,6 @@ pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
     if (search) {
         const unsigned long long pos = s_base + s_warp[warp] + __popc(mask & pc_lanemask_lt());
         keys[pos] = key;
-        vals[pos] = (uint32_t)i;
-    }
-}
-
-// ---- spatial sharding of one batch across ranks (pc_batch_shard) -------------------------------------------------
-// Every rank receives the SAME batch and answers the queries of its own stretch of the Hilbert curve, so that a rank's
-// share is as dense in space as the whole batch (a contiguous slice of a random batch would be n_ranks times sparser,
-// and sparse packets walk more of the tree).  Three small kernels replace the key kernel:
-//   pc_shard_key_kernel   : curve key of every query (early-outs answered by every rank), 4096-bin histogram of the top
-//                           12 curve bits
-//   pc_shard_split_kernel : prefix over the bins -> the bin range whose cumulative count is nearest to this rank's
-//                           equal share (a pure function of the histogram: all ranks compute the same partition)
-//   pc_shard_select_kernel: compact the queries whose bin lies in the range
-#define PC_SHARD_BINS 4096
-
-template <int KIND>
-__global__ void __launch_bounds__(256)
-pc_shard_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const uint32_t *__restrict__ bbox,
-                    pc_radius_dev R, int32_t *__restrict__ out_idx, float *__restrict__ out_f,
-                    uint32_t *__restrict__ key_full, uint32_t *__restrict__ hist)
-{
-    __shared__ uint32_t s_hist[PC_SHARD_BINS];
-    for (int b = threadIdx.x; b < PC_SHARD_BINS; b += blockDim.x) s_hist[b] = 0;
-    __syncthreads();
-    const pc_frame f = pc_make_frame(bbox, 10);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
-        const float *p = q + i * qstride;
-        const float x = p[0], y = p[1], z = p[2];
-        uint32_t key = 0xffffffffu;                                   // no search needed
-        if (KIND == PC_KIND_RADIUS && pc_radius_early_out((double)x, (double)y, (double)z, R)) {
-            pc_write_trivial<KIND>(R, (uint32_t)i, out_idx, out_f);
-        } else {
-            key = pc_hilbert30(x, y, z, f);
-            atomicAdd(&s_hist[key >> 18], 1u);
-        }
-        key_full[i] = key;
-    }
-    __syncthreads();
-    for (int b = threadIdx.x; b < PC_SHARD_BINS; b += blockDim.x)
-        if (s_hist[b]) atomicAdd(&hist[b], s_hist[b]);
-}
-
-// one CTA of 1024 threads; range[0], range[1] = first and one-past-last bin owned by `rank`
-__global__ void __launch_bounds__(1024)
-pc_shard_split_kernel(const uint32_t *__restrict__ hist, int rank, int n_ranks, uint32_t *__restrict__ range)
-{
-    __shared__ unsigned long long s_cum[PC_SHARD_BINS + 1];
-    if (threadIdx.x == 0) {
-        unsigned long long run = 0;
-        for (int b = 0; b < PC_SHARD_BINS; b++) { s_cum[b] = run; run += hist[b]; }
-        s_cum[PC_SHARD_BINS] = run;
-    }
-    __syncthreads();
-    if (threadIdx.x < 2) {
-        const int r = rank + (int)threadIdx.x;                          // boundary r: bins [0, cut_r) go to ranks < r
-        const unsigned long long total = s_cum[PC_SHARD_BINS];
-        uint32_t cut = r <= 0 ? 0u : (r >= n_ranks ? (uint32_t)PC_SHARD_BINS : 0u);
-        if (r > 0 && r < n_ranks) {
-            const unsigned long long target = total * (unsigned long long)r / (unsigned long long)n_ranks;
-            int lo = 0, hi = PC_SHARD_BINS;                             // first bin boundary with cumulative count >= target
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_cum[mid] < target) lo = mid + 1; else hi = mid; }
-            cut = (uint32_t)lo;
-        }
-        range[threadIdx.x] = cut;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-pc_shard_select_kernel(const uint32_t *__restrict__ key_full, int64_t m, const uint32_t *__restrict__ range, int drop_bits,
-                       uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, unsigned long long *__restrict__ n_search)
-{
-    __shared__ uint32_t s_warp[8];
-    __shared__ unsigned long long s_base;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t key = 0xffffffffu;
-    if (i < m) key = key_full[i];
-    const uint32_t bin = key >> 18;
-    const bool mine = key != 0xffffffffu && bin >= range[0] && bin < range[1];
-    const uint32_t mask = __ballot_sync(PC_FULL_MASK, mine);
-    if (lane == 0) s_warp[warp] = __popc(mask);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tot = 0;
-        for (int w = 0; w < 8; w++) { const uint32_t c = s_warp[w]; s_warp[w] = tot; tot += c; }
-        s_base = tot ? atomicAdd(n_search, (unsigned long long)tot) : 0ull;
-    }
-    __syncthreads();
-    if (mine) {
-        const unsigned long long pos = s_base + s_warp[warp] + __popc(mask & pc_lanemask_lt());
-        keys[pos] = key >> drop_bits;
         vals[pos] = (uint32_t)i;
     }
 }

@@ -216,7 +216,11 @@ def c5(n_pts, n_q, shard):
         answered = int(cnt.item())
         ix.batch_shard(0, 1)
     t = torch.tensor([nn_ms], dtype=torch.float64, device=dev)
+    per_rank = [nn_ms]
     if world > 1:
+        allt = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = [float(v.item()) for v in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
         idx, d2 = ix.nearest(q[:4096])
@@ -226,7 +230,7 @@ def c5(n_pts, n_q, shard):
                           "sharding": shard if world > 1 else "none", "queries_answered_over_ranks": answered,
                           "index_build_ms": build_ms, "index_broadcast_ms": bcast_ms,
                           "index_bytes": int(ix.view().leaf_base * 64 + ix.view().n_leaves * 64),
-                          "nearest_ms_max_over_ranks": float(t.item()), "nearest_qps": n_q / float(t.item()) * 1e3,
+                          "nearest_ms_max_over_ranks": float(t.item()), "nearest_ms_per_rank": [round(v, 3) for v in per_rank], "nearest_qps": n_q / float(t.item()) * 1e3,
                           "parity_spot_check": ok}))
     ix.close()
     if world > 1:
