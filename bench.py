@@ -345,7 +345,7 @@ def run_b200(args):
                 "dtype": "f64", "data": "synthetic", "config": workload_config(args),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": NCU_TRAFFIC_BYTES.get(M), "traffic_source": "profiles/r1_full_final.txt (ncu --set full, bytes per launch)",
-                             "kernel": "pc_query_packet_kernel<RADIUS>", "kernel_ms": k_ms,
+                             "kernel": "pc_query_packet2_kernel<RADIUS> (64-query warp packets)", "kernel_ms": k_ms,
                              "batch_order_ms": float(np.mean(order_ms)),
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                              "algorithmic_bytes_per_query": BYTES_PER_QUERY},

@@ -37,6 +37,7 @@ struct pc_lane {
     uint32_t *tile_hist = nullptr; int64_t hist_cap = 0;
     uint32_t *digit_total = nullptr;
     unsigned long long *counter = nullptr;                   // work counter of the persistent query kernel
+    double per_cell = 0.0;                                   // last ordered batch: estimated queries per 1/256-extent cell
     cudaEvent_t done = nullptr;
     cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr;   // profiling: batch start / ordered / searched
 };
@@ -73,7 +74,8 @@ struct pc_index {
     int64_t launches = 0;
     bool profile = false, profiled = false;
     // tuning knobs (environment: PC_QUERY_KERNEL, PC_SORT_BITS, PC_MIN_IDLE), see DESIGN.md "Query kernel variants"
-    int query_kernel = 3;     // 1 = thread per query, 2 = persistent lane refill, 3 = warp packets (ordered batches)
+    int query_kernel = 3;     // 1 = thread per query, 2 = persistent lane refill, 3 = warp packets of 32 (ordered batches), 4 = packets of 64
+    bool query_kernel_auto = true;   // no PC_QUERY_KERNEL in the environment: 3, or 4 for dense batches
     int sort_bits = 24;       // radix-sorted key width of the batch ordering pass (0 = never order)
     bool sort_bits_auto = true;   // no PC_SORT_BITS in the environment: pick 24 or 32 from the batch density
     int min_idle = 8;         // persistent kernel: refill once this many lanes are idle
@@ -179,7 +181,7 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         TRY(cudaGetDeviceProperties(&prop, device));
         if (prop.major < 10) { rc = pc_fail(nullptr, PC_ECUDA, "pc_index_create: device is sm_%d%d, this library is built for sm_100a only", prop.major, prop.minor); break; }
         ix->sm_count = prop.multiProcessorCount;
-        if (const char *v = getenv("PC_QUERY_KERNEL")) { int b_ = atoi(v); ix->query_kernel = (b_ >= 1 && b_ <= 3) ? b_ : 3; }
+        if (const char *v = getenv("PC_QUERY_KERNEL")) { ix->query_kernel_auto = false; int b_ = atoi(v); ix->query_kernel = (b_ >= 1 && b_ <= 4) ? b_ : 3; }
         if (const char *v = getenv("PC_SORT_BITS")) { ix->sort_bits_auto = false; int b_ = atoi(v); ix->sort_bits = b_ <= 0 ? 0 : (b_ <= 16 ? 16 : (b_ <= 24 ? 24 : 32)); }
         if (const char *v = getenv("PC_HOST_CHUNK_QUERIES")) { long long b_ = atoll(v); if (b_ >= 1024) ix->host_chunk = b_; }
         if (const char *v = getenv("PC_MIN_IDLE")) { int b_ = atoi(v); ix->min_idle = b_ < 1 ? 1 : (b_ > 32 ? 32 : b_); }
@@ -449,6 +451,7 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
     // need no search (sensing-range early-outs) are answered by the key kernel and never enter the sort
     int bits = ix->sort_bits;
     int shard_level = 5;                                  // curve cells per axis = 2^level dealt to the ranks (pc_batch_shard)
+    L.per_cell = 0.0;
     if (ix->sort_bits_auto && ((ix->build_timed && cudaEventQuery(ix->ev_b1) == cudaSuccess) || ix->bbox_from_bcast)) {
         // 24 bits (8 per axis) order the batch well when its cells hold a handful of queries; a batch that is dense
         // relative to the cloud's extent (large maps) needs the full 30-bit curve.  Estimated from the cloud's bounding
@@ -462,6 +465,7 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
         const float cell = emax / 256.f;
         const double per_cell = vol > 0.f ? (double)m * cell * cell * cell / vol : 0.0;
         bits = per_cell > 16.0 ? 32 : 24;
+        L.per_cell = per_cell;
         // pc_batch_shard: the finest curve cells (<= 128 per axis) that still hold ~512 queries each
         if (vol > 0.f) {
             shard_level = 2;
@@ -517,7 +521,17 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
     if (prof) PC_CUDA(ix, cudaEventRecord(L.t1, L.stream));
     pc_tree T = pc_tree_of(ix);
     const int64_t want = (m + PC_QUERY_THREADS - 1) / PC_QUERY_THREADS;
-    if (ix->query_kernel >= 3 && perm) {
+    // dense batches (>= 3 queries per cell of 1/256 of the cloud's extent): 64-query packets, two queries per lane
+    // (profiles/r1_sweep5*: +10 % radius, +18 % nearest at 10 M queries; -3 % at 2 M, hence the threshold)
+    const bool two_per_lane = ix->query_kernel == 4 || (ix->query_kernel == 3 && ix->query_kernel_auto && L.per_cell >= 3.0);
+    if (two_per_lane && perm) {
+        // Morton-ordered batch, two queries per lane: one warp walks the tree once for 64 neighbouring queries
+        const int grid = (int)((m + 2 * PC_QUERY_THREADS - 1) / (2 * PC_QUERY_THREADS));
+        if (A.kind == PC_Q_NEAREST)
+            pc_query_packet2_kernel<PC_KIND_NEAREST><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
+        else
+            pc_query_packet2_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
+    } else if (ix->query_kernel >= 3 && perm) {
         // Morton-ordered batch: one warp walks the tree once for its 32 neighbouring queries
         const int grid = (int)want;
         if (A.kind == PC_Q_NEAREST)

@@ -402,6 +402,113 @@ pc_query_packet_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, 
     if (valid) pc_write_result<KIND>(R, b, k, out_idx, out_f);
 }
 
+// ---- variant 4: packets of 64 queries, two per lane ---------------------------------------------------------------
+// The packet walk is bound by instruction issue and by L1 register fill (every lane receives the full 64-byte record
+// of every visited node).  Giving each lane TWO queries -- slots t and t + 32 of the warp's 64 consecutive ordered
+// queries -- halves the record bytes and the control instructions per query-visit; the price is a slightly larger packet.
+__device__ __forceinline__ void pc_scan_leaf2(const float4 *__restrict__ pts, const float qa[3], const float qb[3], pc_best &ba, pc_best &bb)
+{
+    float4 p[PC_LEAF];
+    float da[PC_LEAF], db[PC_LEAF];
+#pragma unroll
+    for (int i = 0; i < PC_LEAF; i++) p[i] = __ldg(pts + i);
+    float mina = FLT_MAX, minb = FLT_MAX;
+#pragma unroll
+    for (int i = 0; i < PC_LEAF; i++) {
+        float dx = p[i].x - qa[0], dy = p[i].y - qa[1], dz = p[i].z - qa[2];
+        da[i] = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        mina = fminf(mina, da[i]);
+        dx = p[i].x - qb[0]; dy = p[i].y - qb[1]; dz = p[i].z - qb[2];
+        db[i] = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        minb = fminf(minb, db[i]);
+    }
+    if (mina <= ba.thr) {
+#pragma unroll
+        for (int i = 0; i < PC_LEAF; i++) pc_consider(p[i], da[i], qa[0], qa[1], qa[2], ba);
+    }
+    if (minb <= bb.thr) {
+#pragma unroll
+        for (int i = 0; i < PC_LEAF; i++) pc_consider(p[i], db[i], qb[0], qb[1], qb[2], bb);
+    }
+}
+
+__device__ __forceinline__ void pc_packet2_traverse(const pc_tree &T, const float qa[3], const float qb[3], pc_best &ba, pc_best &bb, int lane)
+{
+    if (__ballot_sync(PC_FULL_MASK, ba.thr >= 0.f || bb.thr >= 0.f) == 0) return;
+    uint32_t my_entry = 0;
+    int sp = 0;
+    uint32_t node = 1;
+    for (;;) {
+        const float4 *pair = T.nodes + 4ull * node;
+        const float4 lo0 = __ldg(pair), hi0 = __ldg(pair + 1), lo1 = __ldg(pair + 2), hi1 = __ldg(pair + 3);
+        const float a0 = pc_box_d2(lo0, hi0, qa[0], qa[1], qa[2]), a1 = pc_box_d2(lo1, hi1, qa[0], qa[1], qa[2]);
+        const float b0 = pc_box_d2(lo0, hi0, qb[0], qb[1], qb[2]), b1 = pc_box_d2(lo1, hi1, qb[0], qb[1], qb[2]);
+        const bool wa0 = a0 <= ba.thr, wa1 = a1 <= ba.thr, wb0 = b0 <= bb.thr, wb1 = b1 <= bb.thr;
+        const uint32_t w0 = __ballot_sync(PC_FULL_MASK, wa0 || wb0);
+        const uint32_t w1 = __ballot_sync(PC_FULL_MASK, wa1 || wb1);
+        const uint32_t c0 = 2u * node;
+        bool pop = true;
+        if (w0 | w1) {
+            // majority vote over the interested QUERIES (two votes per lane)
+            const uint32_t ia = __ballot_sync(PC_FULL_MASK, wa0 || wa1), ib = __ballot_sync(PC_FULL_MASK, wb0 || wb1);
+            const uint32_t pa = __ballot_sync(PC_FULL_MASK, a0 <= a1) & ia, pb = __ballot_sync(PC_FULL_MASK, b0 <= b1) & ib;
+            const bool first0 = w1 == 0 || (w0 != 0 && 2 * (__popc(pa) + __popc(pb)) >= __popc(ia) + __popc(ib));
+            const uint32_t cn = c0 + (first0 ? 0u : 1u), cf = cn ^ 1u;
+            const bool both = w0 != 0 && w1 != 0;
+            if (c0 >= T.P) {
+                pc_scan_leaf2(T.points + (size_t)(cn - T.P) * PC_LEAF, qa, qb, ba, bb);
+                if (both && __ballot_sync(PC_FULL_MASK, (first0 ? a1 : a0) <= ba.thr || (first0 ? b1 : b0) <= bb.thr))
+                    pc_scan_leaf2(T.points + (size_t)(cf - T.P) * PC_LEAF, qa, qb, ba, bb);
+            } else {
+                if (both) { if (lane == sp) my_entry = cf; sp++; }
+                node = cn;
+                pop = false;
+            }
+        }
+        if (pop) {
+            if (sp == 0) break;
+            sp--;
+            node = __shfl_sync(PC_FULL_MASK, my_entry, sp);
+        }
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(PC_QUERY_THREADS)
+pc_query_packet2_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, int64_t m, int qstride,
+                        const uint32_t *__restrict__ perm, const unsigned long long *__restrict__ m_eff,
+                        int32_t *__restrict__ out_idx, float *__restrict__ out_f)
+{
+    const int lane = threadIdx.x & 31;
+    const long long m_search = m_eff ? (long long)*m_eff : (long long)m;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long base = warp_id * 64;
+    if (base >= m_search) return;
+    float qv[2][3] = { { 0.f, 0.f, 0.f }, { 0.f, 0.f, 0.f } };
+    uint32_t k[2] = { 0u, 0u };
+    bool valid[2];
+    pc_best b[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const long long t = base + 32 * j + lane;
+        valid[j] = t < m_search;
+        b[j].d2 = INFINITY; b[j].idx = -1; b[j].thr = -1.0f;
+        if (valid[j]) {
+            k[j] = perm ? perm[t] : (uint32_t)t;
+            const float *qq = q + (size_t)k[j] * qstride;
+            qv[j][0] = qq[0]; qv[j][1] = qq[1]; qv[j][2] = qq[2];
+            bool search = T.n_points > 0;
+            if (KIND == PC_KIND_RADIUS && search && !m_eff && pc_radius_early_out((double)qv[j][0], (double)qv[j][1], (double)qv[j][2], R)) search = false;
+            if (search) b[j].thr = (KIND == PC_KIND_RADIUS) ? R.bound_thr : FLT_MAX;
+            else { pc_write_trivial<KIND>(R, k[j], out_idx, out_f); valid[j] = false; }
+        }
+    }
+    pc_packet2_traverse(T, qv[0], qv[1], b[0], b[1], lane);
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+        if (valid[j]) pc_write_result<KIND>(R, b[j], k[j], out_idx, out_f);
+}
+
 // ---- ordering pass of a batch --------------------------------------------------------------------------
 // Morton key of every query in the index's frame (top `30 - drop_bits` bits), so that the lanes of a warp walk the
 // same part of the tree.  For radius batches the sensing-range early-out (corridor_finder.cpp:115-116) is evaluated
