@@ -32,8 +32,8 @@ PARAMS = dict(search_margin=0.25, max_radius=1.5, sample_range=30.0)   # clean_d
 BYTES_PER_QUERY = 16            # algorithmic: 12 B query (xyz float32) in + 4 B radius out
 FRAME_POINTS = 300_000          # C3 frame for the build-ms metric
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on the default workload, from the
-# `ncu --set full` capture summarised in profiles/r1_full_final.txt (547.9 MB + 105.4 MB); re-measure when the kernel changes
-NCU_TRAFFIC_BYTES = {10_000_000: 653_369_856}
+# `ncu --set full` capture summarised in profiles/r1_full_final.txt (547.9 MB + 104.1 MB); re-measure when the kernel changes
+NCU_TRAFFIC_BYTES = {10_000_000: 652_018_176}
 
 
 def parse():
