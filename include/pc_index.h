@@ -57,6 +57,8 @@ extern "C" {
 #define PC_HOST   0
 #define PC_DEVICE 1
 #define PC_HOST_ASYNC 2   /* pc_nearest_batch / pc_radius_batch only: host buffers (pinned), the call returns at once */
+#define PC_DEVICE_ASYNC 3 /* pc_nearest_batch / pc_radius_batch only: device buffers, batches rotate over three internal
+                             streams (ordered after the handle's stream at call time); results valid after pc_index_sync */
 
 /* flags for pc_radius_batch / pc_clearance_batch */
 #define PC_RADIUS_BOUNDED   0  /* default: search only within max_radius + search_margin (exact for the radius) */

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpcindex.so")
 
 PC_OK, PC_EINVAL, PC_ENOMEM, PC_ECUDA, PC_ECAP, PC_ENCCL, PC_ENOTIMPL = 0, -1, -2, -3, -4, -5, -6
-PC_HOST, PC_DEVICE, PC_HOST_ASYNC = 0, 1, 2
+PC_HOST, PC_DEVICE, PC_HOST_ASYNC, PC_DEVICE_ASYNC = 0, 1, 2, 3
 PC_RADIUS_BOUNDED, PC_RADIUS_FULL_NN = 0, 1
 PC_QUERY_AUTO, PC_QUERY_UNSORTED, PC_QUERY_SORTED = 0, 2, 4
 PC_NCCL_UNIQUE_ID_BYTES = 128

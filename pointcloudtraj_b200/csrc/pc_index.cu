@@ -61,7 +61,7 @@ struct pc_index {
     float4 *tree = nullptr; int64_t tree_cap = 0;   // one allocation: boxes [0, 4P) then leaf records [4P, 6P)
     float4 *points = nullptr;                       // = tree + 4P of the current build
     float4 *nodes = nullptr;                        // = tree
-    cudaEvent_t ev_b0 = nullptr, ev_b1 = nullptr, ev_ready = nullptr;
+    cudaEvent_t ev_b0 = nullptr, ev_b1 = nullptr, ev_ready = nullptr, ev_in = nullptr;
     uint32_t *h_bbox = nullptr;                      // pinned host copy of d_bbox, valid once ev_b1 has completed
     bool build_timed = false;
     bool bbox_from_bcast = false;                    // h_bbox was filled by pc_index_broadcast (receiver side)
@@ -190,6 +190,7 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         TRY(cudaEventCreate(&ix->ev_b0));
         TRY(cudaEventCreate(&ix->ev_b1));
         TRY(cudaEventCreateWithFlags(&ix->ev_ready, cudaEventDisableTiming));
+        TRY(cudaEventCreateWithFlags(&ix->ev_in, cudaEventDisableTiming));
         TRY(cudaMalloc((void **)&ix->d_bbox, 8 * sizeof(uint32_t)));
         TRY(cudaHostAlloc((void **)&ix->h_bbox, 8 * sizeof(uint32_t), cudaHostAllocDefault));
         TRY(cudaMalloc((void **)&ix->digit_total, RS_RADIX * sizeof(uint32_t)));
@@ -239,6 +240,7 @@ extern "C" void pc_index_destroy(pc_index *ix)
     if (ix->ev_b0) cudaEventDestroy(ix->ev_b0);
     if (ix->ev_b1) cudaEventDestroy(ix->ev_b1);
     if (ix->ev_ready) cudaEventDestroy(ix->ev_ready);
+    if (ix->ev_in) cudaEventDestroy(ix->ev_in);
     if (ix->own_stream && ix->stream) cudaStreamDestroy(ix->stream);
     delete ix;
 }
@@ -600,6 +602,21 @@ static int pc_query_dispatch(pc_index *ix, const pc_qargs &A, const float *q, in
 
     // order the side lanes after the last (possibly still running) index build / broadcast on the handle's stream
     for (int l = 1; l < PC_PIPE_LANES; l++) PC_CUDA(ix, cudaStreamWaitEvent(ix->lane[l].stream, ix->ev_ready, 0));
+    if (space == PC_DEVICE_ASYNC) {
+        // device-resident batch on the next lane: consecutive calls overlap one batch's ordering pass (memory-bound) with the
+        // previous batch's search (issue-bound).  The lane starts after whatever the handle's stream holds now (the
+        // caller's producers of q); results are valid after pc_index_sync.
+        pc_lane &L = ix->lane[ix->next_lane];
+        ix->next_lane = (ix->next_lane + 1) % PC_PIPE_LANES;
+        if (&L != &ix->lane[0]) {
+            PC_CUDA(ix, cudaEventRecord(ix->ev_in, ix->stream));
+            PC_CUDA(ix, cudaStreamWaitEvent(L.stream, ix->ev_in, 0));
+        }
+        int rc = pc_run_batch(ix, L, A, q, m, qs, out_idx, out_f);
+        if (rc != PC_OK) return rc;
+        PC_CUDA(ix, cudaEventRecord(L.done, L.stream));
+        return PC_OK;
+    }
     if (space == PC_HOST_ASYNC) {
         // the whole batch on the next lane, no wait: consecutive calls overlap their H2D / kernels / D2H
         pc_lane &L = ix->lane[ix->next_lane];
@@ -647,7 +664,7 @@ static int pc_query_dispatch(pc_index *ix, const pc_qargs &A, const float *q, in
 static int pc_check_query_args(pc_index *ix, const char *fn, const float *q, int64_t m, int64_t q_stride, int space)
 {
     if (!ix) return PC_EINVAL;
-    if (m < 0 || (m > 0 && !q) || (q_stride != 3 && q_stride != 4) || (space != PC_HOST && space != PC_DEVICE && space != PC_HOST_ASYNC))
+    if (m < 0 || (m > 0 && !q) || (q_stride != 3 && q_stride != 4) || (space != PC_HOST && space != PC_DEVICE && space != PC_HOST_ASYNC && space != PC_DEVICE_ASYNC))
         return pc_fail(ix, PC_EINVAL, "%s: bad argument (m=%lld stride=%lld space=%d)", fn, (long long)m, (long long)q_stride, space);
     if (m > ((int64_t)1 << 32) - 1) return pc_fail(ix, PC_EINVAL, "%s: at most 2^32-1 queries per call", fn);
     return PC_OK;

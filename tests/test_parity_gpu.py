@@ -281,3 +281,27 @@ def test_spatial_batch_sharding(ix, n_ranks):
     assert max(shares) <= 1.25 * len(q) / n_ranks                     # balanced along the curve
     idx, _ = ix.nearest(q)
     assert (idx == ref_idx).all()                                     # sharding switched off again
+
+
+def test_async_device_batches(ix):
+    """PC_DEVICE_ASYNC: device batches rotate over the internal streams; results valid after sync and equal to PC_DEVICE."""
+    torch = pytest.importorskip("torch")
+    import ctypes as C
+    from pointcloudtraj_b200 import _lib as L
+    pts, half = synth.forest_cloud(150_000, seed=8, variant="J", return_half=True)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        h = PointCloudIndex(max_points=len(pts), device=0, stream=s.cuda_stream)
+        h.build(torch.from_numpy(pts).cuda())
+        P = PcRadiusParams.make(start=(0, 0, 2), **CLEAN_DEMO)
+        qs = [torch.from_numpy(synth.rrt_queries(100_000 + 7 * k, half, seed=40 + k)).cuda() for k in range(6)]
+        ref = [h.radius(q, P) for q in qs]
+        outs = [torch.full((len(q),), -5.0, device="cuda") for q in qs]
+        for q, o in zip(qs, outs):
+            rc = h._L.pc_radius_batch(h._h, C.c_void_p(q.data_ptr()), len(q), 3, L.PC_DEVICE_ASYNC, 0, C.byref(P), C.c_void_p(o.data_ptr()), None)
+            assert rc == 0
+        h.sync()
+        torch.cuda.synchronize()
+        for r, o in zip(ref, outs):
+            assert (r == o).all().item()
+        h.close()
