@@ -22,7 +22,8 @@
 #define PC_VERSION_STRING "pcindex 0.1 (sm_100a)"
 #define PC_PIPE_LANES 3                 // concurrent H2D / kernel / D2H chunks for PC_HOST calls
 #define PC_HOST_CHUNK (1 << 21)         // queries per pipelined chunk (scripts/e2e_sweep.py: 2 Mi is the optimum for 10 M batches)
-#define PC_SORT_MIN_BATCH (1 << 15)     // PC_QUERY_AUTO sorts batches at least this large
+#define PC_SORT_MIN_BATCH (1 << 17)     // PC_QUERY_AUTO orders batches at least this large (scripts/small_batch_ab.py: below
+                                        // ~130k queries one thread per query on the unordered batch has the lower latency)
 
 static thread_local char g_create_error[256] = "";
 
