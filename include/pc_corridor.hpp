@@ -10,6 +10,8 @@
 //   radiusSearch    corridor_finder.cpp:113-133    early-outs, float32 cast of the point, 1-NN, min(sqrt(d2) - search_margin, max_radius)
 //   checkTrajPtCol  corridor_finder.cpp:412-416    radiusSearch(pt) < 0
 //   checkSafeTrajectory  Planner/src/sim_planning_demo.cpp:729-781 (a free function there; it only needs the cloud)
+//   firstCollision  Planner/src/status_inspector.cpp:33-46   ground-truth collision check of executed positions
+//   observe         Planner/src/camera_sensor.cpp:133-145    LiDAR-mode observation (all points within max_dist)
 //
 // No Eigen/PCL/ROS dependency: points are plain double[3] / float arrays (pcl::PointXYZ is x,y,z,pad float32 =
 // stride 4; Eigen::Vector3d::data() is double[3]).
@@ -100,6 +102,34 @@ public:
         return pc_clearance_batch(ix_, traj.data(), (int64_t)traj.size(), seg_order.data(), seg_T.data(), seg_coef_off.data(),
                                   (int64_t)seg_order.size(), coef.data(), (int64_t)coef.size(), PC_HOST, dt, stop_time, &params_,
                                   first_hit.data(), min_radius ? min_radius->data() : nullptr, nullptr);
+    }
+
+    // Ground-truth collision arbiter of the experiment harness (Planner/src/status_inspector.cpp:33-46): for every executed
+    // position, is the nearest map point closer than col_rad?  Returns the ordinal of the first colliding position, -1 if none.
+    int64_t firstCollision(const float *positions, int64_t m, int64_t stride_floats, double col_rad, std::vector<float> *nearest_dist = nullptr)
+    {
+        std::vector<float> d2((size_t)m);
+        check(pc_nearest_batch(ix_, positions, m, stride_floats, PC_HOST, PC_QUERY_AUTO, nullptr, d2.data()));
+        int64_t first = -1;
+        if (nearest_dist) nearest_dist->resize((size_t)m);
+        for (int64_t k = 0; k < m; k++) {
+            const double d = std::sqrt((double)d2[(size_t)k]);            // sqrt(points_distances[0]) < col_rad
+            if (nearest_dist) (*nearest_dist)[(size_t)k] = (float)d;
+            if (first < 0 && d < col_rad) first = k;
+        }
+        return first;
+    }
+
+    // LiDAR-mode observation of the sensor node (Planner/src/camera_sensor.cpp:133-145): indices of all map points within
+    // max_dist of the sensor position, ascending.
+    int observe(const double sensor_pos[3], double max_dist, std::vector<int32_t> &indices)
+    {
+        int64_t n = 0;
+        int rc = pc_sphere_gather(ix_, sensor_pos, max_dist, PC_HOST, nullptr, 0, &n);
+        if (rc != PC_OK) return rc;
+        indices.resize((size_t)n);
+        if (n == 0) return PC_OK;
+        return pc_sphere_gather(ix_, sensor_pos, max_dist, PC_HOST, indices.data(), n, &n);
     }
 
     pc_index *handle() { return ix_; }

@@ -131,6 +131,13 @@ int  pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64_t q_strid
                     const double *range, int range_is_scalar,
                     int64_t *out_offsets, int32_t *out_idx, int64_t cap);
 
+/* Sensing gather: ALL points within `radius` of one centre (d2 <= radius^2; the centre is cast to float32 as PCL does),
+ * ascending original index -- the LiDAR-mode observation of the reference's sensor node, one radiusSearch(pos, max_dist)
+ * on the global map (Planner/src/camera_sensor.cpp:133-145).  *out_count (host) is always the number of hits; if it
+ * exceeds cap the call returns PC_ECAP (cap == 0 with out_idx == NULL just counts). */
+int  pc_sphere_gather(pc_index *ix, const double center[3], double radius, int space,
+                      int32_t *out_idx, int64_t cap, int64_t *out_count);
+
 /* Per trajectory: walk the segments from t_now in steps of dt while the accumulated time <= horizon
  * (sim_planning_demo.cpp:745-749), evaluate p = T_i * sum_j C(n,j) c_ij u^j (1-u)^(n-j), u = t/T_i,
  * cast to float32 and apply radiusSearch.  seg_coef_off[s] is the offset (in doubles) of segment s's

@@ -24,7 +24,7 @@ ERROR_NAMES = {PC_EINVAL: "PC_EINVAL", PC_ENOMEM: "PC_ENOMEM", PC_ECUDA: "PC_ECU
 ABI_SYMBOLS = [
     "pc_index_create", "pc_index_destroy", "pc_index_sync", "pc_last_error", "pc_version",
     "pc_index_build", "pc_index_size", "pc_index_view_get", "pc_index_last_build_ms",
-    "pc_nearest_batch", "pc_radius_batch", "pc_range_batch", "pc_clearance_batch",
+    "pc_nearest_batch", "pc_radius_batch", "pc_range_batch", "pc_clearance_batch", "pc_sphere_gather",
     "pc_host_alloc", "pc_host_free",
     "pc_comm_unique_id", "pc_comm_init", "pc_comm_destroy", "pc_index_broadcast", "pc_shard_range",
     "pc_launch_count", "pc_profile_enable", "pc_profile_last_batch", "pc_batch_shard",
@@ -91,6 +91,7 @@ def load():
     L.pc_range_batch.argtypes = [vp, vp, i64, i64, i32, vp, i32, vp, vp, i64]
     L.pc_clearance_batch.argtypes = [vp, vp, i64, vp, vp, vp, i64, vp, i64, i32, C.c_double, C.c_double,
                                      C.POINTER(PcRadiusParams), vp, vp, vp]
+    L.pc_sphere_gather.argtypes = [vp, C.POINTER(C.c_double), C.c_double, i32, vp, i64, C.POINTER(i64)]
     L.pc_host_alloc.argtypes = [i64]
     L.pc_host_alloc.restype = vp
     L.pc_host_free.argtypes = [vp]

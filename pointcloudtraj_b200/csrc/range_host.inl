@@ -89,3 +89,54 @@ extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64
     }
     return PC_OK;
 }
+
+extern "C" int pc_sphere_gather(pc_index *ix, const double center[3], double radius, int space,
+                                int32_t *out_idx, int64_t cap, int64_t *out_count)
+{
+    if (!ix) return PC_EINVAL;
+    if (!center || !out_count || cap < 0 || (cap > 0 && !out_idx) || (space != PC_HOST && space != PC_DEVICE) || !(radius == radius))
+        return pc_fail(ix, PC_EINVAL, "pc_sphere_gather: bad argument");
+    PC_CUDA(ix, cudaSetDevice(ix->device));
+    *out_count = 0;
+    if (ix->n == 0) return PC_OK;
+    cudaStream_t st = ix->stream;
+    pc_lane &L = ix->lane[0];
+    // only the real points: the tail of the last leaf repeats the last point
+    const int64_t n = ix->n;
+    const int64_t want = cap < n ? cap : n;
+    int rc;
+    if (want > L.sort_cap) {
+        cudaFree(L.keys_a); cudaFree(L.keys_b); cudaFree(L.vals_a); cudaFree(L.vals_b);
+        L.keys_a = L.keys_b = L.vals_a = L.vals_b = nullptr; L.sort_cap = 0;
+        PC_CUDA(ix, cudaMalloc((void **)&L.keys_a, (size_t)want * 4));
+        PC_CUDA(ix, cudaMalloc((void **)&L.keys_b, (size_t)want * 4));
+        PC_CUDA(ix, cudaMalloc((void **)&L.vals_a, (size_t)want * 4));
+        PC_CUDA(ix, cudaMalloc((void **)&L.vals_b, (size_t)want * 4));
+        L.sort_cap = want;
+    }
+    if ((rc = pc_grow(ix, &L.tile_hist, &L.hist_cap, (int64_t)RS_RADIX * (rs_num_tiles<16>(want > 0 ? want : 1) + 1))) != PC_OK) return rc;
+    const float cx = (float)center[0], cy = (float)center[1], cz = (float)center[2];   // PCL searches with a float32 point
+    const double r2 = radius * radius;
+    float thr = (float)r2;
+    thr = nextafterf(thr, INFINITY) * PC_THR_SLACK;
+    if (!(thr < FLT_MAX)) thr = FLT_MAX;
+    PC_CUDA(ix, cudaMemsetAsync(L.counter, 0, 2 * sizeof(unsigned long long), st));
+    pc_sphere_gather_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(ix->points, n, cx, cy, cz, r2, thr, L.keys_a, (unsigned long long)want, L.counter + 1);
+    ix->launches++;
+    PC_CHECK_LAUNCH(ix);
+    unsigned long long total = 0;
+    PC_CUDA(ix, cudaMemcpyAsync(&total, L.counter + 1, sizeof total, cudaMemcpyDeviceToHost, st));
+    PC_CUDA(ix, cudaStreamSynchronize(st));
+    *out_count = (int64_t)total;
+    if ((int64_t)total > cap) return cap == 0 && !out_idx ? PC_OK : pc_fail(ix, PC_ECAP, "pc_sphere_gather: %lld hits exceed cap %lld", (long long)total, (long long)cap);
+    if (total == 0) return PC_OK;
+    // ascending original index: sort the appended ids (values are not needed; the key buffer doubles as value buffer)
+    int bits = 8;
+    while (bits < 32 && ((unsigned long long)n >> bits) != 0) bits += 8;
+    int which = rs_sort_pairs<uint32_t, 16>(L.keys_a, L.vals_a, L.keys_b, L.vals_b, (int64_t)total, 0, bits, L.tile_hist, L.digit_total, st, &ix->launches);
+    PC_CHECK_LAUNCH(ix);
+    const uint32_t *sorted = which ? L.keys_b : L.keys_a;
+    PC_CUDA(ix, cudaMemcpyAsync(out_idx, sorted, (size_t)total * sizeof(int32_t), space == PC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+    if (space == PC_HOST) PC_CUDA(ix, cudaStreamSynchronize(st));
+    return PC_OK;
+}

@@ -193,3 +193,40 @@ pc_scan_write_offsets(const int64_t *__restrict__ counts, int64_t m, const int64
         if (base + i == m - 1) offsets[m] = run;
     }
 }
+
+// ---- sensing gather: every point within `radius` of one centre ---------------------------------------------------
+// The LiDAR-mode sensor of the reference gathers the observed map with ONE radius search of ~20 m on the global cloud
+// (Planner/src/camera_sensor.cpp:133-145).  A result of 10^5..10^6 points is a stream compaction, not a tree walk:
+// every point is tested (fp32 filter, fp64 decision as everywhere), hits are appended CTA by CTA, and the list is then
+// radix-sorted by original index.
+__global__ void __launch_bounds__(256)
+pc_sphere_gather_kernel(const float4 *__restrict__ points, int64_t n, float cx, float cy, float cz, double r2, float thr,
+                        uint32_t *__restrict__ out, unsigned long long cap, unsigned long long *__restrict__ count)
+{
+    __shared__ uint32_t s_warp[8];
+    __shared__ unsigned long long s_base;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    bool hit = false;
+    uint32_t id = 0;
+    if (i < n) {
+        const float4 p = __ldg(points + i);
+        const float dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
+        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (d <= thr) hit = pc_exact_d2(p.x, p.y, p.z, (double)cx, (double)cy, (double)cz) <= r2;
+        id = __float_as_uint(p.w);
+    }
+    const uint32_t mask = __ballot_sync(PC_FULL_MASK, hit);
+    if (lane == 0) s_warp[warp] = __popc(mask);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < 8; w++) { const uint32_t c = s_warp[w]; s_warp[w] = tot; tot += c; }
+        s_base = tot ? atomicAdd(count, (unsigned long long)tot) : 0ull;
+    }
+    __syncthreads();
+    if (hit) {
+        const unsigned long long pos = s_base + s_warp[warp] + __popc(mask & pc_lanemask_lt());
+        if (pos < cap) out[pos] = id;
+    }
+}

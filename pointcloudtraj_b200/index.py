@@ -178,6 +178,15 @@ class PointCloudIndex:
             raise L.PcError(rc, f"range: {int(off[-1])} hits exceed cap {cap}")
         return off, out[: int(off[-1])]
 
+    def sphere_gather(self, center, radius):
+        """All points within `radius` of `center`, ascending original index (camera_sensor.cpp:133-145, LiDAR mode)."""
+        c = (C.c_double * 3)(*[float(v) for v in center])
+        cnt = C.c_int64(0)
+        self._check(self._L.pc_sphere_gather(self._h, c, float(radius), L.PC_HOST, C.c_void_p(0), 0, C.byref(cnt)))
+        out = np.empty(max(cnt.value, 1), dtype=np.int32)
+        self._check(self._L.pc_sphere_gather(self._h, c, float(radius), L.PC_HOST, C.c_void_p(out.ctypes.data), cnt.value, C.byref(cnt)))
+        return out[: cnt.value]
+
     def clearance(self, traj_first_seg, seg_order, seg_T, seg_coef_off, coef, params: L.PcRadiusParams,
                   t_now=None, dt=0.02, horizon=2.0):
         """checkSafeTrajectory for a batch of piecewise Bezier trajectories (host arrays, CSR layout of

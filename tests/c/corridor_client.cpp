@@ -37,6 +37,21 @@ int main(int argc, char **argv)
     if (planner.checkTrajPtCol(qf.data(), m, 3, col) != PC_OK) return 8;
     for (int64_t k = 0; k < m; k += 97)
         if (planner.checkTrajPtCol(&q[3 * (size_t)k]) != (r1[(size_t)k] < 0.0)) return 9;
+    // the neighbouring rows: ground-truth arbiter and LiDAR observation
+    std::vector<float> nd;
+    const int64_t first_col = planner.firstCollision(qf.data(), m, 3, 0.3, &nd);
+    int64_t expect_first = -1;
+    for (int64_t k = 0; k < m && expect_first < 0; k++) if (nd[(size_t)k] < 0.3f && (double)nd[(size_t)k] < 0.3) expect_first = k;
+    if (first_col != expect_first) return 11;
+    std::vector<int32_t> seen;
+    if (planner.observe(start, 6.0, seen) != PC_OK) return 12;
+    for (size_t i = 1; i < seen.size(); i++) if (seen[i] <= seen[i - 1]) return 13;
+    size_t brute = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const double dx = (double)pts[4 * (size_t)i] - (double)(float)start[0], dy = (double)pts[4 * (size_t)i + 1] - (double)(float)start[1], dz = (double)pts[4 * (size_t)i + 2] - (double)(float)start[2];
+        if ((dx * dx + dy * dy) + dz * dz <= 36.0) brute++;
+    }
+    if (brute != seen.size()) return 14;
     FILE *o = fopen(argv[2], "wb");
     if (!o) return 10;
     fwrite(r1.data(), 8, (size_t)m, o);

@@ -158,3 +158,18 @@ def test_clearance_edge_cases(ix):
         ix.clearance(first[:2], [13], [T], [0, len(coef)], coef, P)
     with pytest.raises(PcError):
         ix.clearance(first[:2], [n], [T], [0, len(coef)], coef, P, dt=0.0)
+
+
+def test_sphere_gather_matches_brute_force(ix):
+    """pc_sphere_gather: the LiDAR-mode observation (camera_sensor.cpp:133-145) = all points within max_dist of the sensor."""
+    pts, half = synth.forest_cloud(250_000, seed=4, variant="J", return_half=True)
+    ix.build(pts)
+    for center, radius in (((1.0, -2.0, 2.0), 20.0), ((half, half, 0.0), 6.5), ((0.0, 0.0, 100.0), 5.0), ((0.0, 0.0, 2.0), 1e4)):
+        got = ix.sphere_gather(center, radius)
+        c = np.array(center, np.float32).astype(np.float64)
+        d = pts.astype(np.float64) - c
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        want = np.nonzero(d2 <= radius * radius)[0]
+        assert got.dtype == np.int32 and (got == want).all() if len(got) == len(want) else False
+    ix.build(np.zeros((0, 3), np.float32))
+    assert ix.sphere_gather((0, 0, 0), 5.0).size == 0
