@@ -109,3 +109,21 @@ def test_arena_growth_and_shrink(ix):
     P = PcRadiusParams.make(0.25, 1.5, 30.0, (0, 0, 2))
     r, i = ix.radius(q, P, flags=PC_RADIUS_FULL_NN, want_idx=True)
     assert (i == idx).all()
+
+
+def test_non_finite_points_in_the_cloud_are_never_returned(ix):
+    pts = synth.uniform_cloud(30_000, half=5.0, seed=8)
+    dirty = pts.copy()
+    bad = np.arange(0, len(pts), 113)
+    dirty[bad[0::3], 0] = np.nan
+    dirty[bad[1::3], 1] = np.inf
+    dirty[bad[2::3], 2] = -np.inf
+    q = synth.rrt_queries(40_000, 5.0, seed=9)
+    ix.build(dirty)
+    idx, d2 = ix.nearest(q)
+    clean = np.ones(len(pts), bool)
+    clean[bad] = False
+    keep = np.nonzero(clean)[0]
+    bi, bd, _ = oracle.brute_nearest(pts[keep], q[:4000])          # brute force over the finite points only
+    assert (idx[:4000] == keep[bi]).all() and (d2[:4000] == bd.astype(np.float32)).all()
+    assert np.isin(idx, keep).all() and np.isfinite(d2).all()
