@@ -40,6 +40,9 @@ struct pc_lane {
     unsigned long long *counter = nullptr;                   // work counter of the persistent query kernel
     double per_cell = 0.0;                                   // last ordered batch: estimated queries per 1/256-extent cell
     cudaEvent_t done = nullptr;
+    cudaStream_t order_stream = nullptr;                     // high-priority stream for the ordering pass of pipelined batches
+    cudaStream_t os = nullptr;                               // stream the current batch's ordering pass runs on
+    cudaEvent_t ev_deps = nullptr, ev_ordered = nullptr;
     cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr;   // profiling: batch start / ordered / searched
 };
 
@@ -200,6 +203,13 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
             if (l == 0) { ix->lane[l].stream = ix->stream; ix->lane[l].own_stream = false; }
             else { TRY(cudaStreamCreateWithFlags(&ix->lane[l].stream, cudaStreamNonBlocking)); ix->lane[l].own_stream = true; }
             TRY(cudaEventCreateWithFlags(&ix->lane[l].done, cudaEventDisableTiming));
+            TRY(cudaEventCreateWithFlags(&ix->lane[l].ev_deps, cudaEventDisableTiming));
+            TRY(cudaEventCreateWithFlags(&ix->lane[l].ev_ordered, cudaEventDisableTiming));
+            {
+                int lo_p = 0, hi_p = 0;
+                TRY(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+                TRY(cudaStreamCreateWithPriority(&ix->lane[l].order_stream, cudaStreamNonBlocking, hi_p));
+            }
             TRY(cudaEventCreate(&ix->lane[l].t0));
             TRY(cudaEventCreate(&ix->lane[l].t1));
             TRY(cudaEventCreate(&ix->lane[l].t2));
@@ -230,6 +240,9 @@ extern "C" void pc_index_destroy(pc_index *ix)
         cudaFree(L.keys_a); cudaFree(L.keys_b); cudaFree(L.vals_a); cudaFree(L.vals_b);
         cudaFree(L.tile_hist); cudaFree(L.digit_total); cudaFree(L.counter);
         if (L.done) cudaEventDestroy(L.done);
+        if (L.ev_deps) cudaEventDestroy(L.ev_deps);
+        if (L.ev_ordered) cudaEventDestroy(L.ev_ordered);
+        if (L.order_stream) { cudaStreamSynchronize(L.order_stream); cudaStreamDestroy(L.order_stream); }
         if (L.t0) cudaEventDestroy(L.t0);
         if (L.t1) cudaEventDestroy(L.t1);
         if (L.t2) cudaEventDestroy(L.t2);
@@ -483,13 +496,13 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
     const int drop = 30 - bits > 0 ? 30 - bits : 0;     // 24-bit sort = top 24 curve bits, 32-bit sort = all 30
     const int grid = (int)((m + 255) / 256);
     if (A.kind == PC_Q_RADIUS)
-        pc_query_key_kernel<PC_KIND_RADIUS><<<grid, 256, 0, L.stream>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n, 30 - 3 * shard_level);
+        pc_query_key_kernel<PC_KIND_RADIUS><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n, 30 - 3 * shard_level);
     else
-        pc_query_key_kernel<PC_KIND_NEAREST><<<grid, 256, 0, L.stream>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n, 30 - 3 * shard_level);
+        pc_query_key_kernel<PC_KIND_NEAREST><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n, 30 - 3 * shard_level);
     ix->launches++;
     PC_CHECK_LAUNCH(ix);
     // only the L.counter[1] compacted entries (device-side count <= m) are sorted
-    int which = rs_sort_pairs<uint32_t, 16>(L.keys_a, L.vals_a, L.keys_b, L.vals_b, m, 0, bits, L.tile_hist, L.digit_total, L.stream,
+    int which = rs_sort_pairs<uint32_t, 16>(L.keys_a, L.vals_a, L.keys_b, L.vals_b, m, 0, bits, L.tile_hist, L.digit_total, L.os,
                                             &ix->launches, L.counter + 1);
     PC_CHECK_LAUNCH(ix);
     *perm = which ? L.vals_b : L.vals_a;
@@ -507,19 +520,32 @@ static bool pc_want_sort(const pc_index *ix, int flags, int64_t m)
 
 // run one device-resident batch on lane L
 static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float *d_q, int64_t m, int qstride,
-                        int32_t *d_idx, float *d_f)
+                        int32_t *d_idx, float *d_f, bool split_streams = false)
 {
     if (m == 0) return PC_OK;
+    // Pipelined (ASYNC) batches run their ordering pass on the lane's high-priority stream: its short, memory-bound kernels
+    // are scheduled ahead of the queued CTAs of OTHER lanes' search kernels (issue-bound) and overlap with them.  Everything
+    // already queued on the lane (input copy, the lane's previous batch, which still reads the sort buffers) comes first.
+    L.os = L.stream;
+    if (split_streams && pc_want_sort(ix, A.flags, m)) {
+        PC_CUDA(ix, cudaEventRecord(L.ev_deps, L.stream));
+        PC_CUDA(ix, cudaStreamWaitEvent(L.order_stream, L.ev_deps, 0));
+        L.os = L.order_stream;
+    }
     const uint32_t *perm = nullptr;
     const unsigned long long *m_eff = nullptr;
     const bool prof = ix->profile && &L == &ix->lane[0];
     if (prof) PC_CUDA(ix, cudaEventRecord(L.t0, L.stream));
     // counter[0]: work counter of the persistent kernel, counter[1]: queries that need a search after the ordering pass
-    PC_CUDA(ix, cudaMemsetAsync(L.counter, 0, 2 * sizeof(unsigned long long), L.stream));
+    PC_CUDA(ix, cudaMemsetAsync(L.counter, 0, 2 * sizeof(unsigned long long), L.os));
     if (pc_want_sort(ix, A.flags, m)) {
         int rc = pc_sort_queries(ix, L, A, d_q, m, qstride, d_idx, d_f, &perm);
         if (rc != PC_OK) return rc;
         m_eff = L.counter + 1;
+    }
+    if (L.os != L.stream) {
+        PC_CUDA(ix, cudaEventRecord(L.ev_ordered, L.os));
+        PC_CUDA(ix, cudaStreamWaitEvent(L.stream, L.ev_ordered, 0));
     }
     if (prof) PC_CUDA(ix, cudaEventRecord(L.t1, L.stream));
     pc_tree T = pc_tree_of(ix);
@@ -613,7 +639,7 @@ static int pc_query_dispatch(pc_index *ix, const pc_qargs &A, const float *q, in
             PC_CUDA(ix, cudaEventRecord(ix->ev_in, ix->stream));
             PC_CUDA(ix, cudaStreamWaitEvent(L.stream, ix->ev_in, 0));
         }
-        int rc = pc_run_batch(ix, L, A, q, m, qs, out_idx, out_f);
+        int rc = pc_run_batch(ix, L, A, q, m, qs, out_idx, out_f, true);
         if (rc != PC_OK) return rc;
         PC_CUDA(ix, cudaEventRecord(L.done, L.stream));
         return PC_OK;
@@ -631,7 +657,7 @@ static int pc_query_dispatch(pc_index *ix, const pc_qargs &A, const float *q, in
             if (out_idx) PC_CUDA(ix, cudaMemcpyAsync(L.d_i32, out_idx, (size_t)m * sizeof(int32_t), cudaMemcpyHostToDevice, L.stream));
             if (out_f) PC_CUDA(ix, cudaMemcpyAsync(L.d_f32, out_f, (size_t)m * sizeof(float), cudaMemcpyHostToDevice, L.stream));
         }
-        rc = pc_run_batch(ix, L, A, L.d_q, m, qs, out_idx ? L.d_i32 : nullptr, out_f ? L.d_f32 : nullptr);
+        rc = pc_run_batch(ix, L, A, L.d_q, m, qs, out_idx ? L.d_i32 : nullptr, out_f ? L.d_f32 : nullptr, true);
         if (rc != PC_OK) return rc;
         if (out_idx) PC_CUDA(ix, cudaMemcpyAsync(out_idx, L.d_i32, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, L.stream));
         if (out_f) PC_CUDA(ix, cudaMemcpyAsync(out_f, L.d_f32, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, L.stream));
