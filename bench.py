@@ -280,6 +280,24 @@ def run_b200(args):
         order_ms.append(a)
         search_ms.append(b)
     ix.profile(False)
+    # the same batch with the sensing-range early-out disabled (sample_range < 0): every query is searched
+    P_all = PcRadiusParams.make(start=start, search_margin=PARAMS["search_margin"], max_radius=PARAMS["max_radius"], sample_range=-1.0)
+    t_all = torch.empty_like(t_r)
+
+    def step_all():
+        rc = lib.pc_radius_batch(ix._h, C.c_void_p(t_q.data_ptr()), M, 3, PC_DEVICE, 0, C.byref(P_all), C.c_void_p(t_all.data_ptr()), None)
+        if rc != 0:
+            raise RuntimeError(lib.pc_last_error(ix._h).decode())
+
+    for _ in range(2):
+        step_all()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    for _ in range(5):
+        step_all()
+    eb.record()
+    torch.cuda.synchronize()
+    all_searched_qps = M * 5 / (ea.elapsed_time(eb) * 1e-3)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -366,6 +384,7 @@ def run_b200(args):
                         "mode": "PC_HOST_ASYNC, 3 batches in flight, one wait at the end", "blocking_call_value": e2e_blocking},
                 "gpu_launches": launches, "clocks": clocks,
                 "index_build_ms_per_frame": {"points": FRAME_POINTS, "median": float(np.median(fms[2:])), "min": float(min(fms))},
+                "all_queries_searched": {"value": all_searched_qps, "unit": UNIT, "note": "per GPU, same batch with sample_range = -1 (no early-outs), one stream"},
                 "index_build_ms_1M": float(np.median(build_ms[1:])), "index_broadcast_ms": bcast_ms,
                 "replicas_match_root": replica_ok}
         if not args.no_cpu_baseline and world == 1:
