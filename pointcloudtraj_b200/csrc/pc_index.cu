@@ -745,3 +745,12 @@ extern "C" int pc_radius_batch(pc_index *ix, const float *q_xyz, int64_t m, int6
 #include "clearance_host.inl"
 #include "comm_host.inl"
 #include "kd_compat.inl"
+
+#ifdef PC_STATS
+extern "C" int pc_stats_read(unsigned long long out[65], int reset)
+{
+    if (cudaMemcpyFromSymbol(out, pc_stats_hist, 65 * sizeof(unsigned long long)) != cudaSuccess) return PC_ECUDA;
+    if (reset) { unsigned long long z[65] = { 0 }; cudaMemcpyToSymbol(pc_stats_hist, z, sizeof z); }
+    return PC_OK;
+}
+#endif

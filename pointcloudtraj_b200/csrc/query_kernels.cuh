@@ -432,6 +432,9 @@ __device__ __forceinline__ void pc_scan_leaf2(const float4 *__restrict__ pts, co
     }
 }
 
+#ifdef PC_STATS
+__device__ unsigned long long pc_stats_hist[65];
+#endif
 __device__ __forceinline__ void pc_packet2_traverse(const pc_tree &T, const float qa[3], const float qb[3], pc_best &ba, pc_best &bb, int lane)
 {
     if (__ballot_sync(PC_FULL_MASK, ba.thr >= 0.f || bb.thr >= 0.f) == 0) return;
@@ -447,6 +450,12 @@ __device__ __forceinline__ void pc_packet2_traverse(const pc_tree &T, const floa
         const uint32_t w0 = __ballot_sync(PC_FULL_MASK, wa0 || wb0);
         const uint32_t w1 = __ballot_sync(PC_FULL_MASK, wa1 || wb1);
         const uint32_t c0 = 2u * node;
+#ifdef PC_STATS
+        {   // histogram of how many of the 64 queries wanted this node's children (diagnostic build only)
+            const int na = __popc(__ballot_sync(PC_FULL_MASK, wa0 || wa1)) + __popc(__ballot_sync(PC_FULL_MASK, wb0 || wb1));
+            if (lane == 0) atomicAdd(&pc_stats_hist[na], 1ull);
+        }
+#endif
         bool pop = true;
         if (w0 | w1) {
             // majority vote over the interested QUERIES (two votes per lane)
