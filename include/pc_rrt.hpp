@@ -13,6 +13,8 @@
 //   updateHeuristicRegion corridor_finder.cpp:298-330
 //   tracePath / checkValidEnd / isSuccessor     corridor_finder.cpp:578-641, 669-702
 //   SafeRegionExpansion  corridor_finder.cpp:704-763      (the wall-clock budget becomes an iteration budget)
+//   SafeRegionRefine     corridor_finder.cpp:765-815      the same loop on the existing tree
+//   SafeRegionEvaluate   corridor_finder.cpp:817-936      lazy re-validation of the best path against a new cloud (batched)
 //
 // Two drivers over the same restated logic:
 //   expand(max_iter)              one radius query per iteration, exactly the reference's loop order ("replay" mode: with
@@ -166,9 +168,11 @@ public:
     }
 
     // SafeRegionExpansion, one cloud query per iteration (corridor_finder.cpp:704-763)
-    int expand(int max_iterations)
+    int expand(int max_iterations) { initRoot(); return refine(max_iterations); }
+
+    // SafeRegionRefine (corridor_finder.cpp:765-815): the same loop on the existing tree (more samples, more rewiring)
+    int refine(int max_iterations)
     {
-        initRoot();
         int it = 0;
         for (; it < max_iterations && it < max_samples; it++) {
             double s[3];
@@ -188,9 +192,10 @@ public:
     }
 
     // speculative batches of K samples against a frozen snapshot of the node tree
-    int expandBatched(int max_iterations, int K)
+    int expandBatched(int max_iterations, int K) { initRoot(); return refineBatched(max_iterations, K); }
+
+    int refineBatched(int max_iterations, int K)
     {
-        initRoot();
         std::vector<double> centers((size_t)K * 3), radii((size_t)K);
         int it = 0;
         while (it < max_iterations && it < max_samples) {
@@ -220,6 +225,68 @@ public:
         removeInvalid();
         tracePath();
         return it;
+    }
+
+    // SafeRegionEvaluate (corridor_finder.cpp:817-936): after a NEW cloud has arrived, lazily re-validate the nodes of the
+    // current best path -- shrink radii, drop nodes that became too small or lost the connection to their parent /
+    // children, fall back to the next feasible end -- until the best path is valid again or none is left.  A node's new
+    // radius depends only on its centre, so each pass of the reference's loop is ONE batched radius call here (the
+    // reference issues one cloud query per path node, :835).  treeRepair (:938-1021), which the reference marks optional,
+    // is not restated.  Returns the number of passes.
+    int evaluate()
+    {
+        if (!path_exist_status) return 0;
+        int passes = 0;
+        std::vector<double> centers, radii;
+        for (;;) {
+            passes++;
+            centers.clear();
+            for (RrtNode *p : path_list_) if (p->pre) { centers.push_back(p->coord[0]); centers.push_back(p->coord[1]); centers.push_back(p->coord[2]); }
+            radii.resize(centers.size() / 3);
+            if (!radii.empty()) {
+                radius_(centers.data(), (int)radii.size(), radii.data());
+                cloud_queries += (int64_t)radii.size();
+                radius_calls++;
+            }
+            size_t k = 0;
+            for (RrtNode *ptr : path_list_) {
+                RrtNode *pre = ptr->pre;
+                if (!pre) continue;
+                const double update_radius = radii[k++];
+                const int ret = update_radius < safety_margin ? -1 : (update_radius < ptr->radius ? 0 : 1);   // checkNodeUpdate :661-667
+                ptr->radius = (float)update_radius;
+                if (ret == -1) {
+                    ptr->valid = false; invalid_set_.push_back(ptr); clearBranchS(ptr);
+                } else if (checkNodeRelation(dist(ptr->coord, pre->coord), ptr, pre) != -1) {
+                    if (ptr->valid) { ptr->valid = false; invalid_set_.push_back(ptr); clearBranchS(ptr); }
+                } else {
+                    const std::vector<RrtNode *> children = ptr->nxt;
+                    for (RrtNode *c : children) {
+                        if (checkNodeRelation(dist(ptr->coord, c->coord), ptr, c) != -1 && c->valid) {
+                            c->valid = false; invalid_set_.push_back(c); clearBranchS(c);
+                        }
+                    }
+                }
+            }
+            bool all_valid = true;
+            for (RrtNode *p : path_list_) all_valid = all_valid && p->valid;
+            if (all_valid) break;
+            std::vector<RrtNode *> feasible;
+            for (RrtNode *e : end_list_) if (e->valid && checkEnd(e)) feasible.push_back(e);
+            end_list_ = feasible;
+            if (feasible.empty()) { path_exist_status = false; inform_status = false; best_distance = inf(); break; }
+            best_end_ptr = feasible[0];
+            double best_cost = inf();
+            for (RrtNode *n : feasible) {
+                const double cost = n->g + dist(n->coord, end_pt) + dist(root_node->coord, commit_root);
+                if (cost < best_cost) { best_end_ptr = n; best_cost = cost; best_distance = best_cost; }
+            }
+            path_list_.clear();
+            for (RrtNode *p = best_end_ptr; p; p = p->pre) path_list_.push_back(p);
+        }
+        removeInvalid();
+        tracePath();
+        return passes;
     }
 
     // results (getPath, corridor_finder.h:131-134): centres (k x 3) and radii of the corridor spheres, root first

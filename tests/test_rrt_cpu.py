@@ -2,24 +2,51 @@
 import os
 import subprocess
 
+import numpy as np
+
 from pointcloudtraj_b200 import synth
-from rrt_common import read_records, validate_corridor, write_input
+from rrt_common import blocked_cloud, read_records, validate_corridor, write_input
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build(tmp):
+    exe = os.path.join(tmp, "rrt_cpu_check")
+    odir = os.path.join(ROOT, "oracle")
+    subprocess.run(["g++", "-std=c++14", "-O2", "-o", exe, os.path.join(ROOT, "tests", "c", "rrt_cpu_check.cpp"), "-I", os.path.join(ROOT, "include"),
+                    "-L", odir, "-loracle", f"-Wl,-rpath,{odir}"], check=True, capture_output=True)
+    return exe
+
+
+def _run(exe, tmp, n_rec):
+    p = subprocess.run([exe, os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, (p.returncode, p.stderr)
+    return read_records(os.path.join(tmp, "out.bin"), n_rec)
 
 
 def test_expansion_drivers_build_valid_corridors(tmp_path):
     tmp = str(tmp_path)
     pts, half = synth.forest_cloud(60_000, seed=6, variant="J", return_half=True)
-    write_input(os.path.join(tmp, "in.bin"), pts, max(half, 12.0), max_iter=6000, K=128)
-    exe = os.path.join(tmp, "rrt_cpu_check")
-    odir = os.path.join(ROOT, "oracle")
-    subprocess.run(["g++", "-std=c++14", "-O2", "-o", exe, os.path.join(ROOT, "tests", "c", "rrt_cpu_check.cpp"), "-I", os.path.join(ROOT, "include"),
-                    "-L", odir, "-loracle", f"-Wl,-rpath,{odir}"], check=True, capture_output=True)
-    p = subprocess.run([exe, os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")], capture_output=True, text=True, timeout=600)
-    assert p.returncode == 0, (p.returncode, p.stderr)
-    seq, bat = read_records(os.path.join(tmp, "out.bin"), 2)
+    half = max(half, 12.0)
+    exe = _build(tmp)
+    write_input(os.path.join(tmp, "in.bin"), pts, half, max_iter=6000, K=128)
+    seq, bat = _run(exe, tmp, 2)
     validate_corridor(seq, pts)
     validate_corridor(bat, pts)
     assert seq["cloud_queries"] > 3000 and bat["cloud_queries"] > 3000
     assert seq["nodes"] > 50 and bat["nodes"] > 50
+
+    # a new cloud message with obstacles ON a middle sphere of each corridor: SafeRegionEvaluate (corridor_finder.cpp:817-936)
+    # must drop those spheres; whatever corridor is reported afterwards is valid against the NEW cloud
+    blocked = [seq["path"][seq["k"] // 2], bat["path"][bat["k"] // 2]]
+    pts2 = blocked_cloud(pts, blocked)
+    write_input(os.path.join(tmp, "in.bin"), pts, half, max_iter=6000, K=128, pts2=pts2, refine_iter=2000)
+    recs = _run(exe, tmp, 6)
+    for grow, ev, ref, old, b in ((recs[0], recs[1], recs[2], seq, blocked[0]), (recs[3], recs[4], recs[5], bat, blocked[1])):
+        assert grow["k"] == old["k"] and (grow["path"] == old["path"]).all()          # deterministic first phase
+        assert ev["cloud_queries"] >= grow["cloud_queries"] + old["k"] - 1            # every non-root path node was re-queried
+        for rec in (ev, ref):
+            if rec["k"]:
+                assert not (rec["path"] == b).all(axis=1).any()                       # the blocked sphere is gone
+                validate_corridor(rec, pts2)
+        assert ref["k"] >= 2                                                          # refinement finds a way around the new obstacle
