@@ -110,8 +110,9 @@ pc_leaf_kernel(const float *__restrict__ xyz, int stride, const uint32_t *__rest
     }
     if ((threadIdx.x & (PC_LEAF - 1)) == 0) {
         int64_t leaf = slot / PC_LEAF;
-        // leaf n_leaves (if inside the array) is written as the empty box: it is the sibling of the last leaf when n_leaves is odd
-        if (leaf <= n_leaves && leaf < P) {
+        // the slots after the last leaf, up to the next multiple of 4, are written as empty boxes: they are the siblings /
+        // cousins of the last leaf that the binary (2 boxes per visit) and the 4-ary (4 boxes per visit) walks read
+        if (leaf < ((n_leaves + 4) & ~(int64_t)3) && leaf < P) {
             nodes[2 * (P + leaf)] = make_float4(lx, ly, lz, 0.f);
             nodes[2 * (P + leaf) + 1] = make_float4(hx, hy, hz, 0.f);
         }
@@ -119,8 +120,8 @@ pc_leaf_kernel(const float *__restrict__ xyz, int stride, const uint32_t *__rest
 }
 
 // ---- upper levels: each CTA folds 2*PC_UP_THREADS nodes of level `lvl0` into up to PC_UP_LEVELS levels above ----
-// Level l has base id P >> l and cnt_l = ceil(cnt_{l-1} / 2) real nodes (cnt_0 = n_leaves); node cnt_l of a level
-// (the possible sibling of its last real node) is written as the empty box.
+// Level l has base id P >> l and cnt_l = ceil(cnt_{l-1} / 2) real nodes (cnt_0 = n_leaves); the nodes from cnt_l up to the
+// next multiple of 4 (the possible sibling and cousins of its last real node) are written as empty boxes.
 #define PC_UP_THREADS 128
 #define PC_UP_LEVELS 8   // log2(2 * PC_UP_THREADS)
 
@@ -155,7 +156,7 @@ pc_upper_kernel(float4 *__restrict__ nodes, int64_t P, int lvl0, int64_t cnt0, i
         __syncthreads();   // everyone has read the previous level from shared memory
         if (t < width) {
             s_lo[t] = lo; s_hi[t] = hi;
-            if (k <= cnt && k < base) {   // base == number of slots on this level
+            if (k < ((cnt + 4) & ~(int64_t)3) && k < base) {   // pads up to the next multiple of 4; base == number of slots on this level
                 nodes[2 * (base + k)] = lo;
                 nodes[2 * (base + k) + 1] = hi;
             }

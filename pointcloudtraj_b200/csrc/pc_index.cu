@@ -22,8 +22,9 @@
 #define PC_VERSION_STRING "pcindex 0.1 (sm_100a)"
 #define PC_PIPE_LANES 3                 // concurrent H2D / kernel / D2H chunks for PC_HOST calls
 #define PC_HOST_CHUNK (1 << 21)         // queries per pipelined chunk (scripts/e2e_sweep.py: 2 Mi is the optimum for 10 M batches)
+#define PC_TINY_BATCH 4096              // PC_HOST calls up to this size: one kernel reading / writing mapped pinned host buffers
 #define PC_SORT_MIN_BATCH (1 << 17)     // PC_QUERY_AUTO orders batches at least this large (scripts/small_batch_ab.py: below
-                                        // ~130k queries one thread per query on the unordered batch has the lower latency)
+                                        // ~130k queries one warp per query on the unordered batch has the lower latency)
 
 static thread_local char g_create_error[256] = "";
 
@@ -75,16 +76,25 @@ struct pc_index {
     // generic device scratch for range / clearance
     void *scratch = nullptr; int64_t scratch_cap = 0;
 
+    // tiny PC_HOST batches (the planner's one-query-at-a-time calls): pinned, device-mapped host buffers the kernel reads the
+    // queries from and writes the results to directly -- one launch + one stream sync instead of two staged copies
+    float *tiny_q = nullptr, *tiny_f = nullptr; int32_t *tiny_i = nullptr;          // host addresses
+    float *tiny_q_dev = nullptr, *tiny_f_dev = nullptr; int32_t *tiny_i_dev = nullptr;   // the same memory as the device sees it
+
     int64_t launches = 0;
     bool profile = false, profiled = false;
     // tuning knobs (environment: PC_QUERY_KERNEL, PC_SORT_BITS, PC_MIN_IDLE), see DESIGN.md "Query kernel variants"
-    int query_kernel = 3;     // 1 = thread per query, 2 = persistent lane refill, 3 = warp packets of 32 (ordered batches), 4 = packets of 64
+    int query_kernel = 3;     // 1 = thread per query, 2 = persistent lane refill, 3 = warp packets of 32 (ordered batches) /
+                              // warp per query (small unordered ones), 4 = packets of 64
     bool query_kernel_auto = true;   // no PC_QUERY_KERNEL in the environment: 3, or 4 for dense batches
     int sort_bits = 24;       // radix-sorted key width of the batch ordering pass (0 = never order)
     bool sort_bits_auto = true;   // no PC_SORT_BITS in the environment: pick 24 or 32 from the batch density
     int min_idle = 8;         // persistent kernel: refill once this many lanes are idle
     int next_lane = 0;        // PC_HOST_ASYNC: lane of the next batch
     int shard_rank = 0, shard_n = 1;   // pc_batch_shard
+    int64_t coop_max = PC_SORT_MIN_BATCH;   // unordered batches up to this size run one warp per query (PC_COOP_MAX_BATCH)
+    int64_t sort_min = PC_SORT_MIN_BATCH;   // PC_QUERY_AUTO orders batches at least this large (PC_SORT_MIN_BATCH)
+    int64_t tiny_batch = PC_TINY_BATCH;   // PC_HOST calls up to this many queries take the mapped-memory path (PC_TINY_BATCH_QUERIES, 0 = off)
     int64_t host_chunk = PC_HOST_CHUNK;   // PC_HOST calls: queries per pipelined chunk (PC_HOST_CHUNK_QUERIES)
     char err[256] = "";
 };
@@ -188,6 +198,9 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         if (const char *v = getenv("PC_QUERY_KERNEL")) { ix->query_kernel_auto = false; int b_ = atoi(v); ix->query_kernel = (b_ >= 1 && b_ <= 4) ? b_ : 3; }
         if (const char *v = getenv("PC_SORT_BITS")) { ix->sort_bits_auto = false; int b_ = atoi(v); ix->sort_bits = b_ <= 0 ? 0 : (b_ <= 16 ? 16 : (b_ <= 24 ? 24 : 32)); }
         if (const char *v = getenv("PC_HOST_CHUNK_QUERIES")) { long long b_ = atoll(v); if (b_ >= 1024) ix->host_chunk = b_; }
+        if (const char *v = getenv("PC_COOP_MAX_BATCH")) { long long b_ = atoll(v); ix->coop_max = b_ < 0 ? 0 : b_; }
+        if (const char *v = getenv("PC_SORT_MIN_BATCH")) { long long b_ = atoll(v); ix->sort_min = b_ < 1 ? 1 : b_; }
+        if (const char *v = getenv("PC_TINY_BATCH_QUERIES")) { long long b_ = atoll(v); ix->tiny_batch = b_ < 0 ? 0 : (b_ > PC_TINY_BATCH ? PC_TINY_BATCH : b_); }
         if (const char *v = getenv("PC_MIN_IDLE")) { int b_ = atoi(v); ix->min_idle = b_ < 1 ? 1 : (b_ > 32 ? 32 : b_); }
         if (cuda_stream) { ix->stream = (cudaStream_t)cuda_stream; ix->own_stream = false; }
         else { TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking)); ix->own_stream = true; }
@@ -198,6 +211,12 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         TRY(cudaMalloc((void **)&ix->d_bbox, 8 * sizeof(uint32_t)));
         TRY(cudaHostAlloc((void **)&ix->h_bbox, 8 * sizeof(uint32_t), cudaHostAllocDefault));
         TRY(cudaMalloc((void **)&ix->digit_total, RS_RADIX * sizeof(uint32_t)));
+        TRY(cudaHostAlloc((void **)&ix->tiny_q, PC_TINY_BATCH * 4 * sizeof(float), cudaHostAllocMapped));
+        TRY(cudaHostAlloc((void **)&ix->tiny_f, PC_TINY_BATCH * sizeof(float), cudaHostAllocMapped));
+        TRY(cudaHostAlloc((void **)&ix->tiny_i, PC_TINY_BATCH * sizeof(int32_t), cudaHostAllocMapped));
+        TRY(cudaHostGetDevicePointer((void **)&ix->tiny_q_dev, ix->tiny_q, 0));
+        TRY(cudaHostGetDevicePointer((void **)&ix->tiny_f_dev, ix->tiny_f, 0));
+        TRY(cudaHostGetDevicePointer((void **)&ix->tiny_i_dev, ix->tiny_i, 0));
         for (int l = 0; l < PC_PIPE_LANES; l++) {
             // lane 0 shares the handle's stream (PC_DEVICE calls are ordered on it); the others overlap copies
             if (l == 0) { ix->lane[l].stream = ix->stream; ix->lane[l].own_stream = false; }
@@ -248,6 +267,9 @@ extern "C" void pc_index_destroy(pc_index *ix)
         if (L.t2) cudaEventDestroy(L.t2);
     }
     if (ix->h_bbox) cudaFreeHost(ix->h_bbox);
+    if (ix->tiny_q) cudaFreeHost(ix->tiny_q);
+    if (ix->tiny_f) cudaFreeHost(ix->tiny_f);
+    if (ix->tiny_i) cudaFreeHost(ix->tiny_i);
     cudaFree(ix->d_xyz); cudaFree(ix->d_bbox); cudaFree(ix->keys_a); cudaFree(ix->keys_b);
     cudaFree(ix->vals_a); cudaFree(ix->vals_b); cudaFree(ix->tile_hist); cudaFree(ix->digit_total);
     cudaFree(ix->tree); cudaFree(ix->scratch);
@@ -373,7 +395,7 @@ extern "C" int pc_index_build(pc_index *ix, const float *xyz, int64_t n, int64_t
     ix->nodes = ix->tree;
     ix->points = ix->tree + 4 * P;
     {
-        int64_t slots = (n_leaves + 1) * PC_LEAF;
+        int64_t slots = (n_leaves + 4) * PC_LEAF;       // up to 3 empty pad leaves after the last one
         int grid = (int)((slots + PC_BUILD_THREADS - 1) / PC_BUILD_THREADS);
         pc_leaf_kernel<<<grid, PC_BUILD_THREADS, 0, st>>>(src, stride, order, n, n_leaves, P, ix->points, ix->nodes);
         ix->launches++;
@@ -384,9 +406,9 @@ extern "C" int pc_index_build(pc_index *ix, const float *xyz, int64_t n, int64_t
     int64_t cnt = n_leaves;
     for (int lvl0 = 0; lvl0 < top;) {
         int nl = top - lvl0 < PC_UP_LEVELS ? top - lvl0 : PC_UP_LEVELS;
-        // one CTA more than the children need: the empty pad node next to the last real node of EVERY produced
-        // level must be written (index cnt_s of level s lives in CTA (cnt_s << s) / 256 <= (cnt + 255) / 256)
-        int grid = (int)((cnt + 2 * PC_UP_THREADS - 1) / (2 * PC_UP_THREADS)) + 1;
+        // four CTAs more than the children need: the empty pad nodes after the last real node of EVERY produced level
+        // (up to index cnt_s + 3) must be written, and index k of level s lives in CTA (k << s) / 256 <= (cnt + 255) / 256 + 3
+        int grid = (int)((cnt + 2 * PC_UP_THREADS - 1) / (2 * PC_UP_THREADS)) + 4;
         pc_upper_kernel<<<grid, PC_UP_THREADS, 0, st>>>(ix->nodes, P, lvl0, cnt, nl);
         ix->launches++;
         PC_CHECK_LAUNCH(ix);
@@ -515,7 +537,7 @@ static bool pc_want_sort(const pc_index *ix, int flags, int64_t m)
     if (ix->shard_n > 1) return true;          // the share is selected by the ordering pass
     if (flags & PC_QUERY_SORTED) return true;
     if (flags & PC_QUERY_UNSORTED) return false;
-    return m >= PC_SORT_MIN_BATCH;
+    return m >= ix->sort_min;
 }
 
 // run one device-resident batch on lane L
@@ -567,6 +589,13 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
             pc_query_packet_kernel<PC_KIND_NEAREST><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
         else
             pc_query_packet_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
+    } else if (ix->query_kernel >= 3 && !perm && m <= ix->coop_max) {
+        // small unordered batch: one warp per query (a thread-per-query search is a chain of dependent loads)
+        const int grid = (int)((m + PC_COOP_WARPS - 1) / PC_COOP_WARPS);
+        if (A.kind == PC_Q_NEAREST)
+            pc_query_coop_kernel<PC_KIND_NEAREST><<<grid, 32 * PC_COOP_WARPS, 0, L.stream>>>(T, A.R, d_q, m, qstride, d_idx, d_f);
+        else
+            pc_query_coop_kernel<PC_KIND_RADIUS><<<grid, 32 * PC_COOP_WARPS, 0, L.stream>>>(T, A.R, d_q, m, qstride, d_idx, d_f);
     } else if (ix->query_kernel != 2) {
         const int grid = (int)want;
         if (A.kind == PC_Q_NEAREST)
@@ -618,6 +647,39 @@ extern "C" int pc_profile_last_batch(pc_index *ix, float *order_ms, float *searc
     return PC_OK;
 }
 
+// Blocking PC_HOST call with a handful of queries -- what the unmodified planner loop issues (one radiusSearch per RRT*
+// iteration, corridor_finder.cpp:404).  Two staged copies plus three stream syncs cost ~65 us per call; here the
+// kernel reads the queries from, and writes the results to, pinned host memory mapped into the device's address space
+// (a few PCIe transactions), so a call is one launch and one sync on the handle's stream, and the kernel puts a whole warp on
+// every query (pc_query_coop_kernel).
+static int pc_tiny_host_batch(pc_index *ix, const pc_qargs &A, const float *q, int64_t m, int qs, int32_t *out_idx, float *out_f)
+{
+    memcpy(ix->tiny_q, q, (size_t)m * qs * sizeof(float));
+    pc_tree T = pc_tree_of(ix);
+    int32_t *d_i = out_idx ? ix->tiny_i_dev : nullptr;
+    float *d_f = out_f ? ix->tiny_f_dev : nullptr;
+    if (ix->query_kernel == 1) {             // PC_QUERY_KERNEL=1: one thread per query, for comparison
+        const int grid = (int)((m + PC_QUERY_THREADS - 1) / PC_QUERY_THREADS);
+        if (A.kind == PC_Q_NEAREST)
+            pc_query_simple_kernel<PC_KIND_NEAREST><<<grid, PC_QUERY_THREADS, 0, ix->stream>>>(T, A.R, ix->tiny_q_dev, m, qs, nullptr, nullptr, d_i, d_f);
+        else
+            pc_query_simple_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, ix->stream>>>(T, A.R, ix->tiny_q_dev, m, qs, nullptr, nullptr, d_i, d_f);
+    } else {
+        // one warp per query: the search of a single query is a chain of dependent loads, the warp shortens it
+        const int grid = (int)((m + PC_COOP_WARPS - 1) / PC_COOP_WARPS);
+        if (A.kind == PC_Q_NEAREST)
+            pc_query_coop_kernel<PC_KIND_NEAREST><<<grid, 32 * PC_COOP_WARPS, 0, ix->stream>>>(T, A.R, ix->tiny_q_dev, m, qs, d_i, d_f);
+        else
+            pc_query_coop_kernel<PC_KIND_RADIUS><<<grid, 32 * PC_COOP_WARPS, 0, ix->stream>>>(T, A.R, ix->tiny_q_dev, m, qs, d_i, d_f);
+    }
+    ix->launches++;
+    PC_CHECK_LAUNCH(ix);
+    PC_CUDA(ix, cudaStreamSynchronize(ix->stream));
+    if (out_idx) memcpy(out_idx, ix->tiny_i, (size_t)m * sizeof(int32_t));
+    if (out_f) memcpy(out_f, ix->tiny_f, (size_t)m * sizeof(float));
+    return PC_OK;
+}
+
 // PC_HOST: chunked pipeline over the lanes; PC_DEVICE: one batch on the handle's stream
 static int pc_query_dispatch(pc_index *ix, const pc_qargs &A, const float *q, int64_t m, int64_t q_stride, int space,
                              int32_t *out_idx, float *out_f)
@@ -626,6 +688,7 @@ static int pc_query_dispatch(pc_index *ix, const pc_qargs &A, const float *q, in
     if (m == 0) return PC_OK;
     const int qs = (int)q_stride;
     if (space == PC_DEVICE) return pc_run_batch(ix, ix->lane[0], A, q, m, qs, out_idx, out_f);
+    if (space == PC_HOST && m <= ix->tiny_batch && !pc_want_sort(ix, A.flags, m)) return pc_tiny_host_batch(ix, A, q, m, qs, out_idx, out_f);
 
     // order the side lanes after the last (possibly still running) index build / broadcast on the handle's stream
     for (int l = 1; l < PC_PIPE_LANES; l++) PC_CUDA(ix, cudaStreamWaitEvent(ix->lane[l].stream, ix->ev_ready, 0));

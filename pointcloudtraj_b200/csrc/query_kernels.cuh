@@ -407,7 +407,11 @@ pc_query_packet_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, 
 // of every visited node).  Giving each lane TWO queries -- slots t and t + 32 of the warp's 64 consecutive ordered
 // queries -- halves the record bytes and the control instructions per query-visit; the price is a slightly larger packet.
 // (Rejecting stale stack entries with a per-entry minimum distance and __reduce_min/max_sync was measured again on this
-// kernel: 12 % of the visits are stale, yet the extra warp reductions cost more than the visits saved -- 2.19 vs 2.03 ms.)
+// kernel: 12 % of the visits are stale, yet the extra warp reductions cost more than the visits saved -- 2.19 vs 2.03 ms.
+// So was a 4-ary walk of the same tree -- the grandchildren 4i..4i+3 of node i are one aligned 128-byte line, so a visit can
+// test four boxes and skip a level, children ordered by a packed-vote warp reduction: identical results, 2.06 vs 2.04 ms on
+// radius batches and 8.46 vs 7.84 ms on unbounded nearest batches (profiles/r1_sweep6*): the box tests it wastes on
+// grandchildren whose parent would have been pruned cost what the saved votes and stack traffic gain.)
 __device__ __forceinline__ void pc_scan_leaf2(const float4 *__restrict__ pts, const float qa[3], const float qb[3], pc_best &ba, pc_best &bb)
 {
     float4 p[PC_LEAF];
@@ -518,6 +522,92 @@ pc_query_packet2_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q,
 #pragma unroll
     for (int j = 0; j < 2; j++)
         if (valid[j]) pc_write_result<KIND>(R, b[j], k[j], out_idx, out_f);
+}
+
+// ---- variant 6: one WARP per query (tiny batches) ----------------------------------------------------------------------
+// The planner's own loop asks for ONE radius per call (corridor_finder.cpp:404), and then a search is a chain of dependent
+// loads: ~60-100 node visits of 0.5 us each with one thread per query.  Here the 32 lanes of a warp work on the same
+// query: the open nodes sit on a LIFO frontier in shared memory, every step the warp takes the (up to) 32 most recently
+// pushed -- deepest, nearest -- nodes, one per lane, tests their two child boxes (or scans their four points), shares the
+// tightened bound with one warp reduction and pushes the surviving children, the nearer ones on top.  The number of
+// dependent steps drops from the number of visits to roughly the depth of the tree.  The walk starts from the (real) nodes
+// of level 5.  Exactness as everywhere: fp32 filter against the shared bound, fp64 re-evaluation, and the lanes' private
+// bests are merged at the end by (d2, index).
+#define PC_COOP_CAP 1024
+#define PC_COOP_WARPS 4
+
+template <int KIND>
+__global__ void __launch_bounds__(32 * PC_COOP_WARPS)
+pc_query_coop_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, int64_t m, int qstride,
+                     int32_t *__restrict__ out_idx, float *__restrict__ out_f)
+{
+    __shared__ uint2 s_front[PC_COOP_WARPS][PC_COOP_CAP];      // (node, float bits of its box distance)
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t k = (int64_t)blockIdx.x * PC_COOP_WARPS + w;
+    if (k >= m) return;
+    const float *qq = q + (size_t)k * qstride;
+    const float qx = qq[0], qy = qq[1], qz = qq[2];
+    bool search = T.n_points > 0;
+    if (KIND == PC_KIND_RADIUS && search && pc_radius_early_out((double)qx, (double)qy, (double)qz, R)) search = false;
+    if (!search) { if (lane == 0) pc_write_trivial<KIND>(R, (uint32_t)k, out_idx, out_f); return; }
+    pc_best b; b.d2 = INFINITY; b.idx = -1; b.thr = (KIND == PC_KIND_RADIUS) ? R.bound_thr : FLT_MAX;
+    uint2 *F = s_front[w];
+    int size = 1;
+    if (T.P >= 64) {
+        // level 5 = nodes 32..63, each covering P / 32 leaves: only the real ones (the pads behind them are not all written)
+        const int64_t per = (int64_t)(T.P >> 5), n_leaves = (T.n_points + PC_LEAF - 1) / PC_LEAF;
+        size = (int)((n_leaves + per - 1) / per);
+        if (lane < size) F[lane] = make_uint2(32u + (uint32_t)lane, 0u);
+    } else if (lane == 0) F[0] = make_uint2(1u, 0u);
+    __syncwarp();
+    const uint32_t lt = (1u << lane) - 1u;
+    while (size > 0) {
+        // take the top of the frontier, one node per lane; near the capacity fall back to one node per step (a plain DFS,
+        // which grows the frontier by at most one entry per level)
+        const int take = (size + 64 <= PC_COOP_CAP) ? min(size, 32) : 1;
+        bool active = lane < take;
+        uint2 e = make_uint2(0u, 0u);
+        if (active) e = F[size - 1 - lane];
+        size -= take;
+        __syncwarp();
+        active = active && __uint_as_float(e.y) <= b.thr;
+        float dn = INFINITY, df = INFINITY;
+        uint32_t cn = 0, cf = 0;
+        if (active) {
+            if (e.x >= T.P) {
+                pc_scan_leaf(T.points + (size_t)(e.x - T.P) * PC_LEAF, qx, qy, qz, b);
+            } else {
+                const float4 *pair = T.nodes + 4ull * e.x;
+                const float4 lo0 = __ldg(pair), hi0 = __ldg(pair + 1), lo1 = __ldg(pair + 2), hi1 = __ldg(pair + 3);
+                const float d0 = pc_box_d2(lo0, hi0, qx, qy, qz), d1 = pc_box_d2(lo1, hi1, qx, qy, qz);
+                const bool first0 = d0 <= d1;
+                cn = 2u * e.x + (first0 ? 0u : 1u); cf = cn ^ 1u;
+                dn = fminf(d0, d1); df = fmaxf(d0, d1);
+            }
+        }
+        // one bound for the whole warp (thr >= 0, so the float order is the order of its bits)
+        b.thr = __uint_as_float(__reduce_min_sync(PC_FULL_MASK, __float_as_uint(b.thr)));
+        const bool wn = dn <= b.thr, wf = df <= b.thr;
+        const uint32_t mf = __ballot_sync(PC_FULL_MASK, wf), mn = __ballot_sync(PC_FULL_MASK, wn);
+        const int nf = __popc(mf), nn = __popc(mn);
+        if (wf) F[size + __popc(mf & lt)] = make_uint2(cf, __float_as_uint(df));
+        if (wn) F[size + nf + (nn - 1 - __popc(mn & lt))] = make_uint2(cn, __float_as_uint(dn));   // lane 0's child ends on top
+        size += nf + nn;
+        __syncwarp();
+    }
+    // merge the lanes' private bests: smallest (d2, index); d2 >= 0, so its bit pattern orders like the value
+    long long key = __double_as_longlong(b.d2);
+    uint32_t id = (uint32_t)b.idx;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long k2 = __shfl_xor_sync(PC_FULL_MASK, key, o);
+        const uint32_t i2 = __shfl_xor_sync(PC_FULL_MASK, id, o);
+        if (k2 < key || (k2 == key && i2 < id)) { key = k2; id = i2; }
+    }
+    if (lane == 0) {
+        b.d2 = __longlong_as_double(key); b.idx = (int32_t)id;
+        pc_write_result<KIND>(R, b, (uint32_t)k, out_idx, out_f);
+    }
 }
 
 // ---- ordering pass of a batch --------------------------------------------------------------------------

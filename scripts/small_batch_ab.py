@@ -13,13 +13,14 @@ pts, half = synth.forest_cloud(1_000_000, seed=1, variant="J", return_half=True)
 t_pts = torch.from_numpy(pts).to(dev)
 P = PcRadiusParams.make(0.25, 1.5, 30.0, (0.0, 0.0, 2.0))
 print(f"{'m':>8s} {'kernel':>6s} {'flags':>9s} {'ms':>8s}")
-for m in (1000, 5000, 20000, 50000, 100000, 200000):
+for m in (1000, 5000, 20000, 50000, 100000, 200000, 400000):
     q = torch.from_numpy(synth.rrt_queries(m, half, seed=5)).to(dev)
     out = torch.empty(m, dtype=torch.float32, device=dev)
+    # kernel 1 = one thread per query; 3 unsorted = one warp per query (pc_query_coop_kernel); 3 sorted = ordered warp packets
     for kern in (1, 3):
         for flags, fname in ((2, "unsorted"), (4, "sorted")):
-            if kern == 3 and flags == 2: continue
             os.environ["PC_QUERY_KERNEL"] = str(kern)
+            os.environ["PC_COOP_MAX_BATCH"] = str(1 << 30)
             ix = PointCloudIndex(max_points=len(pts), stream=stream)
             ix.build(t_pts)
             L = ix._L

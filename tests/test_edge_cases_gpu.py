@@ -127,3 +127,38 @@ def test_non_finite_points_in_the_cloud_are_never_returned(ix):
     bi, bd, _ = oracle.brute_nearest(pts[keep], q[:4000])          # brute force over the finite points only
     assert (idx[:4000] == keep[bi]).all() and (d2[:4000] == bd.astype(np.float32)).all()
     assert np.isin(idx, keep).all() and np.isfinite(d2).all()
+
+
+def test_tiny_host_batches_take_the_mapped_memory_path_with_identical_results(monkeypatch):
+    """PC_HOST calls of <= 4096 queries (the planner's one-query-at-a-time radiusSearch) run as one kernel on mapped pinned
+    memory; a handle with that path switched off (staged copies) must give the same bits, also across the size threshold."""
+    pts, half = synth.forest_cloud(80_000, seed=3, variant="J", return_half=True)
+    q = synth.rrt_queries(4200, half, seed=9)
+    P = PcRadiusParams.make(0.25, 1.5, 30.0, (0.0, 0.0, 2.0))
+    fast = PointCloudIndex(max_points=len(pts), device=0)
+    monkeypatch.setenv("PC_TINY_BATCH_QUERIES", "0")
+    staged = PointCloudIndex(max_points=len(pts), device=0)
+    monkeypatch.delenv("PC_TINY_BATCH_QUERIES")
+    try:
+        fast.build(pts); staged.build(pts)
+        ko = oracle.KdOracle().build(pts)
+        o_idx, o_d2 = ko.nearest(q)
+        for m in (1, 2, 31, 129, 4096, 4097, 4200):
+            n0 = fast.launches()
+            r1, i1 = fast.radius(q[:m], P, want_idx=True)
+            launches = fast.launches() - n0
+            r2, i2 = staged.radius(q[:m], P, want_idx=True)
+            assert (r1 == r2).all() and (i1 == i2).all()
+            assert launches == 1 or m > 4096                      # one kernel, no ordering pass
+            j1, d1 = fast.nearest(q[:m])
+            assert fast.nearest(q[:m], want_idx=False)[0] is None
+            j2, d2 = staged.nearest(q[:m])
+            assert (j1 == j2).all() and (d1 == d2).all() and (j1 == o_idx[:m]).all() and (d1 == o_d2[:m].astype(np.float32)).all()
+        # stride-4 queries, outputs partly disabled, empty index
+        q4 = np.zeros((100, 4), np.float32); q4[:, :3] = q[:100]
+        assert (fast.radius(q4, P) == staged.radius(q[:100], P)).all()
+        fast.build(np.zeros((0, 3), np.float32))
+        r, i = fast.radius(q[:5], P, want_idx=True)
+        assert (r == np.float32(1.25)).all() and (i == -1).all()
+    finally:
+        fast.close(); staged.close()
