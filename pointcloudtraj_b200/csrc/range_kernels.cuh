@@ -122,6 +122,123 @@ pc_range_fill_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstr
     pc_sort_list(out_idx + begin, want);
 }
 
+// ---- one WARP per range query -----------------------------------------------------------------------------------------
+// Same frontier walk as pc_query_coop_kernel (query_kernels.cuh), without a bound to tighten: the open nodes sit on a LIFO
+// frontier in shared memory, every step each lane takes one of them and either tests its two child boxes (survivors are
+// pushed with ballot-computed positions) or scans its leaf (hits are appended with ballot-computed positions).  The count
+// pass and the fill pass are the same walk; the fill pass then sorts its list by original index with a bitonic network in
+// the same shared memory (lists up to 1024 hits; longer ones fall back to the single-thread heap sort).
+#define PC_RCOOP_CAP 1024
+#define PC_RCOOP_WARPS 4
+
+template <bool FILL>
+__global__ void __launch_bounds__(32 * PC_RCOOP_WARPS)
+pc_range_coop_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstride,
+                     const double *__restrict__ range, int range_is_scalar,
+                     int64_t *__restrict__ counts, const int64_t *__restrict__ offsets, int32_t *__restrict__ out_idx)
+{
+    __shared__ uint32_t s_front[PC_RCOOP_WARPS][PC_RCOOP_CAP];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t k = (int64_t)blockIdx.x * PC_RCOOP_WARPS + w;
+    if (k >= m) return;
+    int64_t begin = 0, want = 0;
+    if (FILL) {
+        begin = offsets[k]; want = offsets[k + 1] - begin;
+        if (want == 0) return;
+    }
+    const float *qq = q + k * qstride;
+    const float qx = qq[0], qy = qq[1], qz = qq[2];
+    const double qxd = (double)qx, qyd = (double)qy, qzd = (double)qz;
+    const double r = range[range_is_scalar ? 0 : k];
+    const double r2 = __dmul_rn(r, r);
+    if (T.n_points == 0 || !(r2 == r2)) {          // empty index, NaN range
+        if (!FILL && lane == 0) counts[k] = 0;
+        return;
+    }
+    const float thr = fminf(__fmul_ru(__double2float_ru(r2), PC_THR_SLACK), FLT_MAX);
+    uint32_t *F = s_front[w];
+    int size = 1;
+    if (T.P >= 64) {
+        const int64_t per = (int64_t)(T.P >> 5), n_leaves = (T.n_points + PC_LEAF - 1) / PC_LEAF;
+        size = (int)((n_leaves + per - 1) / per);
+        if (lane < size) F[lane] = 32u + (uint32_t)lane;
+    } else if (lane == 0) F[0] = 1u;
+    __syncwarp();
+    const uint32_t lt = (1u << lane) - 1u;
+    int64_t total = 0;
+    while (size > 0) {
+        const int take = (size + 64 <= PC_RCOOP_CAP) ? min(size, 32) : 1;
+        const bool active = lane < take;
+        uint32_t node = 0;
+        if (active) node = F[size - 1 - lane];
+        size -= take;
+        __syncwarp();
+        const bool leaf = active && node >= T.P;
+        bool in0 = false, in1 = false;
+        if (active && !leaf) {
+            const float4 *pair = T.nodes + 4ull * node;
+            const float4 lo0 = __ldg(pair), hi0 = __ldg(pair + 1), lo1 = __ldg(pair + 2), hi1 = __ldg(pair + 3);
+            in0 = pc_box_d2(lo0, hi0, qx, qy, qz) <= thr;
+            in1 = pc_box_d2(lo1, hi1, qx, qy, qz) <= thr;
+        }
+        if (__ballot_sync(PC_FULL_MASK, leaf)) {
+            bool hit[PC_LEAF];
+            int32_t id[PC_LEAF];
+#pragma unroll
+            for (int i = 0; i < PC_LEAF; i++) { hit[i] = false; id[i] = 0; }
+            if (leaf) {
+                const int64_t slot0 = (int64_t)(node - T.P) * PC_LEAF;
+                const float4 *pts = T.points + slot0;
+#pragma unroll
+                for (int i = 0; i < PC_LEAF; i++) {
+                    const float4 p = __ldg(pts + i);
+                    const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+                    const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    if (d <= thr && slot0 + i < T.n_points)      // the tail of the last leaf repeats the last point
+                        hit[i] = pc_exact_d2(p.x, p.y, p.z, qxd, qyd, qzd) <= r2;
+                    id[i] = __float_as_int(p.w);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < PC_LEAF; i++) {
+                const uint32_t mask = __ballot_sync(PC_FULL_MASK, hit[i]);
+                if (FILL && hit[i]) out_idx[begin + total + __popc(mask & lt)] = id[i];
+                total += __popc(mask);
+            }
+        }
+        const uint32_t m0 = __ballot_sync(PC_FULL_MASK, in0), m1 = __ballot_sync(PC_FULL_MASK, in1);
+        const int n0 = __popc(m0);
+        if (in0) F[size + __popc(m0 & lt)] = 2u * node;
+        if (in1) F[size + n0 + __popc(m1 & lt)] = 2u * node + 1u;
+        size += n0 + __popc(m1);
+        __syncwarp();
+    }
+    if (!FILL) {
+        if (lane == 0) counts[k] = total;
+        return;
+    }
+    // canonical order: ascending original index
+    if (want <= PC_RCOOP_CAP) {
+        int N = 32;
+        while (N < want) N <<= 1;
+        for (int i = lane; i < N; i += 32) F[i] = i < want ? (uint32_t)out_idx[begin + i] : 0x7fffffffu;
+        __syncwarp();
+        for (int k2 = 2; k2 <= N; k2 <<= 1) {
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                for (int t = lane; t < (N >> 1); t += 32) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                    const uint32_t a = F[i], b = F[l];
+                    if ((a > b) == ((i & k2) == 0)) { F[i] = b; F[l] = a; }
+                }
+                __syncwarp();
+            }
+        }
+        for (int i = lane; i < want; i += 32) out_idx[begin + i] = (int32_t)F[i];
+    } else if (lane == 0) {
+        pc_sort_list(out_idx + begin, want);
+    }
+}
+
 // ---- exclusive scan of int64 counts into offsets[m + 1] (three small kernels) ---------------------------
 #define PC_SCAN_THREADS 256
 #define PC_SCAN_ITEMS 8

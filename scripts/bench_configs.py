@@ -12,6 +12,7 @@ Every config prints one JSON line with device-side timings (CUDA events) and a p
 brute force in the reference's operation order (torch on the GPU; independent of the library).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import sys
@@ -84,7 +85,20 @@ def c1_like(name, n_pts, n_q, seed):
     t0 = time.perf_counter()
     off, lst = ix.range(q, 1.0)
     range_ms = (time.perf_counter() - t0) * 1e3
+    # the same with device buffers (queries, offsets and lists stay on the GPU), CUDA events
+    t_off = torch.empty(n_q + 1, dtype=torch.int64, device=dev)
+    t_lst = torch.empty(max(int(off[-1]), 1), dtype=torch.int32, device=dev)
+    t_r = torch.ones(1, dtype=torch.float64, device=dev)       # PC_DEVICE: the range array is a device pointer too
+
+    def range_dev():
+        rc = ix._L.pc_range_batch(ix._h, C.c_void_p(t_q.data_ptr()), n_q, 3, 1, C.c_void_p(t_r.data_ptr()), 1, C.c_void_p(t_off.data_ptr()),
+                                  C.c_void_p(t_lst.data_ptr()), t_lst.numel())
+        assert rc == 0
+    range_dev_ms, _ = timed(range_dev)
+    same = bool((t_off.cpu().numpy() == off).all() and (t_lst.cpu().numpy()[: int(off[-1])] == lst).all())
     print(json.dumps({"config": name, "points": n_pts, "queries": n_q, "index_build_ms": build_ms,
+                      "range_r1_ms_device_buffers": range_dev_ms, "range_r1_device_qps": n_q / range_dev_ms * 1e3,
+                      "range_device_matches_host": same, "range_kernel": os.environ.get("PC_QUERY_KERNEL", "default (warp per query)"),
                       "range_r1_ms_host_buffers": range_ms, "range_r1_qps": n_q / range_ms * 1e3, "range_r1_mean_hits": float(off[-1]) / n_q,
                       "nearest_ms": nn_ms, "nearest_qps": n_q / nn_ms * 1e3, "radius_ms": rad_ms, "radius_qps": n_q / rad_ms * 1e3,
                       "radius_host_buffers_ms": host_ms, "parity_spot_check": brute_check(t_pts, t_q, idx, d2)}))
