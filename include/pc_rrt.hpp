@@ -15,6 +15,7 @@
 //   SafeRegionExpansion  corridor_finder.cpp:704-763      (the wall-clock budget becomes an iteration budget)
 //   SafeRegionRefine     corridor_finder.cpp:765-815      the same loop on the existing tree
 //   SafeRegionEvaluate   corridor_finder.cpp:817-936      lazy re-validation of the best path against a new cloud (batched)
+//   treeRepair           corridor_finder.cpp:938-1021     re-validation of the failed nodes' neighbourhoods (one batched call)
 //
 // Two drivers over the same restated logic:
 //   expand(max_iter)              one radius query per iteration, exactly the reference's loop order ("replay" mode: with
@@ -231,13 +232,14 @@ public:
     // current best path -- shrink radii, drop nodes that became too small or lost the connection to their parent /
     // children, fall back to the next feasible end -- until the best path is valid again or none is left.  A node's new
     // radius depends only on its centre, so each pass of the reference's loop is ONE batched radius call here (the
-    // reference issues one cloud query per path node, :835).  treeRepair (:938-1021), which the reference marks optional,
-    // is not restated.  Returns the number of passes.
+    // reference issues one cloud query per path node, :835).  The failed nodes are handed to treeRepair (:933).  Returns the
+    // number of passes.
     int evaluate()
     {
         if (!path_exist_status) return 0;
         int passes = 0;
         std::vector<double> centers, radii;
+        std::vector<FailedNode> fail_list;
         for (;;) {
             passes++;
             centers.clear();
@@ -253,17 +255,23 @@ public:
                 RrtNode *pre = ptr->pre;
                 if (!pre) continue;
                 const double update_radius = radii[k++];
-                const int ret = update_radius < safety_margin ? -1 : (update_radius < ptr->radius ? 0 : 1);   // checkNodeUpdate :661-667
+                const int ret = checkNodeUpdate(update_radius, ptr->radius);
+                const float old_radius = ptr->radius;
                 ptr->radius = (float)update_radius;
                 if (ret == -1) {
                     ptr->valid = false; invalid_set_.push_back(ptr); clearBranchS(ptr);
+                    fail_list.push_back(FailedNode(ptr->coord, old_radius));
                 } else if (checkNodeRelation(dist(ptr->coord, pre->coord), ptr, pre) != -1) {
-                    if (ptr->valid) { ptr->valid = false; invalid_set_.push_back(ptr); clearBranchS(ptr); }
+                    if (ptr->valid) {
+                        ptr->valid = false; invalid_set_.push_back(ptr); clearBranchS(ptr);
+                        fail_list.push_back(FailedNode(ptr->coord, old_radius));
+                    }
                 } else {
                     const std::vector<RrtNode *> children = ptr->nxt;
                     for (RrtNode *c : children) {
                         if (checkNodeRelation(dist(ptr->coord, c->coord), ptr, c) != -1 && c->valid) {
                             c->valid = false; invalid_set_.push_back(c); clearBranchS(c);
+                            fail_list.push_back(FailedNode(c->coord, c->radius));
                         }
                     }
                 }
@@ -285,9 +293,69 @@ public:
             for (RrtNode *p = best_end_ptr; p; p = p->pre) path_list_.push_back(p);
         }
         removeInvalid();
+        if (repair_after_evaluate) treeRepair(fail_list);
         tracePath();
         return passes;
     }
+
+    // treeRepair (corridor_finder.cpp:938-1021): where nodes failed, their neighbours most likely fail too -- re-query every
+    // valid node within 2 x radius of a failed node and invalidate what is too small or disconnected now.  A node's radius
+    // depends only on its centre, so the neighbours of ALL failed nodes are gathered first and answered by ONE batched
+    // radius call (the reference: one cloud query per neighbour, :973); the invalidation logic then runs in the
+    // reference's order on the cached radii.
+    struct FailedNode {
+        double coord[3]; float radius;
+        FailedNode(const double c[3], float r) : radius(r) { coord[0] = c[0]; coord[1] = c[1]; coord[2] = c[2]; }
+    };
+    void treeRepair(const std::vector<FailedNode> &fail_list)
+    {
+        std::vector<std::vector<RrtNode *>> near(fail_list.size());
+        std::vector<RrtNode *> todo;
+        for (size_t i = 0; i < fail_list.size(); i++) {
+            const float pos[3] = { (float)fail_list[i].coord[0], (float)fail_list[i].coord[1], (float)fail_list[i].coord[2] };
+            node_tree_.range(pos, fail_list[i].radius * 2.0f, near[i]);
+            for (RrtNode *p : near[i]) if (p != root_node && p->pre != root_node) todo.push_back(p);
+        }
+        std::sort(todo.begin(), todo.end(), [](const RrtNode *x, const RrtNode *y) { return x->serial < y->serial; });
+        todo.erase(std::unique(todo.begin(), todo.end()), todo.end());
+        std::vector<double> centers(todo.size() * 3), radii(todo.size());
+        for (size_t i = 0; i < todo.size(); i++) for (int a = 0; a < 3; a++) centers[3 * i + a] = todo[i]->coord[a];
+        if (!todo.empty()) {
+            radius_(centers.data(), (int)todo.size(), radii.data());
+            cloud_queries += (int64_t)todo.size();
+            radius_calls++;
+        }
+        auto cached = [&](const RrtNode *p) {
+            const size_t i = std::lower_bound(todo.begin(), todo.end(), p, [](const RrtNode *x, const RrtNode *y) { return x->serial < y->serial; }) - todo.begin();
+            return radii[i];
+        };
+        for (size_t i = 0; i < fail_list.size(); i++) {
+            for (RrtNode *ptr : near[i]) {
+                if (!ptr->valid) continue;
+                RrtNode *pre = ptr->pre;
+                if (pre == root_node || ptr == root_node) continue;
+                const double update_radius = cached(ptr);
+                const int ret = checkNodeUpdate(update_radius, ptr->radius);
+                ptr->radius = (float)update_radius;
+                if (ret == -1) {
+                    ptr->valid = false; invalid_set_.push_back(ptr); clearBranchS(ptr);
+                    continue;
+                }
+                if (pre && checkNodeRelation(dist(pre->coord, ptr->coord), pre, ptr) != -1 && pre->valid) {
+                    pre->valid = false; invalid_set_.push_back(pre); clearBranchS(pre);
+                    continue;
+                }
+                const std::vector<RrtNode *> children = ptr->nxt;
+                for (RrtNode *c : children) {
+                    if (checkNodeRelation(dist(ptr->coord, c->coord), ptr, c) != -1 && c->valid) {
+                        c->valid = false; invalid_set_.push_back(c); clearBranchS(c);
+                    }
+                }
+            }
+        }
+        removeInvalid();
+    }
+    bool repair_after_evaluate = true;      // the reference always calls treeRepair from SafeRegionEvaluate (:933)
 
     // results (getPath, corridor_finder.h:131-134): centres (k x 3) and radii of the corridor spheres, root first
     std::vector<double> path;
@@ -383,6 +451,13 @@ private:
         recordNode(n);
         treePrune(n);
         if ((int)invalid_set_.size() >= cach_size) removeInvalid();
+    }
+
+    // corridor_finder.cpp:661-667
+    int checkNodeUpdate(double new_radius, double old_radius) const
+    {
+        if (new_radius < safety_margin) return -1;
+        return new_radius < old_radius ? 0 : 1;
     }
 
     static int checkNodeRelation(double dis, const RrtNode *n1, const RrtNode *n2)
