@@ -12,6 +12,7 @@
 //   checkSafeTrajectory  Planner/src/sim_planning_demo.cpp:729-781 (a free function there; it only needs the cloud)
 //   firstCollision  Planner/src/status_inspector.cpp:33-46   ground-truth collision check of executed positions
 //   observe         Planner/src/camera_sensor.cpp:133-145    LiDAR-mode observation (all points within max_dist)
+//   NodeSnapshotIndex   corridor_finder.cpp:428-437          batched findNearstVertex against a frozen node set
 //
 // No Eigen/PCL/ROS dependency: points are plain double[3] / float arrays (pcl::PointXYZ is x,y,z,pad float32 =
 // stride 4; Eigen::Vector3d::data() is double[3]).
@@ -146,6 +147,33 @@ private:
     }
     pc_index *ix_ = nullptr;
     pc_radius_params params_;
+};
+
+// The RRT* NODE tree's nearest-vertex queries for a whole batch of samples: the reference asks kd_nearestf on
+// the node kd-tree once per sample (corridor_finder.cpp:428-437); in the speculative-batch driver the K samples of a batch
+// see the same frozen node set, so the set is indexed once (a few thousand centres: ~0.1 ms) and the K queries are one
+// exact batched nearest call -- same metric as kd_nearestf (fp64 distance to the float32 centres), ties -> lowest node index.
+class NodeSnapshotIndex {
+public:
+    explicit NodeSnapshotIndex(int device = 0, int64_t max_nodes = 1 << 16)
+    {
+        if (pc_index_create(&ix_, device, max_nodes, nullptr) != PC_OK)
+            throw std::runtime_error(std::string("pc_index_create: ") + pc_last_error(nullptr));
+    }
+    ~NodeSnapshotIndex() { pc_index_destroy(ix_); }
+    NodeSnapshotIndex(const NodeSnapshotIndex &) = delete;
+    NodeSnapshotIndex &operator=(const NodeSnapshotIndex &) = delete;
+
+    int nearest(const float *node_pos, int64_t n_nodes, const float *samples, int64_t k, int32_t *out_nearest, float *out_d2 = nullptr)
+    {
+        int rc = pc_index_build(ix_, node_pos, n_nodes, 3, PC_HOST);
+        if (rc != PC_OK) return rc;
+        return pc_nearest_batch(ix_, samples, k, 3, PC_HOST, PC_QUERY_AUTO, out_nearest, out_d2);
+    }
+    const char *lastError() const { return pc_last_error(ix_); }
+
+private:
+    pc_index *ix_ = nullptr;
 };
 
 }  // namespace pc

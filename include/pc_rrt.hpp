@@ -78,12 +78,13 @@ public:
         }
         items_.push_back(it);
     }
-    RrtNode *nearest(const float q[3]) const
+    RrtNode *nearest(const float q[3], double *out_d2 = nullptr) const
     {
         if (items_.empty()) return nullptr;
         int best = 0;
         double best_d2 = d2(0, q);
         search(0, q, best, best_d2);
+        if (out_d2) *out_d2 = best_d2;
         return items_[best].node;
     }
     // all nodes with d2 <= range^2, ascending insertion order
@@ -197,15 +198,26 @@ public:
 
     int refineBatched(int max_iterations, int K)
     {
-        std::vector<double> centers((size_t)K * 3), radii((size_t)K);
+        std::vector<double> centers((size_t)K * 3), radii((size_t)K), samples((size_t)K * 3);
+        std::vector<float> node_pos, sample_pos((size_t)K * 3);
+        std::vector<int32_t> nearest_idx((size_t)K);
         int it = 0;
         while (it < max_iterations && it < max_samples) {
             const int k_now = std::min(K, std::min(max_iterations, max_samples) - it);
             int n = 0;
+            for (int j = 0; j < k_now; j++) genSample(&samples[(size_t)j * 3]);
+            if (snapshot_nearest_) {
+                // the K nearest-vertex queries of a batch go against the SAME frozen node set, so they are one
+                // batched exact-NN call on the node centres (float positions, like kd_nearestf)
+                node_pos.resize(node_list_.size() * 3);
+                for (size_t i = 0; i < node_list_.size(); i++) for (int a = 0; a < 3; a++) node_pos[3 * i + a] = (float)node_list_[i]->coord[a];
+                for (size_t i = 0; i < (size_t)k_now * 3; i++) sample_pos[i] = (float)samples[i];
+                snapshot_nearest_(node_pos.data(), (int)node_list_.size(), sample_pos.data(), k_now, nearest_idx.data());
+                node_tree_calls++;
+            }
             for (int j = 0; j < k_now; j++) {
-                double s[3];
-                genSample(s);
-                RrtNode *nearest = findNearestVertex(s);
+                const double *s = &samples[(size_t)j * 3];
+                RrtNode *nearest = snapshot_nearest_ ? (nearest_idx[(size_t)j] >= 0 ? node_list_[(size_t)nearest_idx[(size_t)j]] : nullptr) : findNearestVertex(s);
                 if (!nearest || !nearest->valid) continue;
                 steer(s, nearest, &centers[(size_t)n * 3]);
                 n++;
@@ -362,7 +374,13 @@ public:
     std::vector<double> radius;
     bool path_exist_status = true;
     size_t nodeCount() const { return node_list_.size(); }
-    int64_t cloud_queries = 0, radius_calls = 0;
+    int64_t cloud_queries = 0, radius_calls = 0, node_tree_calls = 0;
+
+    // optional: batched nearest-vertex provider for the snapshot phase of expandBatched / refineBatched.
+    // node_pos: n_nodes x 3 float centres in node-list order; out_nearest[j] = index of the node nearest to sample j.
+    using SnapshotNearestFn = std::function<void(const float *node_pos, int n_nodes, const float *samples, int k, int32_t *out_nearest)>;
+    void setSnapshotNearest(SnapshotNearestFn fn) { snapshot_nearest_ = std::move(fn); }
+    const NodeKdTree &nodeTree() const { return node_tree_; }
 
     double safety_margin = 0, search_margin = 0, max_radius = 0, sample_range = 0;
 
@@ -653,6 +671,7 @@ private:
     }
 
     RadiusBatchFn radius_;
+    SnapshotNearestFn snapshot_nearest_;
     std::default_random_engine eng_;
     U rand_x, rand_y, rand_z, rand_bias, rand_x_in, rand_y_in, rand_z_in;
     U rand_u = U(0.0, 1.0), rand_v = U(0.0, 1.0), rand_phi = U(0.0, 2 * M_PI);

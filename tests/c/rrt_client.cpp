@@ -3,8 +3,9 @@
 //   A  GPU, one query per iteration        (pc::SafeRegionCloud::radiusSearch(double[3]))
 //   B  CPU oracle, one query per iteration (po_radius_search of oracle/planner_oracle.c)   -- TEST-ONLY checker
 //   C  GPU, speculative batches of K       (pc_radius_batch on the float32-cast centres)
+//   D  as C + the batch's nearest-vertex queries on the GPU (pc::NodeSnapshotIndex), checked against the CPU node tree
 // A and B must produce bit-identical corridors (replay mode); C is validated by the pytest against the oracle.
-// usage: rrt_client <in.bin> <out.bin>      file formats: rrt_io.hpp; output = the records of A, then B, then C
+// usage: rrt_client <in.bin> <out.bin>      file formats: rrt_io.hpp; output = the records of A, then B, then C, then D
 #include <cstdlib>
 #include "pc_corridor.hpp"
 #include "rrt_io.hpp"
@@ -57,6 +58,32 @@ int main(int argc, char **argv)
         for (int i = 0; i < m; i++) out[i] = rf[(size_t)i];
     });
     rrt_run(o, C, in, true, gpu_cloud);
+
+    // D  as C, plus the nearest-vertex queries of every batch answered on the GPU against the frozen node set;
+    //    every answer is checked here against the driver's own CPU node tree (same fp64 distance; ties may pick another node)
+    pc::NodeSnapshotIndex nodes(0, 1 << 16);
+    pc::SafeRegionRrtStarDriver D([&](const double *c, int m, double *out) {
+        qf.resize((size_t)m * 3); rf.resize((size_t)m);
+        for (size_t i = 0; i < qf.size(); i++) qf[i] = (float)c[i];
+        if (cloud.radiusSearch(qf.data(), m, 3, rf.data()) != PC_OK) exit(8);
+        for (int i = 0; i < m; i++) out[i] = rf[(size_t)i];
+    });
+    std::vector<float> nd2;
+    int batch_no = 0;
+    D.setSnapshotNearest([&](const float *node_pos, int n_nodes, const float *samples, int k, int32_t *out_nearest) {
+        nd2.resize((size_t)k);
+        if (nodes.nearest(node_pos, n_nodes, samples, k, out_nearest, nd2.data()) != PC_OK) exit(9);
+        if ((batch_no++ & 3) != 0) return;                      // check every fourth batch (keeps the timing meaningful)
+        for (int j = 0; j < k; j++) {
+            double want = 0.0;
+            D.nodeTree().nearest(samples + 3 * j, &want);
+            const float *p = node_pos + 3 * (size_t)out_nearest[j];
+            double got = 0.0;
+            for (int a = 0; a < 3; a++) { const double d = (double)p[a] - (double)samples[3 * j + a]; got += d * d; }
+            if (got != want || nd2[(size_t)j] != (float)want) { fprintf(stderr, "node-tree nearest mismatch: sample %d got %.17g want %.17g\n", j, got, want); exit(10); }
+        }
+    });
+    rrt_run(o, D, in, true, gpu_cloud);
     fclose(o);
     kdo_free(kt[0]); kdo_free(kt[1]);
     return 0;
