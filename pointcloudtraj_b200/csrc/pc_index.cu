@@ -21,7 +21,8 @@
 
 #define PC_VERSION_STRING "pcindex 0.1 (sm_100a)"
 #define PC_PIPE_LANES 3                 // concurrent H2D / kernel / D2H chunks for PC_HOST calls
-#define PC_HOST_CHUNK (1 << 21)         // queries per pipelined chunk (scripts/e2e_sweep.py: 2 Mi is the optimum for 10 M batches)
+#define PC_HOST_CHUNK (3 << 20)         // queries per pipelined chunk (scripts/e2e_sweep.py: 3 Mi with a 1/4, 1/2 ramp is the
+                                        // optimum for 10 M batches; smaller chunks are sparser subsets -> less coherent packets)
 #define PC_TINY_BATCH 4096              // PC_HOST calls up to this size: one kernel reading / writing mapped pinned host buffers
 #define PC_SORT_MIN_BATCH (1 << 17)     // PC_QUERY_AUTO orders batches at least this large (scripts/small_batch_ab.py: below
                                         // ~130k queries one warp per query on the unordered batch has the lower latency)
@@ -95,6 +96,7 @@ struct pc_index {
     int64_t coop_max = PC_SORT_MIN_BATCH;   // unordered batches up to this size run one warp per query (PC_COOP_MAX_BATCH)
     int64_t sort_min = PC_SORT_MIN_BATCH;   // PC_QUERY_AUTO orders batches at least this large (PC_SORT_MIN_BATCH)
     int64_t tiny_batch = PC_TINY_BATCH;   // PC_HOST calls up to this many queries take the mapped-memory path (PC_TINY_BATCH_QUERIES, 0 = off)
+    bool host_ramp = true;                // PC_HOST calls: smaller first chunks (PC_HOST_RAMP=0 switches it off)
     int64_t host_chunk = PC_HOST_CHUNK;   // PC_HOST calls: queries per pipelined chunk (PC_HOST_CHUNK_QUERIES)
     char err[256] = "";
 };
@@ -197,6 +199,7 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         ix->sm_count = prop.multiProcessorCount;
         if (const char *v = getenv("PC_QUERY_KERNEL")) { ix->query_kernel_auto = false; int b_ = atoi(v); ix->query_kernel = (b_ >= 1 && b_ <= 4) ? b_ : 3; }
         if (const char *v = getenv("PC_SORT_BITS")) { ix->sort_bits_auto = false; int b_ = atoi(v); ix->sort_bits = b_ <= 0 ? 0 : (b_ <= 16 ? 16 : (b_ <= 24 ? 24 : 32)); }
+        if (const char *v = getenv("PC_HOST_RAMP")) ix->host_ramp = atoi(v) != 0;
         if (const char *v = getenv("PC_HOST_CHUNK_QUERIES")) { long long b_ = atoll(v); if (b_ >= 1024) ix->host_chunk = b_; }
         if (const char *v = getenv("PC_COOP_MAX_BATCH")) { long long b_ = atoll(v); ix->coop_max = b_ < 0 ? 0 : b_; }
         if (const char *v = getenv("PC_SORT_MIN_BATCH")) { long long b_ = atoll(v); ix->sort_min = b_ < 1 ? 1 : b_; }
@@ -729,9 +732,16 @@ static int pc_query_dispatch(pc_index *ix, const pc_qargs &A, const float *q, in
     }
     const int64_t chunk = ix->host_chunk;
     int li = 0;
-    for (int64_t off = 0; off < m; off += chunk, li = (li + 1) % PC_PIPE_LANES) {
+    // ramp: the first chunks are smaller (1/4, 1/2 of the chunk size) so that the first kernel starts after a short copy
+    // instead of a full one -- the call is bound by the chain copy(first chunk) -> kernels of all chunks -> copy-back(last)
+    int64_t c = chunk;
+    int ramp = (ix->host_ramp && m > 2 * chunk) ? 2 : 0;
+    for (int64_t off = 0; off < m; off += c, li = (li + 1) % PC_PIPE_LANES) {
         pc_lane &L = ix->lane[li];
-        int64_t c = m - off < chunk ? m - off : chunk;
+        c = chunk >> ramp;
+        if (ramp > 0) ramp--;
+        if (c < PC_SORT_MIN_BATCH) c = chunk;
+        if (m - off < c) c = m - off;
         int rc;
         if ((rc = pc_grow(ix, &L.d_q, &L.q_cap, c * qs, chunk * 4)) != PC_OK) return rc;
         if (out_idx && (rc = pc_grow(ix, &L.d_i32, &L.i32_cap, c, chunk)) != PC_OK) return rc;
