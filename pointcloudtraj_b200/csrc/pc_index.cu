@@ -743,9 +743,11 @@ static int pc_query_dispatch(pc_index *ix, const pc_qargs &A, const float *q, in
         if (c < PC_SORT_MIN_BATCH) c = chunk;
         if (m - off < c) c = m - off;
         int rc;
-        if ((rc = pc_grow(ix, &L.d_q, &L.q_cap, c * qs, chunk * 4)) != PC_OK) return rc;
-        if (out_idx && (rc = pc_grow(ix, &L.d_i32, &L.i32_cap, c, chunk)) != PC_OK) return rc;
-        if (out_f && (rc = pc_grow(ix, &L.d_f32, &L.f32_cap, c, chunk)) != PC_OK) return rc;
+        // a multi-chunk call sizes the lane buffers for full chunks at once; a small call allocates only what it needs
+        const int64_t floor_q = m > chunk ? chunk : 0;
+        if ((rc = pc_grow(ix, &L.d_q, &L.q_cap, c * qs, floor_q * 4)) != PC_OK) return rc;
+        if (out_idx && (rc = pc_grow(ix, &L.d_i32, &L.i32_cap, c, floor_q)) != PC_OK) return rc;
+        if (out_f && (rc = pc_grow(ix, &L.d_f32, &L.f32_cap, c, floor_q)) != PC_OK) return rc;
         PC_CUDA(ix, cudaMemcpyAsync(L.d_q, q + off * qs, (size_t)c * qs * sizeof(float), cudaMemcpyHostToDevice, L.stream));
         if (ix->shard_n > 1) {
             // entries of other ranks' queries must come back untouched: stage the caller's current output contents
