@@ -161,10 +161,31 @@ def run_reference(args):
                                        "kd_nearest3 + radiusSearch epilogue, OpenMP over queries"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---- this repo's arm -----------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(props):
+    """Multi-GPU runs: pin this rank's threads to the CPUs next to its GPU (NVML's ideal CPU affinity) BEFORE any pinned
+    host buffer is allocated, so that the e2e leg's DMA traffic stays on the GPU's own socket (first-touch allocation).
+    Returns the CPU list (for the JSON line) or None when NVML gives no answer."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus_id = f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.encode())
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception as e:  # noqa: BLE001 -- binding is an optimisation only
+        print(f"[bench] NUMA binding skipped: {e}", file=sys.stderr)
+    return None
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -177,6 +198,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = bind_to_gpu_numa_node(torch.cuda.get_device_properties(local)) if world > 1 else None
     # one explicit non-default stream for everything: the library's kernels, torch's copies and the timing events
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     if world > 1:
@@ -386,19 +408,37 @@ def run_b200(args):
                 "index_build_ms_per_frame": {"points": FRAME_POINTS, "median": float(np.median(fms[2:])), "min": float(min(fms))},
                 "all_queries_searched": {"value": all_searched_qps, "unit": UNIT, "note": "per GPU, same batch with sample_range = -1 (no early-outs), one stream"},
                 "index_build_ms_1M": float(np.median(build_ms[1:])), "index_broadcast_ms": bcast_ms,
+                "host_cpu_binding": (f"{len(numa_cpus)} CPUs next to the GPU (NVML affinity)" if numa_cpus else None),
                 "replicas_match_root": replica_ok}
         if not args.no_cpu_baseline and world == 1:
             cb, r_cpu = cpu_baseline(pts, q_host, start, args.cpu_sample)
             cb["gpu_matches_cpu_sample"] = bool((r_cpu.astype(np.float32) == t_r[: len(r_cpu)].cpu().numpy()).all())
             line["cpu_baseline"] = cb
-        print(json.dumps(line))
+        emit(line)
     ix.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """Write the ONE JSON result line to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 if __name__ == "__main__":
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner at communicator
+    # creation, for one) is sent to stderr instead
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)
