@@ -27,7 +27,10 @@
  * arguments live in that space.  PC_DEVICE calls are asynchronous on the handle's stream (call
  * pc_index_sync or synchronise the stream you passed to pc_index_create); PC_HOST calls return
  * when the results are in the caller's host buffers (pinned buffers from pc_host_alloc make the
- * copies asynchronous and pipelined with the kernels).  PC_HOST_ASYNC calls (pinned host buffers) only enqueue the
+ * copies asynchronous and pipelined with the kernels).  Blocking PC_HOST calls of up to 4096
+ * queries -- the planner's own one-radiusSearch-per-iteration pattern -- take a low-latency path:
+ * queries and results travel through mapped pinned memory and a whole warp works on each
+ * search (about 20 us per single-query call, any host memory).  PC_HOST_ASYNC calls (pinned host buffers) only enqueue the
  * batch -- copy in, kernels, copy out -- on one of three internal streams in turn and return; results are valid after
  * pc_index_sync.  Back-to-back PC_HOST_ASYNC batches overlap their PCIe copies with each other's kernels; the caller
  * must give every batch in flight its own buffers.
