@@ -93,6 +93,9 @@ struct pc_index {
     int min_idle = 8;         // persistent kernel: refill once this many lanes are idle
     int next_lane = 0;        // PC_HOST_ASYNC: lane of the next batch
     int shard_rank = 0, shard_n = 1;   // pc_batch_shard
+    int coop_group = 0;                     // lanes per query of the small-batch kernel: 0 = by batch size, else 32 / 16 / 8 (PC_COOP_GROUP)
+    int64_t coop_g32_max = 24576, coop_g16_max = 65536;  // batch sizes up to which 32 / 16 lanes per query are used (measured:
+                                                         // narrower groups gain 5-12 % above these sizes, lose below)
     int64_t coop_max = PC_SORT_MIN_BATCH;   // unordered batches up to this size run one warp per query (PC_COOP_MAX_BATCH)
     int64_t sort_min = PC_SORT_MIN_BATCH;   // PC_QUERY_AUTO orders batches at least this large (PC_SORT_MIN_BATCH)
     int64_t tiny_batch = PC_TINY_BATCH;   // PC_HOST calls up to this many queries take the mapped-memory path (PC_TINY_BATCH_QUERIES, 0 = off)
@@ -201,6 +204,7 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         if (const char *v = getenv("PC_SORT_BITS")) { ix->sort_bits_auto = false; int b_ = atoi(v); ix->sort_bits = b_ <= 0 ? 0 : (b_ <= 16 ? 16 : (b_ <= 24 ? 24 : 32)); }
         if (const char *v = getenv("PC_HOST_RAMP")) ix->host_ramp = atoi(v) != 0;
         if (const char *v = getenv("PC_HOST_CHUNK_QUERIES")) { long long b_ = atoll(v); if (b_ >= 1024) ix->host_chunk = b_; }
+        if (const char *v = getenv("PC_COOP_GROUP")) { int b_ = atoi(v); ix->coop_group = (b_ == 32 || b_ == 16 || b_ == 8) ? b_ : 0; }
         if (const char *v = getenv("PC_COOP_MAX_BATCH")) { long long b_ = atoll(v); ix->coop_max = b_ < 0 ? 0 : b_; }
         if (const char *v = getenv("PC_SORT_MIN_BATCH")) { long long b_ = atoll(v); ix->sort_min = b_ < 1 ? 1 : b_; }
         if (const char *v = getenv("PC_TINY_BATCH_QUERIES")) { long long b_ = atoll(v); ix->tiny_batch = b_ < 0 ? 0 : (b_ > PC_TINY_BATCH ? PC_TINY_BATCH : b_); }
@@ -543,6 +547,30 @@ static bool pc_want_sort(const pc_index *ix, int flags, int64_t m)
     return m >= ix->sort_min;
 }
 
+// small unordered batch: G lanes per query.  A whole warp per query has the lowest latency while the batch fits the GPU's
+// resident warps; beyond that, narrower groups put more queries in flight (scripts/small_batch_ab.py).
+template <int G>
+static void pc_launch_coop_g(const pc_qargs &A, const pc_tree &T, const float *d_q, int64_t m, int qstride,
+                             int32_t *d_idx, float *d_f, cudaStream_t st)
+{
+    const int64_t per_cta = (int64_t)PC_COOP_WARPS * (32 / G);
+    const int grid = (int)((m + per_cta - 1) / per_cta);
+    if (A.kind == PC_Q_NEAREST)
+        pc_query_coop_kernel<PC_KIND_NEAREST, G><<<grid, 32 * PC_COOP_WARPS, 0, st>>>(T, A.R, d_q, m, qstride, d_idx, d_f);
+    else
+        pc_query_coop_kernel<PC_KIND_RADIUS, G><<<grid, 32 * PC_COOP_WARPS, 0, st>>>(T, A.R, d_q, m, qstride, d_idx, d_f);
+}
+
+static void pc_launch_coop(const pc_index *ix, const pc_qargs &A, const pc_tree &T, const float *d_q, int64_t m, int qstride,
+                           int32_t *d_idx, float *d_f, cudaStream_t st)
+{
+    int g = ix->coop_group;
+    if (g == 0) g = m <= ix->coop_g32_max ? 32 : (m <= ix->coop_g16_max ? 16 : 8);
+    if (g == 32) pc_launch_coop_g<32>(A, T, d_q, m, qstride, d_idx, d_f, st);
+    else if (g == 16) pc_launch_coop_g<16>(A, T, d_q, m, qstride, d_idx, d_f, st);
+    else pc_launch_coop_g<8>(A, T, d_q, m, qstride, d_idx, d_f, st);
+}
+
 // run one device-resident batch on lane L
 static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float *d_q, int64_t m, int qstride,
                         int32_t *d_idx, float *d_f, bool split_streams = false)
@@ -594,11 +622,7 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
             pc_query_packet_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
     } else if (ix->query_kernel >= 3 && !perm && m <= ix->coop_max) {
         // small unordered batch: one warp per query (a thread-per-query search is a chain of dependent loads)
-        const int grid = (int)((m + PC_COOP_WARPS - 1) / PC_COOP_WARPS);
-        if (A.kind == PC_Q_NEAREST)
-            pc_query_coop_kernel<PC_KIND_NEAREST><<<grid, 32 * PC_COOP_WARPS, 0, L.stream>>>(T, A.R, d_q, m, qstride, d_idx, d_f);
-        else
-            pc_query_coop_kernel<PC_KIND_RADIUS><<<grid, 32 * PC_COOP_WARPS, 0, L.stream>>>(T, A.R, d_q, m, qstride, d_idx, d_f);
+        pc_launch_coop(ix, A, T, d_q, m, qstride, d_idx, d_f, L.stream);
     } else if (ix->query_kernel != 2) {
         const int grid = (int)want;
         if (A.kind == PC_Q_NEAREST)
@@ -669,11 +693,7 @@ static int pc_tiny_host_batch(pc_index *ix, const pc_qargs &A, const float *q, i
             pc_query_simple_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, ix->stream>>>(T, A.R, ix->tiny_q_dev, m, qs, nullptr, nullptr, d_i, d_f);
     } else {
         // one warp per query: the search of a single query is a chain of dependent loads, the warp shortens it
-        const int grid = (int)((m + PC_COOP_WARPS - 1) / PC_COOP_WARPS);
-        if (A.kind == PC_Q_NEAREST)
-            pc_query_coop_kernel<PC_KIND_NEAREST><<<grid, 32 * PC_COOP_WARPS, 0, ix->stream>>>(T, A.R, ix->tiny_q_dev, m, qs, d_i, d_f);
-        else
-            pc_query_coop_kernel<PC_KIND_RADIUS><<<grid, 32 * PC_COOP_WARPS, 0, ix->stream>>>(T, A.R, ix->tiny_q_dev, m, qs, d_i, d_f);
+        pc_launch_coop(ix, A, T, ix->tiny_q_dev, m, qs, d_i, d_f, ix->stream);
     }
     ix->launches++;
     PC_CHECK_LAUNCH(ix);

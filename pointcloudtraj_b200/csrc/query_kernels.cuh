@@ -524,52 +524,58 @@ pc_query_packet2_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q,
         if (valid[j]) pc_write_result<KIND>(R, b[j], k[j], out_idx, out_f);
 }
 
-// ---- variant 6: one WARP per query (tiny batches) ----------------------------------------------------------------------
+// ---- variant 6: a GROUP of lanes per query (small batches) ------------------------------------------------------------
 // The planner's own loop asks for ONE radius per call (corridor_finder.cpp:404), and then a search is a chain of dependent
-// loads: ~60-100 node visits of 0.5 us each with one thread per query.  Here the 32 lanes of a warp work on the same
-// query: the open nodes sit on a LIFO frontier in shared memory, every step the warp takes the (up to) 32 most recently
-// pushed -- deepest, nearest -- nodes, one per lane, tests their two child boxes (or scans their four points), shares the
-// tightened bound with one warp reduction and pushes the surviving children, the nearer ones on top.  The number of
-// dependent steps drops from the number of visits to roughly the depth of the tree.  The walk starts from the (real) nodes
-// of level 5.  Exactness as everywhere: fp32 filter against the shared bound, fp64 re-evaluation, and the lanes' private
-// bests are merged at the end by (d2, index).
-#define PC_COOP_CAP 1024
+// loads: ~60-100 node visits of 0.5 us each with one thread per query.  Here G lanes (a whole warp for the smallest batches,
+// 16 or 8 lanes when there are more queries than the GPU holds warps) work on the same query: the open nodes sit on a LIFO
+// frontier in shared memory, every step the group takes the (up to) G most recently pushed -- deepest, nearest -- nodes,
+// one per lane, tests their two child boxes (or scans their four points), shares the tightened bound with one warp
+// reduction and pushes the surviving children, the nearer ones on top.  The number of dependent steps drops from the
+// number of visits to roughly the depth of the tree.  The walk starts from the (real) nodes of level 5 / 4 / 3.
+// Exactness as everywhere: fp32 filter against the shared bound, fp64 re-evaluation, and the lanes' private bests are
+// merged at the end by (d2, index).  Groups of one warp run different numbers of steps; every warp-level primitive is
+// called with the group's own lane mask.
 #define PC_COOP_WARPS 4
+#define PC_COOP_CAP(G) (32 * (G))          // frontier entries per group: 8 KB of shared memory per warp for every G
 
-template <int KIND>
+template <int KIND, int G>
 __global__ void __launch_bounds__(32 * PC_COOP_WARPS)
 pc_query_coop_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, int64_t m, int qstride,
                      int32_t *__restrict__ out_idx, float *__restrict__ out_f)
 {
-    __shared__ uint2 s_front[PC_COOP_WARPS][PC_COOP_CAP];      // (node, float bits of its box distance)
+    constexpr int GROUPS = 32 / G, CAP = PC_COOP_CAP(G), SEED_LEVEL = G == 32 ? 5 : (G == 16 ? 4 : 3);
+    __shared__ uint2 s_front[PC_COOP_WARPS * GROUPS][CAP];      // (node, float bits of its box distance)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t k = (int64_t)blockIdx.x * PC_COOP_WARPS + w;
+    const int gl = lane & (G - 1), grp = lane / G;              // lane inside the group, group inside the warp
+    const uint32_t gmask = G == 32 ? PC_FULL_MASK : (((1u << G) - 1u) << (grp * G));
+    const int64_t k = ((int64_t)blockIdx.x * PC_COOP_WARPS + w) * GROUPS + grp;
     if (k >= m) return;
     const float *qq = q + (size_t)k * qstride;
     const float qx = qq[0], qy = qq[1], qz = qq[2];
     bool search = T.n_points > 0;
     if (KIND == PC_KIND_RADIUS && search && pc_radius_early_out((double)qx, (double)qy, (double)qz, R)) search = false;
-    if (!search) { if (lane == 0) pc_write_trivial<KIND>(R, (uint32_t)k, out_idx, out_f); return; }
+    if (!search) { if (gl == 0) pc_write_trivial<KIND>(R, (uint32_t)k, out_idx, out_f); return; }
     pc_best b; b.d2 = INFINITY; b.idx = -1; b.thr = (KIND == PC_KIND_RADIUS) ? R.bound_thr : FLT_MAX;
-    uint2 *F = s_front[w];
+    uint2 *F = s_front[w * GROUPS + grp];
     int size = 1;
-    if (T.P >= 64) {
-        // level 5 = nodes 32..63, each covering P / 32 leaves: only the real ones (the pads behind them are not all written)
-        const int64_t per = (int64_t)(T.P >> 5), n_leaves = (T.n_points + PC_LEAF - 1) / PC_LEAF;
+    if (T.P >= 2u * G) {
+        // the seed level holds G nodes (ids G .. 2G-1), each covering P / G leaves: only the real ones (the pads behind them
+        // are not all written)
+        const int64_t per = (int64_t)(T.P >> SEED_LEVEL), n_leaves = (T.n_points + PC_LEAF - 1) / PC_LEAF;
         size = (int)((n_leaves + per - 1) / per);
-        if (lane < size) F[lane] = make_uint2(32u + (uint32_t)lane, 0u);
-    } else if (lane == 0) F[0] = make_uint2(1u, 0u);
-    __syncwarp();
-    const uint32_t lt = (1u << lane) - 1u;
+        if (gl < size) F[gl] = make_uint2((uint32_t)G + (uint32_t)gl, 0u);
+    } else if (gl == 0) F[0] = make_uint2(1u, 0u);
+    __syncwarp(gmask);
+    const uint32_t lt = (1u << gl) - 1u;
     while (size > 0) {
-        // take the top of the frontier, one node per lane; near the capacity fall back to one node per step (a plain DFS,
-        // which grows the frontier by at most one entry per level)
-        const int take = (size + 64 <= PC_COOP_CAP) ? min(size, 32) : 1;
-        bool active = lane < take;
+        // take the top of the frontier, one node per lane (grows it by at most G entries); within G + 32 entries of the
+        // capacity fall back to one node per step -- a plain DFS, which adds at most one entry per tree level (< 32)
+        const int take = (size + G + 32 <= CAP) ? min(size, G) : 1;
+        bool active = gl < take;
         uint2 e = make_uint2(0u, 0u);
-        if (active) e = F[size - 1 - lane];
+        if (active) e = F[size - 1 - gl];
         size -= take;
-        __syncwarp();
+        __syncwarp(gmask);
         active = active && __uint_as_float(e.y) <= b.thr;
         float dn = INFINITY, df = INFINITY;
         uint32_t cn = 0, cf = 0;
@@ -585,26 +591,26 @@ pc_query_coop_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, in
                 dn = fminf(d0, d1); df = fmaxf(d0, d1);
             }
         }
-        // one bound for the whole warp (thr >= 0, so the float order is the order of its bits)
-        b.thr = __uint_as_float(__reduce_min_sync(PC_FULL_MASK, __float_as_uint(b.thr)));
+        // one bound for the whole group (thr >= 0, so the float order is the order of its bits)
+        b.thr = __uint_as_float(__reduce_min_sync(gmask, __float_as_uint(b.thr)));
         const bool wn = dn <= b.thr, wf = df <= b.thr;
-        const uint32_t mf = __ballot_sync(PC_FULL_MASK, wf), mn = __ballot_sync(PC_FULL_MASK, wn);
+        const uint32_t mf = (__ballot_sync(gmask, wf) & gmask) >> (grp * G), mn = (__ballot_sync(gmask, wn) & gmask) >> (grp * G);
         const int nf = __popc(mf), nn = __popc(mn);
         if (wf) F[size + __popc(mf & lt)] = make_uint2(cf, __float_as_uint(df));
         if (wn) F[size + nf + (nn - 1 - __popc(mn & lt))] = make_uint2(cn, __float_as_uint(dn));   // lane 0's child ends on top
         size += nf + nn;
-        __syncwarp();
+        __syncwarp(gmask);
     }
     // merge the lanes' private bests: smallest (d2, index); d2 >= 0, so its bit pattern orders like the value
     long long key = __double_as_longlong(b.d2);
     uint32_t id = (uint32_t)b.idx;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const long long k2 = __shfl_xor_sync(PC_FULL_MASK, key, o);
-        const uint32_t i2 = __shfl_xor_sync(PC_FULL_MASK, id, o);
+    for (int o = G / 2; o > 0; o >>= 1) {
+        const long long k2 = __shfl_xor_sync(gmask, key, o);
+        const uint32_t i2 = __shfl_xor_sync(gmask, id, o);
         if (k2 < key || (k2 == key && i2 < id)) { key = k2; id = i2; }
     }
-    if (lane == 0) {
+    if (gl == 0) {
         b.d2 = __longlong_as_double(key); b.idx = (int32_t)id;
         pc_write_result<KIND>(R, b, (uint32_t)k, out_idx, out_f);
     }

@@ -162,3 +162,29 @@ def test_tiny_host_batches_take_the_mapped_memory_path_with_identical_results(mo
         assert (r == np.float32(1.25)).all() and (i == -1).all()
     finally:
         fast.close(); staged.close()
+
+
+@pytest.mark.parametrize("group", [8, 16])
+def test_small_batch_kernel_group_widths_agree(monkeypatch, group):
+    """The small-batch kernel puts 32, 16 or 8 lanes on a query depending on the batch size; forced widths must return the
+    same bits as the default choice -- on a tie-heavy lattice cloud (lowest index among exact ties) and on small trees."""
+    monkeypatch.setenv("PC_COOP_GROUP", str(group))
+    forced = PointCloudIndex(max_points=0, device=0)
+    monkeypatch.delenv("PC_COOP_GROUP")
+    auto = PointCloudIndex(max_points=0, device=0)
+    P = PcRadiusParams.make(0.0, 5.0, 30.0, (0.0, 0.0, 2.0))            # simulation.launch parameters: long free-space searches
+    try:
+        pts, half = synth.forest_cloud(120_000, seed=6, variant="L", return_half=True)
+        q = synth.rrt_queries(20_000, half, seed=4)
+        q[::2] = np.round(q[::2] / 0.05) * 0.05                          # half of the queries snapped to the lattice: exact ties
+        for n in (120_000, 5, 9, 40, 130, 700):
+            forced.build(pts[:n]); auto.build(pts[:n])
+            for m in (1, 333, 4096, 20_000):
+                i1, d1 = forced.nearest(q[:m]); i2, d2 = auto.nearest(q[:m])
+                assert (i1 == i2).all() and (d1 == d2).all()
+                r1, j1 = forced.radius(q[:m], P, want_idx=True); r2, j2 = auto.radius(q[:m], P, want_idx=True)
+                assert (r1 == r2).all() and (j1 == j2).all()
+        forced.build(pts[:30_000])
+        check_lowest_index_everywhere(pts[:30_000], q[:3000], forced.nearest(q[:3000])[0])     # independent of the default kernel
+    finally:
+        forced.close(); auto.close()
