@@ -393,7 +393,7 @@ extern "C" int pc_index_build(pc_index *ix, const float *xyz, int64_t n, int64_t
                  : pc_build_sorted<uint32_t, 8>(ix, src, stride, n, bits, &order);
     } else {
         if (ix->key_bytes < 8) return pc_fail(ix, PC_ECUDA, "internal: key buffer too narrow");
-        rc = pc_build_sorted<uint64_t, 16>(ix, src, stride, n, bits, &order);
+        rc = pc_build_sorted<uint64_t, 8>(ix, src, stride, n, bits, &order);
     }
     if (rc != PC_OK) return rc;
 

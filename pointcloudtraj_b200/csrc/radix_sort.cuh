@@ -7,7 +7,8 @@
 //   rs_histogram : per-tile digit histograms (warp-private shared-memory counters)
 //   rs_scan_rows : exclusive scan of each digit's row of tile counts (one CTA per digit)
 //   rs_scatter   : stable rank of every element inside its tile (match_any ballots per warp round,
-//                  warp-level running counters, scan across warps) + global base -> scatter
+//                  warp-level running counters, scan across warps), tile staged in shared memory in
+//                  output order, then written run by run (coalesced) to its global position
 // Stability: a warp owns a contiguous slice of the tile and walks it in rounds of 32 consecutive
 // elements, so (warp, round, lane) order is the input order.
 #pragma once
@@ -90,8 +91,10 @@ rs_scatter(const KeyT *__restrict__ keys_in, const uint32_t *__restrict__ vals_i
     if ((int64_t)blockIdx.x * (RS_THREADS * ITEMS) >= n) return;   // tile past the device-side count
     // counter[w][d]: first the running count of digit d seen by warp w, then its output base
     __shared__ uint32_t counter[RS_WARPS][RS_RADIX + 1];
-    __shared__ uint32_t digit_base[RS_RADIX];
+    __shared__ uint32_t digit_base[RS_RADIX], local_base[RS_RADIX], out_base[RS_RADIX];
     __shared__ uint32_t warp_sum[RS_WARPS];
+    __shared__ KeyT s_key[RS_THREADS * ITEMS];
+    __shared__ uint32_t s_val[RS_THREADS * ITEMS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < RS_WARPS * (RS_RADIX + 1); i += RS_THREADS) (&counter[0][0])[i] = 0;
 
@@ -140,24 +143,51 @@ rs_scatter(const KeyT *__restrict__ keys_in, const uint32_t *__restrict__ vals_i
         __syncwarp();
     }
     __syncthreads();
-    // thread d turns the per-warp counts of digit d into output bases
+    // thread d: the per-warp counts of digit d become offsets inside the digit's run of this tile; the tile's digit counts
+    // are scanned into the run's position in the tile (local_base) and paired with its position in the output (out_base)
     {
-        uint32_t run = digit_base[tid] + tile_prefix[(int64_t)tid * num_tiles + blockIdx.x];
+        uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) {
             uint32_t c = counter[w][tid];
             counter[w][tid] = run;
             run += c;
         }
+        uint32_t incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(PC_FULL_MASK, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sum[warp] = incl;      // (the digit_total scan above is done with warp_sum: synced since)
+        __syncthreads();
+        uint32_t woff = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) if (w < warp) woff += warp_sum[w];
+        local_base[tid] = woff + incl - run;
+        out_base[tid] = digit_base[tid] + tile_prefix[(int64_t)tid * num_tiles + blockIdx.x];
     }
     __syncthreads();
+    // stage the tile in shared memory in output order (digit runs, stable inside a run) ...
 #pragma unroll
     for (int r = 0; r < ITEMS; r++) {
         if (dig[r] < RS_RADIX) {
-            uint32_t pos = counter[warp][dig[r]] + rank[r];
-            keys_out[pos] = key[r];
-            vals_out[pos] = val[r];
+            const uint32_t lpos = local_base[dig[r]] + counter[warp][dig[r]] + rank[r];
+            s_key[lpos] = key[r];
+            s_val[lpos] = val[r];
         }
+    }
+    __syncthreads();
+    // ... and write it out run by run: consecutive threads write consecutive addresses inside a run (a run of 16 pairs is two
+    // full sectors per array instead of 32 single-element sector writes spread over ITEMS store instructions)
+    const int64_t tile_base = (int64_t)blockIdx.x * (RS_THREADS * ITEMS);
+    const int tile_n = (int)(n - tile_base < (int64_t)(RS_THREADS * ITEMS) ? n - tile_base : (int64_t)(RS_THREADS * ITEMS));
+    for (int j = tid; j < tile_n; j += RS_THREADS) {
+        const KeyT k = s_key[j];
+        const uint32_t d = rs_digit(k, shift);
+        const uint32_t pos = out_base[d] + ((uint32_t)j - local_base[d]);
+        keys_out[pos] = k;
+        vals_out[pos] = s_val[j];
     }
 }
 
