@@ -33,7 +33,7 @@ BYTES_PER_QUERY = 16            # algorithmic: 12 B query (xyz float32) in + 4 B
 FRAME_POINTS = 300_000          # C3 frame for the build-ms metric
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on the default workload, from the
 # `ncu --set full` capture summarised in profiles/r1_full_final.txt (547.9 MB + 104.1 MB); re-measure when the kernel changes
-NCU_TRAFFIC_BYTES = {10_000_000: 652_018_176}
+NCU_TRAFFIC_BYTES = {10_000_000: 652_639_232}
 
 
 def parse():
