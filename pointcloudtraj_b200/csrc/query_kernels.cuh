@@ -470,10 +470,13 @@ __device__ __forceinline__ void pc_packet2_traverse(const pc_tree &T, const floa
             const bool both = w0 != 0 && w1 != 0;
             bool first0 = w1 == 0;
             if (both) {
-                // majority vote over the interested QUERIES (two votes per lane); not needed when only one child is wanted
-                const uint32_t ia = __ballot_sync(PC_FULL_MASK, wa0 || wa1), ib = __ballot_sync(PC_FULL_MASK, wb0 || wb1);
-                const uint32_t pa = __ballot_sync(PC_FULL_MASK, a0 <= a1) & ia, pb = __ballot_sync(PC_FULL_MASK, b0 <= b1) & ib;
-                first0 = 2 * (__popc(pa) + __popc(pb)) >= __popc(ia) + __popc(ib);
+                // majority vote of the lanes' FIRST queries that are interested (not needed when only one child is wanted).
+                // Measured (profiles/r1_sweep8_vote_variants.txt): letting both queries of a lane vote costs two more ballots
+                // and orders no better (1.955 vs 1.841 ms); a packed __reduce_add_sync vote is no faster than ballots (1.954);
+                // letting the first interested lane decide alone is cheaper still but orders worse (1.949).
+                const uint32_t ia = __ballot_sync(PC_FULL_MASK, wa0 || wa1);
+                const uint32_t pa = __ballot_sync(PC_FULL_MASK, a0 <= a1) & ia;
+                first0 = 2 * __popc(pa) >= __popc(ia);
             }
             const uint32_t cn = c0 + (first0 ? 0u : 1u), cf = cn ^ 1u;
             if (c0 >= T.P) {
