@@ -32,6 +32,14 @@ struct pc_tree {
     uint32_t P;            // leaf base (power of two >= 2)
 };
 
+// one box (min, max: 32 bytes, 32-byte aligned) with ONE 256-bit read-only load (sm_100: LDG.E.256)
+__device__ __forceinline__ void pc_load_box(const float4 *__restrict__ box, float4 &lo, float4 &hi)
+{
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+        : "l"(box));
+}
+
 __device__ __forceinline__ float pc_box_d2(const float4 lo, const float4 hi, float qx, float qy, float qz)
 {
     float dx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.0f);
@@ -77,7 +85,7 @@ __device__ __forceinline__ void pc_scan_leaf(const float4 *__restrict__ pts, flo
     float4 p[PC_LEAF];
     float d[PC_LEAF];
 #pragma unroll
-    for (int i = 0; i < PC_LEAF; i++) p[i] = __ldg(pts + i);
+    for (int i = 0; i < PC_LEAF; i += 2) pc_load_box(pts + i, p[i], p[i + 1]);     // two points per 256-bit load
     float dmin = FLT_MAX;
 #pragma unroll
     for (int i = 0; i < PC_LEAF; i++) {
@@ -101,7 +109,9 @@ __device__ __forceinline__ void pc_nearest_traverse(const pc_tree &T, float qx, 
     for (;;) {
         // children of `node` are the aligned pair (2 node, 2 node + 1) = nodes[4 node .. 4 node + 3]
         const float4 *pair = T.nodes + 4ull * node;
-        const float4 lo0 = __ldg(pair), hi0 = __ldg(pair + 1), lo1 = __ldg(pair + 2), hi1 = __ldg(pair + 3);
+        float4 lo0, hi0, lo1, hi1;
+        pc_load_box(pair, lo0, hi0);
+        pc_load_box(pair + 2, lo1, hi1);
         const float d0 = pc_box_d2(lo0, hi0, qx, qy, qz);
         const float d1 = pc_box_d2(lo1, hi1, qx, qy, qz);
         const uint32_t c0 = 2u * node;
@@ -289,7 +299,9 @@ pc_query_persist_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q,
                 node = 0;
             } else {
                 const float4 *pair = T.nodes + 4ull * node;
-                const float4 lo0 = __ldg(pair), hi0 = __ldg(pair + 1), lo1 = __ldg(pair + 2), hi1 = __ldg(pair + 3);
+                float4 lo0, hi0, lo1, hi1;
+                pc_load_box(pair, lo0, hi0);
+                pc_load_box(pair + 2, lo1, hi1);
                 const float d0 = pc_box_d2(lo0, hi0, qx, qy, qz);
                 const float d1 = pc_box_d2(lo1, hi1, qx, qy, qz);
                 const uint32_t c0 = 2u * node;
@@ -330,7 +342,9 @@ __device__ __forceinline__ void pc_packet_traverse(const pc_tree &T, float qx, f
     uint32_t node = 1;
     for (;;) {
         const float4 *pair = T.nodes + 4ull * node;
-        const float4 lo0 = __ldg(pair), hi0 = __ldg(pair + 1), lo1 = __ldg(pair + 2), hi1 = __ldg(pair + 3);
+        float4 lo0, hi0, lo1, hi1;
+        pc_load_box(pair, lo0, hi0);
+        pc_load_box(pair + 2, lo1, hi1);
         const float d0 = pc_box_d2(lo0, hi0, qx, qy, qz);
         const float d1 = pc_box_d2(lo1, hi1, qx, qy, qz);
         const uint32_t w0 = __ballot_sync(PC_FULL_MASK, d0 <= b.thr);
@@ -420,7 +434,7 @@ __device__ __forceinline__ void pc_scan_leaf2(const float4 *__restrict__ pts, co
     float4 p[PC_LEAF];
     float da[PC_LEAF], db[PC_LEAF];
 #pragma unroll
-    for (int i = 0; i < PC_LEAF; i++) p[i] = __ldg(pts + i);
+    for (int i = 0; i < PC_LEAF; i += 2) pc_load_box(pts + i, p[i], p[i + 1]);     // two points per 256-bit load
     float mina = FLT_MAX, minb = FLT_MAX;
 #pragma unroll
     for (int i = 0; i < PC_LEAF; i++) {
@@ -452,7 +466,9 @@ __device__ __forceinline__ void pc_packet2_traverse(const pc_tree &T, const floa
     uint32_t node = 1;
     for (;;) {
         const float4 *pair = T.nodes + 4ull * node;
-        const float4 lo0 = __ldg(pair), hi0 = __ldg(pair + 1), lo1 = __ldg(pair + 2), hi1 = __ldg(pair + 3);
+        float4 lo0, hi0, lo1, hi1;
+        pc_load_box(pair, lo0, hi0);
+        pc_load_box(pair + 2, lo1, hi1);
         const float a0 = pc_box_d2(lo0, hi0, qa[0], qa[1], qa[2]), a1 = pc_box_d2(lo1, hi1, qa[0], qa[1], qa[2]);
         const float b0 = pc_box_d2(lo0, hi0, qb[0], qb[1], qb[2]), b1 = pc_box_d2(lo1, hi1, qb[0], qb[1], qb[2]);
         const bool wa0 = a0 <= ba.thr, wa1 = a1 <= ba.thr, wb0 = b0 <= bb.thr, wb1 = b1 <= bb.thr;
@@ -593,7 +609,9 @@ pc_query_coop_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, in
                 pc_scan_leaf(T.points + (size_t)(e.x - T.P) * PC_LEAF, qx, qy, qz, b);
             } else {
                 const float4 *pair = T.nodes + 4ull * e.x;
-                const float4 lo0 = __ldg(pair), hi0 = __ldg(pair + 1), lo1 = __ldg(pair + 2), hi1 = __ldg(pair + 3);
+                float4 lo0, hi0, lo1, hi1;
+                pc_load_box(pair, lo0, hi0);
+                pc_load_box(pair + 2, lo1, hi1);
                 const float d0 = pc_box_d2(lo0, hi0, qx, qy, qz), d1 = pc_box_d2(lo1, hi1, qx, qy, qz);
                 const bool first0 = d0 <= d1;
                 cn = 2u * e.x + (first0 ? 0u : 1u); cf = cn ^ 1u;
