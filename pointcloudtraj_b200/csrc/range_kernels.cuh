@@ -45,7 +45,9 @@ __device__ __forceinline__ int64_t pc_range_traverse(const pc_tree &T, float qx,
     int64_t count = 0;
     for (;;) {
         const float4 *pair = T.nodes + 4ull * node;
-        const float4 lo0 = __ldg(pair), hi0 = __ldg(pair + 1), lo1 = __ldg(pair + 2), hi1 = __ldg(pair + 3);
+        float4 lo0, hi0, lo1, hi1;
+        pc_load_box(pair, lo0, hi0);
+        pc_load_box(pair + 2, lo1, hi1);
         const bool in0 = pc_box_d2(lo0, hi0, qx, qy, qz) <= thr;
         const bool in1 = pc_box_d2(lo1, hi1, qx, qy, qz) <= thr;
         const uint32_t c0 = 2u * node;
@@ -177,7 +179,9 @@ pc_range_coop_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstr
         bool in0 = false, in1 = false;
         if (active && !leaf) {
             const float4 *pair = T.nodes + 4ull * node;
-            const float4 lo0 = __ldg(pair), hi0 = __ldg(pair + 1), lo1 = __ldg(pair + 2), hi1 = __ldg(pair + 3);
+            float4 lo0, hi0, lo1, hi1;
+            pc_load_box(pair, lo0, hi0);
+            pc_load_box(pair + 2, lo1, hi1);
             in0 = pc_box_d2(lo0, hi0, qx, qy, qz) <= thr;
             in1 = pc_box_d2(lo1, hi1, qx, qy, qz) <= thr;
         }
