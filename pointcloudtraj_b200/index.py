@@ -194,16 +194,19 @@ class PointCloudIndex:
         first = np.ascontiguousarray(traj_first_seg, dtype=np.int32)
         n_traj = first.shape[0] - 1
         tn = np.zeros(n_traj) if t_now is None else np.ascontiguousarray(t_now, dtype=np.float64)
-        traj = (L.PcTraj * max(n_traj, 1))()
-        for t in range(n_traj):
-            traj[t].first_seg = int(first[t]); traj[t].num_seg = int(first[t + 1] - first[t]); traj[t].t_now = float(tn[t])
+        # pc_traj records {int32 first_seg, int32 num_seg, double t_now} filled without a Python loop
+        traj = np.zeros(max(n_traj, 1), dtype=np.dtype([("first_seg", "<i4"), ("num_seg", "<i4"), ("t_now", "<f8")]))
+        assert traj.dtype.itemsize == C.sizeof(L.PcTraj)
+        traj["first_seg"][:n_traj] = first[:-1]
+        traj["num_seg"][:n_traj] = np.diff(first)
+        traj["t_now"][:n_traj] = tn
         so = np.ascontiguousarray(seg_order, dtype=np.int32)
         sT = np.ascontiguousarray(seg_T, dtype=np.float64)
         sc = np.ascontiguousarray(seg_coef_off, dtype=np.int64)
         cf = np.ascontiguousarray(coef, dtype=np.float64)
         fh = np.empty(n_traj, np.int32); mr = np.empty(n_traj, np.float32); ns = np.empty(n_traj, np.int32)
         vp = lambda a: C.c_void_p(a.ctypes.data)
-        self._check(self._L.pc_clearance_batch(self._h, C.cast(traj, C.c_void_p), n_traj, vp(so), vp(sT), vp(sc), so.shape[0],
+        self._check(self._L.pc_clearance_batch(self._h, C.c_void_p(traj.ctypes.data), n_traj, vp(so), vp(sT), vp(sc), so.shape[0],
                                                vp(cf), cf.shape[0], L.PC_HOST, float(dt), float(horizon), C.byref(params),
                                                vp(fh), vp(mr), vp(ns)))
         return fh, mr, ns
