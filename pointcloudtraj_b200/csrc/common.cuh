@@ -106,6 +106,28 @@ __device__ __forceinline__ uint32_t pc_hilbert30(float x, float y, float z, cons
                               pc_cell_coord(z, f.lo[2], f.inv_cell, f.max_cell));
 }
 
+// the same transform for `bits` (11..21) bits per axis, interleaved into a 3 * bits wide key (clouds beyond 4 Mi points)
+__device__ __forceinline__ uint64_t pc_hilbert63(float x, float y, float z, const pc_frame &f, int bits)
+{
+    uint32_t X[3] = { pc_cell_coord(x, f.lo[0], f.inv_cell, f.max_cell), pc_cell_coord(y, f.lo[1], f.inv_cell, f.max_cell),
+                      pc_cell_coord(z, f.lo[2], f.inv_cell, f.max_cell) };
+    const uint32_t M = 1u << (bits - 1);
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {
+        const uint32_t P = Q - 1;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            if (X[i] & Q) X[0] ^= P;
+            else { const uint32_t t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+        }
+    }
+    X[1] ^= X[0];
+    X[2] ^= X[1];
+    uint32_t t = 0;
+    for (uint32_t Q = M; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
+    X[0] ^= t; X[1] ^= t; X[2] ^= t;
+    return (pc_spread21(X[0]) << 2) | (pc_spread21(X[1]) << 1) | pc_spread21(X[2]);
+}
+
 __device__ __forceinline__ uint64_t pc_morton63(float x, float y, float z, const pc_frame &f)
 {
     uint64_t cx = pc_cell_coord(x, f.lo[0], f.inv_cell, f.max_cell);
