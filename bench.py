@@ -33,7 +33,7 @@ BYTES_PER_QUERY = 16            # algorithmic: 12 B query (xyz float32) in + 4 B
 FRAME_POINTS = 300_000          # C3 frame for the build-ms metric
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on the default workload, from the
 # `ncu --set full` capture summarised in profiles/r1_full_final.txt (547.9 MB + 104.1 MB); re-measure when the kernel changes
-NCU_TRAFFIC_BYTES = {10_000_000: 653_782_528}
+NCU_TRAFFIC_BYTES = {10_000_000: 653_199_616}
 
 
 def parse():
@@ -402,7 +402,7 @@ def run_b200(args):
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                              "algorithmic_bytes_per_query": BYTES_PER_QUERY,
                              "limiter": "not HBM: the 32 MB index is L2-resident; ncu (profiles/r1_full_final.txt) shows issue slots "
-                                        "81 % busy, L1/TEX 60 %, DRAM 4 % -- the kernel is instruction-issue bound"},
+                                        "77 % busy, L1/TEX 58 %, DRAM 6 % -- the kernel is instruction-issue bound"},
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 12 * M, "d2h_bytes_per_step": 4 * M,
                         "steps": e2e_steps, "matches_device_result": same,
                         "mode": "PC_HOST_ASYNC, 3 batches in flight, one wait at the end", "blocking_call_value": e2e_blocking},

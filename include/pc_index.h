@@ -66,7 +66,7 @@ extern "C" {
 /* flags for pc_radius_batch / pc_clearance_batch */
 #define PC_RADIUS_BOUNDED   0  /* default: search only within max_radius + search_margin (exact for the radius) */
 #define PC_RADIUS_FULL_NN   1  /* unbounded search: out_idx is the true nearest point even where the radius clamps */
-/* flags for pc_nearest_batch / pc_radius_batch: reorder the batch along a Morton curve first (same results) */
+/* flags for pc_nearest_batch / pc_radius_batch: reorder the batch along a space-filling (Hilbert) curve first (same results) */
 #define PC_QUERY_AUTO      0
 #define PC_QUERY_UNSORTED  2
 #define PC_QUERY_SORTED    4
@@ -182,7 +182,7 @@ void pc_shard_range(int64_t m, int rank, int n_ranks, int64_t *begin, int64_t *e
 /* number of kernels this library launched on the handle since the last reset (for bench.py's gpu_launches) */
 int64_t pc_launch_count(const pc_index *ix, int reset);
 /* When enabled, PC_DEVICE query batches record CUDA events around their two phases on the handle's stream;
- * pc_profile_last_batch waits for them and returns the device time of the Morton ordering of the batch
+ * pc_profile_last_batch waits for them and returns the device time of the curve ordering of the batch
  * (0 when the batch was not reordered) and of the search kernel, in ms. */
 int  pc_profile_enable(pc_index *ix, int on);
 int  pc_profile_last_batch(pc_index *ix, float *order_ms, float *search_ms);

@@ -1,10 +1,10 @@
-// build_kernels.cuh -- index construction kernels (bbox, Morton keys, leaf gather, bounding-box tree).
+// build_kernels.cuh -- index construction kernels (bbox, curve keys, leaf gather, bounding-box tree).
 //
 // Index layout in HBM: ONE float4 array, P = 2^k >= max(2, ceil(n / 2)) leaf slots, heap numbering (root = node 1,
 // children of i are 2i and 2i+1, leaf j is node P + j):
 //   boxes  tree[0 .. 4P)  : node i's box is tree[2i] = min (xyz), tree[2i+1] = max (xyz); the boxes of the two children
 //                           of i are therefore the aligned 64-byte record tree[4i .. 4i+3]
-//   points tree[4P .. 6P) : leaf j holds points[2j], points[2j+1] in Morton order, (x, y, z, original index as int
+//   points tree[4P .. 6P) : leaf j holds points[2j], points[2j+1] in curve order, (x, y, z, original index as int
 //                           bits); when n is odd the last slot repeats the last real point
 // A traversal step loads the record of the node it visits: a box pair (64 B) or a leaf's two points (32 B).
 // Unused box slots hold the empty box (min = +inf, max = -inf).
@@ -97,7 +97,7 @@ pc_keygen_kernel(const float *__restrict__ xyz, int64_t n, int stride, const uin
     }
 }
 
-// ---- leaves: gather the cloud into Morton order (one thread per point slot) and box every 8 slots ----
+// ---- leaves: gather the cloud into curve order (one thread per point slot) and box every PC_LEAF slots ----
 __global__ void __launch_bounds__(PC_BUILD_THREADS)
 pc_leaf_kernel(const float *__restrict__ xyz, int stride, const uint32_t *__restrict__ order, int64_t n,
                int64_t n_leaves, int64_t P, float4 *__restrict__ points, float4 *__restrict__ nodes)

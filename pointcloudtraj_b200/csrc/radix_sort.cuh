@@ -1,7 +1,7 @@
 // radix_sort.cuh -- hand-written stable LSD radix sort of (key, uint32 value) pairs, 8 bits per pass.
 //
 // Replaces the N sequential kd_insert3 calls of the reference (Utils/kdtree/src/kdtree.c:244-251):
-// ordering the cloud along a Morton curve IS the index construction.
+// ordering the cloud along a space-filling curve IS the index construction.
 //
 // Per pass three kernels, no host synchronisation:
 //   rs_histogram : per-tile digit histograms (warp-private shared-memory counters)
