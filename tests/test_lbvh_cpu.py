@@ -12,3 +12,31 @@ def test_radix_tree_nodes_match_recursive_construction(tmp_path):
     p = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stderr
     assert "lbvh ok" in p.stdout
+
+
+def test_planned_index_layout_and_walk_are_exact(tmp_path):
+    """Records laid out as the planned CUDA build will write them (child references in the .w words, leaves of <= 4 points,
+    boxes fitted bottom-up in arbitrary node order) and walked by pc_lbvh_nearest: exact nearest point, lowest index among
+    ties, on a jittered forest, a tie-heavy lattice forest, tiny clouds and coincident points."""
+    import numpy as np
+    from pointcloudtraj_b200 import synth
+    exe = str(tmp_path / "lbvh_index_check")
+    subprocess.run(["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tests", "c", "lbvh_index_check.cpp")],
+                   check=True, capture_output=True)
+    cases = []
+    pts, half = synth.forest_cloud(40_000, seed=6, variant="J", return_half=True)
+    cases.append((pts[:, :3], synth.rrt_queries(600, half, seed=3)))
+    pts, half = synth.forest_cloud(30_000, seed=6, variant="L", return_half=True)
+    q = synth.rrt_queries(600, half, seed=4)
+    q[::2] = np.round(q[::2] / 0.05) * 0.05
+    cases.append((pts[:, :3], q))
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 4, 5, 9, 33):
+        cases.append((rng.normal(size=(n, 3)), rng.normal(size=(100, 3))))
+    cases.append((np.tile([[1.5, -2.0, 0.75]], (300, 1)), rng.normal(size=(50, 3))))
+    for k, (p, q) in enumerate(cases):
+        fp, fq = str(tmp_path / f"p{k}.bin"), str(tmp_path / f"q{k}.bin")
+        np.ascontiguousarray(p, np.float32).tofile(fp)
+        np.ascontiguousarray(q, np.float32).tofile(fq)
+        r = subprocess.run([exe, fp, fq], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "mismatches=0" in r.stdout, (k, r.stdout, r.stderr)
