@@ -40,3 +40,24 @@ def test_planned_index_layout_and_walk_are_exact(tmp_path):
         np.ascontiguousarray(q, np.float32).tofile(fq)
         r = subprocess.run([exe, fp, fq], capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "mismatches=0" in r.stdout, (k, r.stdout, r.stderr)
+
+
+def test_packet_walk_over_the_planned_index_is_exact(tmp_path):
+    """The 64-query packet walk (shared stack, any-query-wants-it tests, vote of the first 32 queries, leaf and inner children
+    mixed under one node) emulated on the CPU over the planned index and over the implicit tree at HEAD: both exact on a
+    tie-heavy lattice forest, bounded and unbounded."""
+    import numpy as np
+    from pointcloudtraj_b200 import synth
+    exe = str(tmp_path / "lbvh_packet_check")
+    subprocess.run(["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tests", "c", "lbvh_packet_check.cpp")],
+                   check=True, capture_output=True)
+    pts, half = synth.forest_cloud(20_000, seed=6, variant="L", return_half=True)
+    q = synth.rrt_queries(2000, half, seed=3)
+    q[::2] = np.round(q[::2] / 0.05) * 0.05
+    fp, fq = str(tmp_path / "p.bin"), str(tmp_path / "q.bin")
+    np.ascontiguousarray(pts[:, :3], np.float32).tofile(fp)
+    np.ascontiguousarray(q, np.float32).tofile(fq)
+    for bound in ("1.75", "0"):
+        for extra in ([], ["implicit"]):
+            r = subprocess.run([exe, fp, fq, bound] + extra, capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0 and "mismatches=0" in r.stdout, (bound, extra, r.stdout, r.stderr)
