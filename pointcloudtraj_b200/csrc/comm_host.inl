@@ -131,6 +131,7 @@ extern "C" int pc_index_broadcast(pc_index *ix, pc_comm *c, int root)
             if ((rc = pc_reserve_cloud(ix, h.n)) != PC_OK) return rc;
         }
         ix->n = h.n; ix->n_leaves = h.n_leaves; ix->P = h.P; ix->build_timed = false;
+        ix->lbvh_ready = false;                 // the experimental second tree is not broadcast: receivers walk the implicit one
         ix->nodes = ix->tree;
         ix->points = ix->tree + 4 * h.P;
         if (h.n > 0) PC_CUDA(ix, cudaMemcpyAsync(ix->d_bbox, h.bbox, sizeof h.bbox, cudaMemcpyHostToDevice, st));

@@ -16,6 +16,7 @@
 #include "radix_sort.cuh"
 #include "build_kernels.cuh"
 #include "query_kernels.cuh"
+#include "lbvh_kernels.cuh"
 #include "range_kernels.cuh"
 #include "clearance_kernels.cuh"
 
@@ -81,6 +82,13 @@ struct pc_index {
     // queries from and writes the results to directly -- one launch + one stream sync instead of two staged copies
     float *tiny_q = nullptr, *tiny_f = nullptr; int32_t *tiny_i = nullptr;          // host addresses
     float *tiny_q_dev = nullptr, *tiny_f_dev = nullptr; int32_t *tiny_i_dev = nullptr;   // the same memory as the device sees it
+
+    // experimental prefix-split tree (lbvh_kernels.cuh), only with PC_LBVH=1 in the environment at pc_index_create
+    bool use_lbvh = false, lbvh_ready = false;
+    float4 *lbvh_rec = nullptr;            // (cap - 1) records of 4 float4
+    int32_t *lbvh_parent = nullptr;
+    int *lbvh_arrived = nullptr;
+    uint32_t lbvh_root = PC_REF_LEAF;
 
     int64_t launches = 0;
     bool profile = false, profiled = false;
@@ -172,8 +180,15 @@ static int pc_reserve_cloud(pc_index *ix, int64_t n)
     PC_CUDA(ix, cudaMalloc((void **)&ix->vals_b, (size_t)cap * sizeof(uint32_t)));
     int64_t leaves = (cap + PC_LEAF - 1) / PC_LEAF;
     int64_t P = pc_pow2_ge(leaves);
-    ix->tree_cap = 4 * P + PC_LEAF * P;
+    ix->tree_cap = 4 * P + PC_LEAF * P + 2 * PC_LEAF;      // + padding points for leaf scans that start anywhere (lbvh)
     PC_CUDA(ix, cudaMalloc((void **)&ix->tree, (size_t)ix->tree_cap * sizeof(float4)));
+    if (ix->use_lbvh) {
+        cudaFree(ix->lbvh_rec); cudaFree(ix->lbvh_parent); cudaFree(ix->lbvh_arrived);
+        ix->lbvh_rec = nullptr; ix->lbvh_parent = nullptr; ix->lbvh_arrived = nullptr; ix->lbvh_ready = false;
+        PC_CUDA(ix, cudaMalloc((void **)&ix->lbvh_rec, (size_t)cap * 4 * sizeof(float4)));
+        PC_CUDA(ix, cudaMalloc((void **)&ix->lbvh_parent, (size_t)cap * sizeof(int32_t)));
+        PC_CUDA(ix, cudaMalloc((void **)&ix->lbvh_arrived, (size_t)cap * sizeof(int)));
+    }
     ix->hist_cap = (int64_t)RS_RADIX * (rs_num_tiles<8>(cap) + 1);
     PC_CUDA(ix, cudaMalloc((void **)&ix->tile_hist, (size_t)ix->hist_cap * sizeof(uint32_t)));
     ix->cap = cap;
@@ -204,6 +219,7 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         if (const char *v = getenv("PC_SORT_BITS")) { ix->sort_bits_auto = false; int b_ = atoi(v); ix->sort_bits = b_ <= 0 ? 0 : (b_ <= 16 ? 16 : (b_ <= 24 ? 24 : 32)); }
         if (const char *v = getenv("PC_HOST_RAMP")) ix->host_ramp = atoi(v) != 0;
         if (const char *v = getenv("PC_HOST_CHUNK_QUERIES")) { long long b_ = atoll(v); if (b_ >= 1024) ix->host_chunk = b_; }
+        if (const char *v = getenv("PC_LBVH")) ix->use_lbvh = atoi(v) != 0;
         if (const char *v = getenv("PC_COOP_GROUP")) { int b_ = atoi(v); ix->coop_group = (b_ == 32 || b_ == 16 || b_ == 8) ? b_ : 0; }
         if (const char *v = getenv("PC_COOP_MAX_BATCH")) { long long b_ = atoll(v); ix->coop_max = b_ < 0 ? 0 : b_; }
         if (const char *v = getenv("PC_SORT_MIN_BATCH")) { long long b_ = atoll(v); ix->sort_min = b_ < 1 ? 1 : b_; }
@@ -280,6 +296,7 @@ extern "C" void pc_index_destroy(pc_index *ix)
     cudaFree(ix->d_xyz); cudaFree(ix->d_bbox); cudaFree(ix->keys_a); cudaFree(ix->keys_b);
     cudaFree(ix->vals_a); cudaFree(ix->vals_b); cudaFree(ix->tile_hist); cudaFree(ix->digit_total);
     cudaFree(ix->tree); cudaFree(ix->scratch);
+    cudaFree(ix->lbvh_rec); cudaFree(ix->lbvh_parent); cudaFree(ix->lbvh_arrived);
     if (ix->ev_b0) cudaEventDestroy(ix->ev_b0);
     if (ix->ev_b1) cudaEventDestroy(ix->ev_b1);
     if (ix->ev_ready) cudaEventDestroy(ix->ev_ready);
@@ -333,7 +350,7 @@ extern "C" void pc_shard_range(int64_t m, int rank, int n_ranks, int64_t *begin,
 
 // ---- index build -----------------------------------------------------------------------------------
 template <typename KeyT, int ITEMS>
-static int pc_build_sorted(pc_index *ix, const float *src, int stride, int64_t n, int bits, uint32_t **order_out)
+static int pc_build_sorted(pc_index *ix, const float *src, int stride, int64_t n, int bits, uint32_t **order_out, void **keys_out)
 {
     cudaStream_t st = ix->stream;
     const int grid = (int)((n + PC_BUILD_THREADS - 1) / PC_BUILD_THREADS < (int64_t)ix->sm_count * 8
@@ -347,6 +364,7 @@ static int pc_build_sorted(pc_index *ix, const float *src, int stride, int64_t n
                                            ix->tile_hist, ix->digit_total, st, &ix->launches);
     PC_CHECK_LAUNCH(ix);
     *order_out = which ? ix->vals_b : ix->vals_a;
+    *keys_out = which ? ix->keys_b : ix->keys_a;
     return PC_OK;
 }
 
@@ -357,7 +375,7 @@ extern "C" int pc_index_build(pc_index *ix, const float *xyz, int64_t n, int64_t
         return pc_fail(ix, PC_EINVAL, "pc_index_build: bad argument (n=%lld stride=%lld space=%d)", (long long)n, (long long)stride_floats, space);
     if (n > ((int64_t)1 << 31) - 16) return pc_fail(ix, PC_EINVAL, "pc_index_build: at most 2^31-16 points");
     PC_CUDA(ix, cudaSetDevice(ix->device));
-    if (n == 0) { ix->n = 0; ix->n_leaves = 0; ix->P = 2; ix->build_timed = false; return PC_OK; }
+    if (n == 0) { ix->n = 0; ix->n_leaves = 0; ix->P = 2; ix->build_timed = false; ix->lbvh_ready = false; return PC_OK; }
     if (n > ix->cap) {
         PC_CUDA(ix, cudaStreamSynchronize(ix->stream));
         int rc = pc_reserve_cloud(ix, n);
@@ -385,15 +403,16 @@ extern "C" int pc_index_build(pc_index *ix, const float *xyz, int64_t n, int64_t
     }
     const int bits = pc_key_bits_per_axis(n);
     uint32_t *order = nullptr;
+    void *sorted_keys = nullptr;
     int rc;
     const bool big = n > ((int64_t)1 << 21);
     if (bits <= 10) {
         if (ix->key_bytes < 4) return pc_fail(ix, PC_ECUDA, "internal: key buffer");
-        rc = big ? pc_build_sorted<uint32_t, 16>(ix, src, stride, n, bits, &order)
-                 : pc_build_sorted<uint32_t, 8>(ix, src, stride, n, bits, &order);
+        rc = big ? pc_build_sorted<uint32_t, 16>(ix, src, stride, n, bits, &order, &sorted_keys)
+                 : pc_build_sorted<uint32_t, 8>(ix, src, stride, n, bits, &order, &sorted_keys);
     } else {
         if (ix->key_bytes < 8) return pc_fail(ix, PC_ECUDA, "internal: key buffer too narrow");
-        rc = pc_build_sorted<uint64_t, 8>(ix, src, stride, n, bits, &order);
+        rc = pc_build_sorted<uint64_t, 8>(ix, src, stride, n, bits, &order, &sorted_keys);
     }
     if (rc != PC_OK) return rc;
 
@@ -421,6 +440,23 @@ extern "C" int pc_index_build(pc_index *ix, const float *xyz, int64_t n, int64_t
         PC_CHECK_LAUNCH(ix);
         for (int s = 0; s < nl; s++) cnt = (cnt + 1) >> 1;
         lvl0 += nl;
+    }
+    ix->lbvh_ready = false;
+    if (ix->use_lbvh && ix->lbvh_rec) {
+        // experimental second tree (lbvh_kernels.cuh): ranges / splits / child links from the sorted keys, then the bottom-up fit
+        if (n > PC_LBVH_LEAF) {
+            const int grid = (int)((n - 1 + 255) / 256);
+            PC_CUDA(ix, cudaMemsetAsync(ix->lbvh_arrived, 0, (size_t)(n - 1) * sizeof(int), st));
+            if (bits <= 10)
+                pc_lbvh_nodes_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t *)sorted_keys, n, n_leaves, ix->lbvh_rec, ix->lbvh_parent, ix->points);
+            else
+                pc_lbvh_nodes_kernel<uint64_t><<<grid, 256, 0, st>>>((const uint64_t *)sorted_keys, n, n_leaves, ix->lbvh_rec, ix->lbvh_parent, ix->points);
+            pc_lbvh_fit_kernel<<<grid, 256, 0, st>>>(ix->lbvh_rec, ix->points, ix->lbvh_parent, ix->lbvh_arrived, n);
+            ix->launches += 2;
+            PC_CHECK_LAUNCH(ix);
+            ix->lbvh_root = 0;
+            ix->lbvh_ready = true;
+        }
     }
     PC_CUDA(ix, cudaMemcpyAsync(ix->h_bbox, ix->d_bbox, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PC_CUDA(ix, cudaEventRecord(ix->ev_b1, st));
@@ -462,6 +498,7 @@ static pc_tree pc_tree_of(const pc_index *ix)
 {
     pc_tree T;
     T.nodes = ix->nodes; T.points = ix->points; T.n_points = ix->n; T.P = (uint32_t)ix->P;
+    T.lbvh = ix->lbvh_ready ? ix->lbvh_rec : nullptr; T.lbvh_root = ix->lbvh_root;
     return T;
 }
 
@@ -609,7 +646,12 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
     if (two_per_lane && perm) {
         // Morton-ordered batch, two queries per lane: one warp walks the tree once for 64 neighbouring queries
         const int grid = (int)((m + 2 * PC_QUERY_THREADS - 1) / (2 * PC_QUERY_THREADS));
-        if (A.kind == PC_Q_NEAREST)
+        if (T.lbvh) {                // experimental prefix-split tree (PC_LBVH=1)
+            if (A.kind == PC_Q_NEAREST)
+                pc_query_packet2_lbvh_kernel<PC_KIND_NEAREST><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
+            else
+                pc_query_packet2_lbvh_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
+        } else if (A.kind == PC_Q_NEAREST)
             pc_query_packet2_kernel<PC_KIND_NEAREST><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
         else
             pc_query_packet2_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);

@@ -30,6 +30,9 @@ struct pc_tree {
     const float4 *__restrict__ points;   // leaf j -> points[PC_LEAF * j ..]
     int64_t n_points;
     uint32_t P;            // leaf base (power of two >= 2)
+    // experimental second tree over the same points (lbvh_kernels.cuh; null unless the index was created with PC_LBVH=1)
+    const float4 *__restrict__ lbvh;
+    uint32_t lbvh_root;
 };
 
 // one box (min, max: 32 bytes, 32-byte aligned) with ONE 256-bit read-only load (sm_100: LDG.E.256)
