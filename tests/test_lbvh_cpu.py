@@ -61,3 +61,29 @@ def test_packet_walk_over_the_planned_index_is_exact(tmp_path):
         for extra in ([], ["implicit"]):
             r = subprocess.run([exe, fp, fq, bound] + extra, capture_output=True, text=True, timeout=600)
             assert r.returncode == 0 and "mismatches=0" in r.stdout, (bound, extra, r.stdout, r.stderr)
+
+
+def test_frontier_walks_over_the_planned_index_are_exact(tmp_path):
+    """The warp-per-query frontier walks (nearest with 32 and 8 lanes per query, and the range walk with the records' per-leaf
+    point counts) emulated on the CPU over the planned index: exact nearest points and exact range sets."""
+    import numpy as np
+    from pointcloudtraj_b200 import synth
+    exe = str(tmp_path / "lbvh_frontier_check")
+    subprocess.run(["g++", "-std=c++14", "-O2", "-ffp-contract=off", "-o", exe, os.path.join(ROOT, "tests", "c", "lbvh_frontier_check.cpp")],
+                   check=True, capture_output=True)
+    rng = np.random.default_rng(0)
+    cases = []
+    pts, half = synth.forest_cloud(20_000, seed=6, variant="L", return_half=True)
+    q = synth.rrt_queries(400, half, seed=3)
+    q[::2] = np.round(q[::2] / 0.05) * 0.05
+    cases.append((pts[:, :3], q, "1.75", "1.0"))
+    cases.append((pts[:, :3], q, "0", "0.5"))
+    for n in (1, 4, 5, 33):
+        cases.append((rng.normal(size=(n, 3)), rng.normal(size=(40, 3)), "0", "1.5"))
+    cases.append((np.tile([[1.5, -2.0, 0.75]], (200, 1)), rng.normal(size=(20, 3)), "0", "3.0"))
+    for k, (p, qq, bound, rad) in enumerate(cases):
+        fp, fq = str(tmp_path / f"p{k}.bin"), str(tmp_path / f"q{k}.bin")
+        np.ascontiguousarray(p, np.float32).tofile(fp)
+        np.ascontiguousarray(qq, np.float32).tofile(fq)
+        r = subprocess.run([exe, fp, fq, bound, rad], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and r.stdout.count("mismatches=0") == 2, (k, r.stdout, r.stderr)
