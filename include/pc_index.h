@@ -90,13 +90,16 @@ typedef struct pc_traj {
     double  t_now;
 } pc_traj;
 
-/* device-side layout of a built index (for inspection and for replication across GPUs) */
+/* device-side layout of a built index (for inspection and for replication across GPUs): a binary radix tree over the
+ * cloud sorted along a Hilbert curve, leaves of <= 4 consecutive points (pointcloudtraj_b200/csrc/build_kernels.cuh) */
 typedef struct pc_index_view {
-    int64_t n_points;      /* points in the cloud                                           */
-    int64_t n_leaves;      /* ceil(n_points / 2)                                            */
-    int64_t leaf_base;     /* P: power of two >= max(2, n_leaves); node ids are [1, 2P)      */
-    const void *points;    /* float4[2 * n_leaves]: x, y, z, original index (int bits); = nodes + 4P */
-    const void *nodes;     /* float4[4 * P]: node i -> lo = nodes[2i], hi = nodes[2i+1]      */
+    int64_t n_points;      /* points in the cloud                                                            */
+    int64_t n_nodes;       /* inner-node records: n_points - 1, or 0 when the whole cloud is one leaf          */
+    uint32_t root;         /* child reference of the whole cloud: inner node 0, or 0x80000000 | 0 (a leaf)      */
+    uint32_t root_count;   /* points of the root when it is a leaf                                            */
+    const void *points;    /* float4[n_points + 4]: x, y, z, original index (int bits), curve order; = records + 4 n_nodes */
+    const void *records;   /* float4[4 * n_nodes]: node i -> [min0 | max0 | min1 | max1] of its two children, .w words:
+                              min.w = child reference (bit 31: leaf, low bits: first point), max.w = leaf point count   */
     float bbox_lo[3], bbox_hi[3];
 } pc_index_view;
 
@@ -133,6 +136,16 @@ int  pc_radius_batch(pc_index *ix, const float *q_xyz, int64_t m, int64_t q_stri
 int  pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64_t q_stride, int space,
                     const double *range, int range_is_scalar,
                     int64_t *out_offsets, int32_t *out_idx, int64_t cap);
+
+/* Arithmetic of the radiusSearch epilogue (pc_radius_batch, pc_clearance_batch) on this handle:
+ *   PC_ARITH_FP64 (default)  radius = sqrt(d2) - search_margin in double precision from the kd-tree's fp64 d2 -- the parity
+ *                            target the north star names (Utils/kdtree), within 1e-6 relative of the variant below;
+ *   PC_ARITH_PCL_FLOAT       d2 rounded to float32, float32 sqrt, then the double subtraction: what corridor_finder.cpp:130-131
+ *                            computes through PCL's interface (std::vector<float> k_sqr_distances; sqrt(float)).  Bit-identical
+ *                            with the unmodified corridor_finder.cpp compiled against an exact 1-NN (tests/test_planner_ref*.py). */
+#define PC_ARITH_FP64      0
+#define PC_ARITH_PCL_FLOAT 1
+int  pc_index_set_radius_arith(pc_index *ix, int mode);
 
 /* Sensing gather: ALL points within `radius` of one centre (d2 <= radius^2; the centre is cast to float32 as PCL does),
  * ascending original index -- the LiDAR-mode observation of the reference's sensor node, one radiusSearch(pos, max_dist)

@@ -29,7 +29,12 @@
 // ellipsoid is updated when an end node is found, as SafeRegionRefine does (:796) -- in SafeRegionExpansion that call is
 // commented out (:742) while inform_status is still set, which samples from uninitialised elli_l / elli_s; (3) the node
 // tree is a small dynamic kd-tree written here (float positions like kd_insertf / kd_nearestf / kd_nearest_rangef),
-// range results are consumed in ascending insertion order; (4) treePrune compares with a 1e-4 slack (see there).
+// range results are consumed in ascending insertion order; (4) treePrune compares with a 1e-4 slack (see there); (5)
+// SafeRegionRefine is also bounded by max_samples.
+// setReferenceQuirks(true) switches (2)-(5) back to the reference's exact behaviour (elli_l = elli_s = 0 until Refine finds
+// a better end, range results in kd_nearest_rangef's own order, exact float prune test, unbounded Refine): in that mode
+// expand() / refine() / evaluate() reproduce the UNMODIFIED corridor_finder.cpp bit for bit -- node list, parents, costs,
+// radii and corridor -- which tests/test_planner_ref.py checks against the compiled reference (oracle/_ref/libplanner_ref.so).
 // No Eigen / PCL / ROS.
 #ifndef PC_RRT_HPP_
 #define PC_RRT_HPP_
@@ -87,6 +92,17 @@ public:
         if (out_d2) *out_d2 = best_d2;
         return items_[best].node;
     }
+    // all nodes with d2 <= range^2, in the order kd_res_next hands them out after kd_nearest_rangef (kdtree.c:262-293: a node
+    // is tested before its subtrees, the side of the query first, the far side only if |dx| < range -- strict --, and
+    // rlist_insert puts every hit at the HEAD of the list, :810-828 with dist_sq = -1, so the list is the visit order reversed)
+    void rangeReferenceOrder(const float q[3], float r, std::vector<RrtNode *> &out) const
+    {
+        out.clear();
+        if (items_.empty()) return;
+        const double qd[3] = { (double)q[0], (double)q[1], (double)q[2] }, rd = (double)r;
+        rangeRec(0, qd, rd, out);
+        std::reverse(out.begin(), out.end());
+    }
     // all nodes with d2 <= range^2, ascending insertion order
     void range(const float q[3], float r, std::vector<RrtNode *> &out) const
     {
@@ -111,6 +127,17 @@ public:
 
 private:
     struct Item { float p[3]; RrtNode *node; int lo, hi, axis; };
+    void rangeRec(int i, const double q[3], double r, std::vector<RrtNode *> &out) const
+    {
+        if (i < 0) return;
+        double s = 0.0;
+        for (int a = 0; a < 3; a++) { const double d = (double)items_[i].p[a] - q[a]; s += d * d; }
+        if (s <= r * r) out.push_back(items_[i].node);
+        const int a = items_[i].axis;
+        const double dx = q[a] - (double)items_[i].p[a];
+        rangeRec(dx <= 0.0 ? items_[i].lo : items_[i].hi, q, r, out);
+        if (std::fabs(dx) < r) rangeRec(dx <= 0.0 ? items_[i].hi : items_[i].lo, q, r, out);
+    }
     double d2(int i, const float q[3]) const
     {
         double s = 0.0;
@@ -169,14 +196,20 @@ public:
         path.clear(); radius.clear();
     }
 
+    // reproduce the reference bit for bit (see the header comment); off by default
+    void setReferenceQuirks(bool on) { quirks_ = on; }
+
     // SafeRegionExpansion, one cloud query per iteration (corridor_finder.cpp:704-763)
-    int expand(int max_iterations) { initRoot(); return refine(max_iterations); }
+    int expand(int max_iterations) { initRoot(); return growLoop(max_iterations, true); }
 
     // SafeRegionRefine (corridor_finder.cpp:765-815): the same loop on the existing tree (more samples, more rewiring)
-    int refine(int max_iterations)
+    int refine(int max_iterations) { return growLoop(max_iterations, false); }
+
+    int growLoop(int max_iterations, bool expansion)
     {
         int it = 0;
-        for (; it < max_iterations && it < max_samples; it++) {
+        in_expansion_ = expansion;
+        for (; it < max_iterations && (it < max_samples || (quirks_ && !expansion)); it++) {
             double s[3];
             genSample(s);
             RrtNode *nearest = findNearestVertex(s);
@@ -198,6 +231,7 @@ public:
 
     int refineBatched(int max_iterations, int K)
     {
+        in_expansion_ = false;
         std::vector<double> centers((size_t)K * 3), radii((size_t)K), samples((size_t)K * 3);
         std::vector<float> node_pos, sample_pos((size_t)K * 3);
         std::vector<int32_t> nearest_idx((size_t)K);
@@ -325,7 +359,8 @@ public:
         std::vector<RrtNode *> todo;
         for (size_t i = 0; i < fail_list.size(); i++) {
             const float pos[3] = { (float)fail_list[i].coord[0], (float)fail_list[i].coord[1], (float)fail_list[i].coord[2] };
-            node_tree_.range(pos, fail_list[i].radius * 2.0f, near[i]);
+            if (quirks_) node_tree_.rangeReferenceOrder(pos, fail_list[i].radius * 2.0f, near[i]);
+            else node_tree_.range(pos, fail_list[i].radius * 2.0f, near[i]);
             for (RrtNode *p : near[i]) if (p != root_node && p->pre != root_node) todo.push_back(p);
         }
         std::sort(todo.begin(), todo.end(), [](const RrtNode *x, const RrtNode *y) { return x->serial < y->serial; });
@@ -386,7 +421,7 @@ public:
 
 private:
     using U = std::uniform_real_distribution<double>;
-    static double inf() { return std::numeric_limits<double>::infinity(); }
+    static double inf() { return 9999999.0; }             // data_type.h:6
     static double dist(const double a[3], const double b[3])
     {
         return std::sqrt((a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]));
@@ -456,13 +491,13 @@ private:
     void tryInsert(const double c[3], double r, RrtNode *nearest)
     {
         if (c[2] < z_l || (float)r < safety_margin) return;
-        RrtNode *n = new RrtNode(c, (float)r, std::numeric_limits<float>::infinity(), (float)dist(c, end_pt));
+        RrtNode *n = new RrtNode(c, (float)r, (float)inf(), (float)dist(c, end_pt));
         treeRewire(n, nearest);
         if (!n->valid) { delete n; return; }          // (the reference leaks these nodes)
         if (checkEnd(n)) {
             if (!inform_status) best_end_ptr = n;
             end_list_.push_back(n);
-            updateHeuristicRegion(n);
+            if (!(quirks_ && in_expansion_)) updateHeuristicRegion(n);      // commented out in SafeRegionExpansion (:742)
             inform_status = true;
         }
         insertIntoTree(n);
@@ -497,7 +532,8 @@ private:
         const float range = newPtr->radius * 2.0f;
         const float pos[3] = { (float)newPtr->coord[0], (float)newPtr->coord[1], (float)newPtr->coord[2] };
         std::vector<RrtNode *> found;
-        node_tree_.range(pos, range, found);
+        if (quirks_) node_tree_.rangeReferenceOrder(pos, range, found);
+        else node_tree_.range(pos, range, found);
         std::vector<RrtNode *> nearPtrList;
         bool isInvalid = false;
         for (RrtNode *nearPtr : found) {
@@ -566,7 +602,8 @@ private:
     {
         // the reference compares the float sum g + f with the double best_distance (:165); for the end node that has just set
         // best_distance the two differ only by float rounding, which prunes it half of the time -- hence the small slack
-        if ((double)n->g + (double)n->f > best_distance + 1e-4) { n->valid = false; invalid_set_.push_back(n); clearBranchS(n); }
+        const bool prune = quirks_ ? (double)(n->g + n->f) > best_distance : (double)n->g + (double)n->f > best_distance + 1e-4;
+        if (prune) { n->valid = false; invalid_set_.push_back(n); clearBranchS(n); }
     }
 
     // corridor_finder.cpp:170-232
@@ -681,7 +718,7 @@ private:
     double translation[3] = { 0, 0, 0 }, rot[3][3] = { { 1, 0, 0 }, { 0, 1, 0 }, { 0, 0, 1 } };
     double inlier_ratio = 0, goal_ratio = 0;
     int max_samples = 0, cach_size = 10;
-    bool inform_status = false;
+    bool inform_status = false, quirks_ = false, in_expansion_ = false;
     RrtNode *root_node = nullptr, *best_end_ptr = nullptr;
     std::vector<RrtNode *> node_list_, end_list_, invalid_set_, path_list_;
     NodeKdTree node_tree_;

@@ -303,3 +303,120 @@ def bezier_pos(coef_row, order, u):
 
 def binomial(n, k):
     return lib().po_binomial(n, k)
+
+
+# ---- the compiled, UNMODIFIED reference planner (oracle/_ref/libplanner_ref.so) ---------------------------------------
+_PLANNER_PATH = os.path.join(_HERE, "_ref", "libplanner_ref.so")
+_planner = None
+
+
+def have_planner_reference() -> bool:
+    return os.path.exists(_PLANNER_PATH)
+
+
+def planner_lib():
+    global _planner
+    if _planner is None:
+        if not os.path.exists(_PLANNER_PATH):
+            raise FileNotFoundError(f"{_PLANNER_PATH} missing: run `make -C oracle` in the container that has /root/reference")
+        L = C.CDLL(_PLANNER_PATH)
+        d = C.c_double
+        L.rp_create.argtypes = [d, d, d, d]
+        L.rp_set_input.argtypes = [_f32p, C.c_longlong, C.c_longlong]
+        L.rp_set_pt.argtypes = [_f64p, _f64p, d, d, d, d, d, d, d, C.c_int, d, d]
+        L.rp_set_start_pt.argtypes = [_f64p, _f64p]
+        L.rp_expand.argtypes = [d]
+        L.rp_refine.argtypes = [d]
+        L.rp_reset_root.argtypes = [_f64p]
+        L.rp_get_path.argtypes = [_f64p, _f64p, C.c_int]
+        L.rp_get_tree.argtypes = [_f64p, C.c_int]
+        L.rp_stats.argtypes = [C.POINTER(C.c_longlong)]
+        L.rp_radius_search.argtypes = [_f64p]
+        L.rp_radius_search.restype = d
+        L.rp_radius_batch.argtypes = [_f64p, C.c_longlong, _f64p]
+        L.rp_check_traj_pt_col.argtypes = [_f64p]
+        L.rp_bezier_pos.argtypes = [C.c_int, _f64p, d, _f64p]
+        L.rp_check_safe_trajectory.argtypes = [C.c_int, _i32p, _f64p, _f64p, C.c_longlong, d, d, _f32p, C.c_longlong,
+                                               C.POINTER(C.c_longlong)]
+        _planner = L
+    return _planner
+
+
+class PlannerReference:
+    """The reference's safeRegionRrtStar (Planner/src/corridor_finder.cpp, unmodified) and checkSafeTrajectory /
+    getPosFromBezier (Planner/src/sim_planning_demo.cpp:715-781, unmodified) behind oracle/ref_planner_harness.cpp.
+    ONE planner object per process (checkSafeTrajectory names a global): creating a new instance re-creates it."""
+
+    def __init__(self, safety_margin=0.6, search_margin=0.25, max_radius=1.5, sample_range=30.0):
+        self._L = planner_lib()
+        self._L.rp_create(safety_margin, search_margin, max_radius, sample_range)
+
+    def set_input(self, xyz):
+        xyz = _as_f32_rows(xyz)
+        self._L.rp_set_input(_ptr(xyz, _f32p), xyz.shape[0], xyz.shape[1])
+        return self
+
+    def reset(self):
+        self._L.rp_reset()
+
+    def set_pt(self, start, end, box, local_range, max_iter, sample_portion, goal_portion):
+        s = np.ascontiguousarray(start, np.float64); e = np.ascontiguousarray(end, np.float64)
+        self._L.rp_set_pt(_ptr(s, _f64p), _ptr(e, _f64p), *[float(v) for v in box], float(local_range), int(max_iter),
+                          float(sample_portion), float(goal_portion))
+
+    def set_start_pt(self, start, end):
+        s = np.ascontiguousarray(start, np.float64); e = np.ascontiguousarray(end, np.float64)
+        self._L.rp_set_start_pt(_ptr(s, _f64p), _ptr(e, _f64p))
+
+    def expand(self, n_iter):
+        self._L.rp_expand(float(n_iter))
+
+    def refine(self, n_iter):
+        self._L.rp_refine(float(n_iter))
+
+    def evaluate(self):
+        self._L.rp_evaluate()
+
+    def path(self, cap=4096):
+        p = np.zeros((cap, 3)); r = np.zeros(cap)
+        n = self._L.rp_get_path(_ptr(p, _f64p), _ptr(r, _f64p), cap)
+        return p[:n].copy(), r[:n].copy()
+
+    def tree(self, cap=1 << 20):
+        """(n, 7): x, y, z, radius, g, parent index in the same list (-1), valid."""
+        t = np.zeros((cap, 7))
+        n = self._L.rp_get_tree(_ptr(t, _f64p), cap)
+        return t[:n].copy()
+
+    def stats(self):
+        s = (C.c_longlong * 6)()
+        self._L.rp_stats(s)
+        return dict(nodes=s[0], path_exists=bool(s[1]), cloud_queries=s[2], rebuilds=s[3], warnings=s[4], global_navi=bool(s[5]))
+
+    def radius_search(self, p):
+        p = np.ascontiguousarray(p, np.float64)
+        return self._L.rp_radius_search(_ptr(p, _f64p))
+
+    def radius_batch(self, pts):
+        """radiusSearch for every row of pts (float64 (m, 3): the planner passes Vector3d)."""
+        pts = np.ascontiguousarray(pts, np.float64)
+        out = np.empty(pts.shape[0])
+        self._L.rp_radius_batch(_ptr(pts, _f64p), pts.shape[0], _ptr(out, _f64p))
+        return out
+
+    def bezier_pos(self, coef_row, order, u):
+        c = np.ascontiguousarray(coef_row, np.float64)
+        out = np.zeros(3)
+        self._L.rp_bezier_pos(int(order), _ptr(c, _f64p), float(u), _ptr(out, _f64p))
+        return out
+
+    def check_safe_trajectory(self, order, T, coef, t_now, stop_time, cap=8192):
+        """Returns (collides, pts float32 (k, 3)): the reference's return value and the sample points it visited."""
+        order = np.ascontiguousarray(order, np.int32); T = np.ascontiguousarray(T, np.float64)
+        coef = np.ascontiguousarray(coef, np.float64)
+        pts = np.zeros((cap, 3), np.float32)
+        n = C.c_longlong(0)
+        hit = self._L.rp_check_safe_trajectory(order.shape[0], _ptr(order, _i32p), _ptr(T, _f64p), _ptr(coef, _f64p),
+                                               coef.shape[1] if coef.ndim == 2 else 0, float(t_now), float(stop_time),
+                                               _ptr(pts, _f32p), cap, C.byref(n))
+        return bool(hit), pts[: min(n.value, cap)].copy(), int(n.value)

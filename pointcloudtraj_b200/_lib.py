@@ -15,6 +15,7 @@ PC_OK, PC_EINVAL, PC_ENOMEM, PC_ECUDA, PC_ECAP, PC_ENCCL, PC_ENOTIMPL = 0, -1, -
 PC_HOST, PC_DEVICE, PC_HOST_ASYNC, PC_DEVICE_ASYNC = 0, 1, 2, 3
 PC_RADIUS_BOUNDED, PC_RADIUS_FULL_NN = 0, 1
 PC_QUERY_AUTO, PC_QUERY_UNSORTED, PC_QUERY_SORTED = 0, 2, 4
+PC_ARITH_FP64, PC_ARITH_PCL_FLOAT = 0, 1
 PC_NCCL_UNIQUE_ID_BYTES = 128
 
 ERROR_NAMES = {PC_EINVAL: "PC_EINVAL", PC_ENOMEM: "PC_ENOMEM", PC_ECUDA: "PC_ECUDA", PC_ECAP: "PC_ECAP",
@@ -27,7 +28,7 @@ ABI_SYMBOLS = [
     "pc_nearest_batch", "pc_radius_batch", "pc_range_batch", "pc_clearance_batch", "pc_sphere_gather",
     "pc_host_alloc", "pc_host_free",
     "pc_comm_unique_id", "pc_comm_init", "pc_comm_destroy", "pc_index_broadcast", "pc_shard_range",
-    "pc_launch_count", "pc_profile_enable", "pc_profile_last_batch", "pc_batch_shard",
+    "pc_launch_count", "pc_profile_enable", "pc_profile_last_batch", "pc_batch_shard", "pc_index_set_radius_arith",
 ]
 
 
@@ -49,8 +50,8 @@ class PcTraj(C.Structure):
 
 
 class PcIndexView(C.Structure):
-    _fields_ = [("n_points", C.c_int64), ("n_leaves", C.c_int64), ("leaf_base", C.c_int64),
-                ("points", C.c_void_p), ("nodes", C.c_void_p),
+    _fields_ = [("n_points", C.c_int64), ("n_nodes", C.c_int64), ("root", C.c_uint32), ("root_count", C.c_uint32),
+                ("points", C.c_void_p), ("records", C.c_void_p),
                 ("bbox_lo", C.c_float * 3), ("bbox_hi", C.c_float * 3)]
 
 
@@ -106,6 +107,7 @@ def load():
     L.pc_launch_count.argtypes = [vp, i32]
     L.pc_launch_count.restype = i64
     L.pc_batch_shard.argtypes = [vp, i32, i32]
+    L.pc_index_set_radius_arith.argtypes = [vp, i32]
     L.pc_profile_enable.argtypes = [vp, i32]
     L.pc_profile_last_batch.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     _lib = L

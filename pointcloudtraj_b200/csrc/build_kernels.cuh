@@ -1,17 +1,23 @@
-// build_kernels.cuh -- index construction kernels (bbox, curve keys, leaf gather, bounding-box tree).
+// build_kernels.cuh -- index construction kernels: bounding box, curve keys, prefix-split tree (nodes + bottom-up box fit).
 //
-// Index layout in HBM: ONE float4 array, P = 2^k >= max(2, ceil(n / 2)) leaf slots, heap numbering (root = node 1,
-// children of i are 2i and 2i+1, leaf j is node P + j):
-//   boxes  tree[0 .. 4P)  : node i's box is tree[2i] = min (xyz), tree[2i+1] = max (xyz); the boxes of the two children
-//                           of i are therefore the aligned 64-byte record tree[4i .. 4i+3]
-//   points tree[4P .. 6P) : leaf j holds points[2j], points[2j+1] in curve order, (x, y, z, original index as int
-//                           bits); when n is odd the last slot repeats the last real point
-// A traversal step loads the record of the node it visits: a box pair (64 B) or a leaf's two points (32 B).
-// Unused box slots hold the empty box (min = +inf, max = -inf).
-// replaces struct kdtree / struct kdnode / struct kdhyperrect (Utils/kdtree/src/kdtree.c:56-80) and
+// Index layout in HBM: ONE float4 array (`tree`) per index,
+//   records tree[0 .. 4 (n-1))   : inner node i of the binary radix tree over the curve-sorted keys (T. Karras, HPG 2012) is the
+//                                  64-byte record tree[4i .. 4i+3] = [min0 | max0 | min1 | max1], the tight boxes of its two
+//                                  children; the .w words hold the children: min.w = child reference, max.w = number of points
+//                                  when the child is a leaf.  Every node is split where the highest differing bit of its first
+//                                  and last key flips, so node boundaries coincide with the cells of the curve.
+//   points  tree[4 (n-1) .. +n+PC_LEAF) : (x, y, z, original index as int bits) in curve order, padded with PC_LEAF copies of
+//                                  the last point (a leaf scan reads PC_LEAF consecutive points from any start).
+// A child whose range holds <= PC_LEAF points is a LEAF: its reference is PC_REF_LEAF | (index of its first point).  Inner
+// nodes whose own range is that small are never referenced and their records stay unwritten.  A cloud of <= PC_LEAF points
+// has no inner node: the root reference is the leaf PC_REF_LEAF | 0.
+// A traversal step loads the record of the node it visits (two 256-bit loads) or the four points of a leaf.
+// replaces struct kdtree / struct kdnode / struct kdhyperrect (Utils/kdtree/src/kdtree.c:56-80), insert_rec (:167-194) and
 // hyperrect_extend (kdtree.c:729-741).
 #pragma once
 #include "common.cuh"
+#define PC_LBVH_LEAF PC_LEAF
+#include "lbvh.cuh"
 
 #define PC_BUILD_THREADS 256
 
@@ -70,11 +76,8 @@ __device__ __forceinline__ pc_frame pc_make_frame(const uint32_t *bbox, int bits
     return f;
 }
 
-// Order of the cloud along a space-filling curve.  The tree above it is implicit -- aligned groups of 2^k consecutive
-// leaves -- so its boxes are only as tight as consecutive stretches of the curve are compact.  A Hilbert stretch always is
-// (consecutive cells are adjacent); a Morton stretch that straddles an octant boundary is not.  Measured on the bench
-// workload: radius search 1.84 -> 1.29 ms, unbounded nearest 7.10 -> 4.15 ms per 10 M queries, identical results
-// (profiles/r1_sweep9_cloud_hilbert_order.txt).
+// Order of the cloud along a space-filling curve.  Every prefix of a Hilbert key is a box of cells (an octant, two adjacent
+// octants or a 2x2x1 slab of them), so the radix tree's nodes are compact; the same curve orders the query batches.
 #ifndef PC_POINT_CURVE
 #define PC_POINT_CURVE 1     // 0 = Morton, 1 = Hilbert
 #endif
@@ -97,84 +100,90 @@ pc_keygen_kernel(const float *__restrict__ xyz, int64_t n, int stride, const uin
     }
 }
 
-// ---- leaves: gather the cloud into curve order (one thread per point slot) and box every PC_LEAF slots ----
+// ---- tree, step 1: one thread per point slot ---------------------------------------------------------------------------------
+// Thread i gathers point order[i] into curve position i and, for i < n - 1, computes inner node i of the radix tree from the
+// sorted keys: range, split, child references (the .w words of its record) and the parent links of its inner children.
+// The arrival counters of the fit kernel are cleared here.
+#define PC_NODE_UNUSED 0xffffffffu
+
+template <typename KeyT>
 __global__ void __launch_bounds__(PC_BUILD_THREADS)
-pc_leaf_kernel(const float *__restrict__ xyz, int stride, const uint32_t *__restrict__ order, int64_t n,
-               int64_t n_leaves, int64_t P, float4 *__restrict__ points, float4 *__restrict__ nodes)
+pc_tree_nodes_kernel(const float *__restrict__ xyz, int stride, const uint32_t *__restrict__ order, const KeyT *__restrict__ keys,
+                     int64_t n, float4 *__restrict__ rec, float4 *__restrict__ points, int32_t *__restrict__ parent,
+                     int *__restrict__ arrived)
 {
-    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // grid covers 8 * n_leaves (rounded up to 8 lanes)
-    const bool in_range = slot < n_leaves * PC_LEAF;
-    int64_t s = slot < n ? slot : n - 1;                                    // tail slots repeat the last real point
-    float x = 0.f, y = 0.f, z = 0.f; uint32_t src = 0;
-    if (in_range) {
-        src = order[s];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n + PC_LEAF) return;
+    {
+        const uint32_t src = order[i < n ? i : n - 1];                 // the pad slots repeat the last point
         const float *p = xyz + (int64_t)src * stride;
-        x = p[0]; y = p[1]; z = p[2];
-        points[slot] = make_float4(x, y, z, __uint_as_float(src));
+        points[i] = make_float4(p[0], p[1], p[2], __uint_as_float(src));
     }
-    // NaN coordinates must not poison the box: fminf/fmaxf ignore them
-    float lx = in_range ? x : INFINITY, ly = in_range ? y : INFINITY, lz = in_range ? z : INFINITY;
-    float hx = in_range ? x : -INFINITY, hy = in_range ? y : -INFINITY, hz = in_range ? z : -INFINITY;
-#pragma unroll
-    for (int o = 1; o < PC_LEAF; o <<= 1) {
-        lx = fminf(lx, __shfl_xor_sync(PC_FULL_MASK, lx, o)); hx = fmaxf(hx, __shfl_xor_sync(PC_FULL_MASK, hx, o));
-        ly = fminf(ly, __shfl_xor_sync(PC_FULL_MASK, ly, o)); hy = fmaxf(hy, __shfl_xor_sync(PC_FULL_MASK, hy, o));
-        lz = fminf(lz, __shfl_xor_sync(PC_FULL_MASK, lz, o)); hz = fmaxf(hz, __shfl_xor_sync(PC_FULL_MASK, hz, o));
-    }
-    if ((threadIdx.x & (PC_LEAF - 1)) == 0) {
-        int64_t leaf = slot / PC_LEAF;
-        // the slots after the last leaf, up to the next multiple of 4, are written as empty boxes: they are the siblings /
-        // cousins of the last leaf that the binary (2 boxes per visit) and the 4-ary (4 boxes per visit) walks read
-        if (leaf < ((n_leaves + 4) & ~(int64_t)3) && leaf < P) {
-            nodes[2 * (P + leaf)] = make_float4(lx, ly, lz, 0.f);
-            nodes[2 * (P + leaf) + 1] = make_float4(hx, hy, hz, 0.f);
-        }
-    }
+    if (i >= n - 1 || n <= PC_LEAF) return;
+    if (i == 0) parent[0] = -1;
+    arrived[i] = 0;
+    int64_t f, l, s;
+    pc_lbvh_node(keys, n, i, &f, &l, &s);
+    float *w = reinterpret_cast<float *>(rec + 4 * i);
+    if (l - f + 1 <= PC_LEAF) { w[3] = __uint_as_float(PC_NODE_UNUSED); return; }   // collapsed into a leaf of its parent
+    uint32_t r0, c0, r1, c1;
+    pc_lbvh_children(f, l, s, &r0, &c0, &r1, &c1);
+    w[3] = __uint_as_float(r0); w[7] = __uint_as_float(c0); w[11] = __uint_as_float(r1); w[15] = __uint_as_float(c1);
+    if (!(r0 & PC_REF_LEAF)) parent[r0] = (int32_t)i;
+    if (!(r1 & PC_REF_LEAF)) parent[r1] = (int32_t)i;
 }
 
-// ---- upper levels: each CTA folds 2*PC_UP_THREADS nodes of level `lvl0` into up to PC_UP_LEVELS levels above ----
-// Level l has base id P >> l and cnt_l = ceil(cnt_{l-1} / 2) real nodes (cnt_0 = n_leaves); the nodes from cnt_l up to the
-// next multiple of 4 (the possible sibling and cousins of its last real node) are written as empty boxes.
-#define PC_UP_THREADS 128
-#define PC_UP_LEVELS 8   // log2(2 * PC_UP_THREADS)
-
-__global__ void __launch_bounds__(PC_UP_THREADS)
-pc_upper_kernel(float4 *__restrict__ nodes, int64_t P, int lvl0, int64_t cnt0, int n_levels)
+__device__ __forceinline__ void pc_leaf_box(const float4 *__restrict__ points, uint32_t first, uint32_t count, float *lo, float *hi)
 {
-    __shared__ float4 s_lo[PC_UP_THREADS], s_hi[PC_UP_THREADS];
-    const int t = threadIdx.x;
-    int64_t child_first = (int64_t)blockIdx.x * (2 * PC_UP_THREADS);   // index inside level lvl0
-    int64_t cnt_child = cnt0;
-    float4 lo, hi;
-    for (int s = 1; s <= n_levels; s++) {
-        const int lvl = lvl0 + s;
-        const int64_t base = P >> lvl;                 // id of the first node of this level
-        const int64_t cnt = (cnt_child + 1) >> 1;      // real nodes on this level
-        const int width = (2 * PC_UP_THREADS) >> s;    // nodes of this level owned by this CTA
-        const int64_t k = (child_first >> s) + t;      // node index inside the level
-        if (t < width) {
-            float4 alo, ahi, blo, bhi;
-            if (s == 1) {
-                const int64_t cbase = P >> lvl0;
-                const int64_t c = 2 * k;
-                const float4 e_lo = make_float4(INFINITY, INFINITY, INFINITY, 0.f), e_hi = make_float4(-INFINITY, -INFINITY, -INFINITY, 0.f);
-                if (c < cnt_child) { alo = nodes[2 * (cbase + c)]; ahi = nodes[2 * (cbase + c) + 1]; } else { alo = e_lo; ahi = e_hi; }
-                if (c + 1 < cnt_child) { blo = nodes[2 * (cbase + c + 1)]; bhi = nodes[2 * (cbase + c + 1) + 1]; } else { blo = e_lo; bhi = e_hi; }
-            } else {
-                alo = s_lo[2 * t]; ahi = s_hi[2 * t]; blo = s_lo[2 * t + 1]; bhi = s_hi[2 * t + 1];
-            }
-            lo = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.f);
-            hi = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.f);
-        }
-        __syncthreads();   // everyone has read the previous level from shared memory
-        if (t < width) {
-            s_lo[t] = lo; s_hi[t] = hi;
-            if (k < ((cnt + 4) & ~(int64_t)3) && k < base) {   // pads up to the next multiple of 4; base == number of slots on this level
-                nodes[2 * (base + k)] = lo;
-                nodes[2 * (base + k) + 1] = hi;
-            }
-        }
-        __syncthreads();
-        cnt_child = cnt;
+    float lx = INFINITY, ly = INFINITY, lz = INFINITY, hx = -INFINITY, hy = -INFINITY, hz = -INFINITY;
+    for (uint32_t k = 0; k < count; k++) {
+        const float4 p = points[first + k];
+        lx = fminf(lx, p.x); ly = fminf(ly, p.y); lz = fminf(lz, p.z);      // fminf / fmaxf ignore NaN coordinates
+        hx = fmaxf(hx, p.x); hy = fmaxf(hy, p.y); hz = fmaxf(hz, p.z);
+    }
+    lo[0] = lx; lo[1] = ly; lo[2] = lz; hi[0] = hx; hi[1] = hy; hi[2] = hz;
+}
+
+// ---- tree, step 2: bottom-up box fit -------------------------------------------------------------------------------------------
+// One thread per used inner node boxes its LEAF children; whichever thread brings a node's arrival counter to 2 merges the
+// node's two child boxes into the slot the node has in its parent's record, and carries on upwards.
+__global__ void __launch_bounds__(PC_BUILD_THREADS)
+pc_tree_fit_kernel(float4 *rec, const float4 *__restrict__ points, const int32_t *__restrict__ parent, int *arrived, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    volatile float *w = reinterpret_cast<volatile float *>(rec + 4 * i);
+    const uint32_t r0 = __float_as_uint(w[3]);
+    if (r0 == PC_NODE_UNUSED) return;
+    const uint32_t c0 = __float_as_uint(w[7]), r1 = __float_as_uint(w[11]), c1 = __float_as_uint(w[15]);
+    int add = 0;
+    float lo[3], hi[3];
+    if (r0 & PC_REF_LEAF) {
+        pc_leaf_box(points, r0 & ~PC_REF_LEAF, c0, lo, hi);
+        w[0] = lo[0]; w[1] = lo[1]; w[2] = lo[2]; w[4] = hi[0]; w[5] = hi[1]; w[6] = hi[2];
+        add++;
+    }
+    if (r1 & PC_REF_LEAF) {
+        pc_leaf_box(points, r1 & ~PC_REF_LEAF, c1, lo, hi);
+        w[8] = lo[0]; w[9] = lo[1]; w[10] = lo[2]; w[12] = hi[0]; w[13] = hi[1]; w[14] = hi[2];
+        add++;
+    }
+    int64_t node = i;
+    while (add > 0) {
+        __threadfence();                                       // my box writes before my arrival
+        const int old = atomicAdd(&arrived[node], add);
+        if (old + add < 2) break;                              // the other child's thread completes this node
+        __threadfence();                                       // the other child's box writes after its arrival
+        const int32_t par = parent[node];
+        if (par < 0) break;                                    // the root is complete
+        volatile float *c = reinterpret_cast<volatile float *>(rec + 4 * node);
+        const float mlx = fminf(c[0], c[8]), mly = fminf(c[1], c[9]), mlz = fminf(c[2], c[10]);
+        const float mhx = fmaxf(c[4], c[12]), mhy = fmaxf(c[5], c[13]), mhz = fmaxf(c[6], c[14]);
+        volatile float *p = reinterpret_cast<volatile float *>(rec + 4 * (int64_t)par);
+        const int slot = __float_as_uint(p[3]) == (uint32_t)node ? 0 : 8;     // left child = first reference of the parent
+        p[slot + 0] = mlx; p[slot + 1] = mly; p[slot + 2] = mlz;
+        p[slot + 4] = mhx; p[slot + 5] = mhy; p[slot + 6] = mhz;
+        node = par;
+        add = 1;
     }
 }

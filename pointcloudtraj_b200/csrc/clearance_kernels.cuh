@@ -8,9 +8,11 @@
 // result of REPEATED addition (not k * dt).  To reproduce them bit for bit, thread 0 of the CTA runs the walk
 // sequentially and publishes a schedule of (segment, t) pairs in shared memory, PC_CLR_CHUNK samples at a time;
 // all threads then evaluate the samples of the chunk in parallel.
-// Powers u^j are built by multiplication (p[j] = p[j/2] * p[j - j/2], <= 2 ulp from libm's pow for j <= 12); the
-// position is cast to float32 exactly where radiusSearch does (corridor_finder.cpp:122-125), which absorbs that
-// difference in all but ~1e-8 of the coordinates (DESIGN.md "Clearance tolerance").
+// Powers u^j: the reference calls libm's pow (sim_planning_demo.cpp:724), whose result is the correctly rounded power in
+// all but ~2^-15 of the cases (glibc's pow carries ~68 bits internally).  Here u^j is built by repeated multiplication in
+// double-double arithmetic (error-free products with fma, relative error < 2^-100 after 12 steps) and rounded to double
+// ONCE, i.e. it IS the correctly rounded power; the position is then cast to float32 exactly where radiusSearch does
+// (corridor_finder.cpp:122-125), which absorbs a last-bit difference of a power in all but ~2^-29 of those rare cases.
 #pragma once
 #include "query_kernels.cuh"
 
@@ -26,7 +28,15 @@ __device__ __forceinline__ void pc_power_table(double u, int n, double *p)
 {
     p[0] = 1.0;
     if (n >= 1) p[1] = u;
-    for (int j = 2; j <= n; j++) p[j] = __dmul_rn(p[j >> 1], p[j - (j >> 1)]);
+    double hi = u, lo = 0.0;                          // u^(j-1) = hi + lo, |lo| <= ulp(hi) / 2
+    for (int j = 2; j <= n; j++) {
+        const double ph = __dmul_rn(hi, u);
+        const double pe = __fma_rn(hi, u, -ph);       // hi * u = ph + pe exactly
+        const double pl = __fma_rn(lo, u, pe);
+        hi = __dadd_rn(ph, pl);                       // fast two-sum: |ph| >= |pl|
+        lo = __dadd_rn(__dsub_rn(ph, hi), pl);
+        p[j] = hi;                                    // = round(hi + lo): hi + lo is normalised
+    }
 }
 
 // p = T * sum_j C(n,j) c_j u^j (1-u)^(n-j) per axis, term evaluated left to right, accumulated from 0
@@ -94,14 +104,15 @@ pc_clearance_kernel(pc_tree T, pc_radius_dev R, const pc_traj_dev *__restrict__ 
             s_done = (i >= nseg);
         }
         __syncthreads();
-        const int cnt = s_count;
+        const int cnt = s_count, done = s_done;      // read BEFORE thread 0 can start publishing the next chunk
         // a warp takes 32 CONSECUTIVE samples: they are a few centimetres apart, i.e. an ideal packet
         for (int base = (threadIdx.x >> 5) * 32; base < cnt; base += PC_CLR_THREADS) {
             const int k = base + (threadIdx.x & 31);
             const bool have = k < cnt;
             double radius = INFINITY;
-            pc_best b; b.d2 = INFINITY; b.idx = -1; b.thr = -1.0f;
-            float qx = 0.f, qy = 0.f, qz = 0.f;
+            pc_best b[1];
+            b[0].d2 = INFINITY; b[0].idx = -1; b[0].thr = -1.0f;
+            float qv[1][3] = { { 0.f, 0.f, 0.f } };
             bool search = false;
             if (have) {
                 const int32_t sg = s_seg[k];
@@ -111,21 +122,21 @@ pc_clearance_kernel(pc_tree T, pc_radius_dev R, const pc_traj_dev *__restrict__ 
                 if (T.n_points == 0 || pc_radius_early_out(pos[0], pos[1], pos[2], R)) {
                     radius = __dsub_rn(R.max_radius, R.search_margin);
                 } else {
-                    qx = (float)pos[0]; qy = (float)pos[1]; qz = (float)pos[2];
-                    search = qx == qx && qy == qy && qz == qz;
-                    if (search) b.thr = R.bound_thr;
+                    qv[0][0] = (float)pos[0]; qv[0][1] = (float)pos[1]; qv[0][2] = (float)pos[2];
+                    search = qv[0][0] == qv[0][0] && qv[0][1] == qv[0][1] && qv[0][2] == qv[0][2];
+                    if (search) b[0].thr = R.bound_thr;
                 }
             }
-            pc_packet_traverse(T, qx, qy, qz, b, threadIdx.x & 31);
+            pc_packet_traverse<1>(T, qv, b, threadIdx.x & 31);
             if (have) {
-                if (search || !(radius < INFINITY)) radius = pc_radius_epilogue(b, R);
+                if (search || !(radius < INFINITY)) radius = pc_radius_epilogue(b[0], R);
                 my_min = fmin(my_min, radius);
                 if (radius < 0.0) atomicMin(&s_first_hit, (int)(chunk_base + k));
             }
         }
         chunk_base += cnt;
         __syncthreads();
-        if (s_done) break;
+        if (done) break;
     }
     // block reduction of the minimum radius
 #pragma unroll

@@ -1,7 +1,8 @@
 // comm_host.inl -- multi-GPU replication of a built index (included by pc_index.cu).
 //
 // One process per GPU.  The cloud index is read-only during queries, so the only exchange on the path is the
-// replication of the index: rank `root` builds it, one ncclBroadcast over NVLink/NVSwitch copies the tree array to
+// replication of the index: rank `root` builds it, one ncclBroadcast over NVLink/NVSwitch copies the tree array (records +
+// points, one contiguous span) to
 // the other ranks' handles, and every rank then answers its own contiguous slice of the query batch
 // (pc_shard_range) with no further collective.  NCCL is bound at run time with dlopen so that the library that a
 // host framework (e.g. torch) already loaded is reused and libpcindex.so has no link-time NCCL dependency.
@@ -100,7 +101,8 @@ extern "C" void pc_comm_destroy(pc_comm *c)
 
 // header of a replicated index, broadcast ahead of the tree array so that receivers can size their arena
 struct pc_bcast_header {
-    int64_t n, n_leaves, P;
+    int64_t n, n_nodes;
+    uint32_t root, root_count;
     uint32_t bbox[6];
     uint32_t leaf;      // PC_LEAF of the sender (must match)
     uint32_t pad;
@@ -117,7 +119,7 @@ extern "C" int pc_index_broadcast(pc_index *ix, pc_comm *c, int root)
     pc_bcast_header h;
     memset(&h, 0, sizeof h);
     if (c->rank == root) {
-        h.n = ix->n; h.n_leaves = ix->n_leaves; h.P = ix->P; h.leaf = PC_LEAF;
+        h.n = ix->n; h.n_nodes = ix->n_nodes; h.root = ix->root; h.root_count = ix->root_count; h.leaf = PC_LEAF;
         if (ix->n > 0) PC_CUDA(ix, cudaMemcpyAsync(h.bbox, ix->d_bbox, sizeof h.bbox, cudaMemcpyDeviceToHost, st));
         PC_CUDA(ix, cudaStreamSynchronize(st));
         PC_CUDA(ix, cudaMemcpyAsync(scr, &h, sizeof h, cudaMemcpyHostToDevice, st));
@@ -130,17 +132,15 @@ extern "C" int pc_index_broadcast(pc_index *ix, pc_comm *c, int root)
         if (h.n > ix->cap) {
             if ((rc = pc_reserve_cloud(ix, h.n)) != PC_OK) return rc;
         }
-        ix->n = h.n; ix->n_leaves = h.n_leaves; ix->P = h.P; ix->build_timed = false;
-        ix->lbvh_ready = false;                 // the experimental second tree is not broadcast: receivers walk the implicit one
-        ix->nodes = ix->tree;
-        ix->points = ix->tree + 4 * h.P;
+        ix->n = h.n; ix->n_nodes = h.n_nodes; ix->root = h.root; ix->root_count = h.root_count; ix->build_timed = false;
+        ix->points = ix->tree + 4 * h.n_nodes;
         if (h.n > 0) PC_CUDA(ix, cudaMemcpyAsync(ix->d_bbox, h.bbox, sizeof h.bbox, cudaMemcpyHostToDevice, st));
         memcpy(ix->h_bbox, h.bbox, sizeof h.bbox);
         ix->bbox_from_bcast = h.n > 0;
     }
     if (h.n > 0) {
-        // boxes [0, 4P) and the leaf records [4P, 4P + PC_LEAF * n_leaves) are one contiguous span of the tree array
-        const size_t bytes = (size_t)(4 * h.P + (int64_t)PC_LEAF * h.n_leaves) * sizeof(float4);
+        // records [0, 4 n_nodes) and the points (+ PC_LEAF pad copies) behind them are one contiguous span of the tree array
+        const size_t bytes = (size_t)(4 * h.n_nodes + h.n + PC_LEAF) * sizeof(float4);
         if ((int64_t)(bytes / sizeof(float4)) > ix->tree_cap) return pc_fail(ix, PC_ENOMEM, "pc_index_broadcast: arena too small");
         PC_NCCL(ix, g_nccl.Broadcast(ix->tree, ix->tree, bytes, 0 /* ncclInt8 */, root, c->nccl, st));
     }

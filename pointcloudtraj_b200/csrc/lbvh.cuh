@@ -1,4 +1,4 @@
-// lbvh.cuh -- groundwork for the prefix-split tree planned in DESIGN.md section 8 (not yet used by libpcindex.so).
+// lbvh.cuh -- the prefix-split tree of the index: per-node range / split function and record layout (host + device).
 //
 // Node ranges and splits of a binary radix tree over SORTED curve keys, one independent computation per inner node
 // (T. Karras, "Maximizing Parallelism in the Construction of BVHs, Octrees, and k-d Trees", HPG 2012, section 3): every
@@ -7,7 +7,7 @@
 // (key[i], i)), so all elements are distinct and the tree is well defined for clouds with coincident points.
 //
 // The functions compile for the host as well (tests/c/lbvh_check.cpp checks them against a recursive top-down
-// construction on the CPU); the CUDA build kernel of the next round calls pc_lbvh_node once per thread.
+// construction on the CPU); pc_tree_nodes_kernel (build_kernels.cuh) calls pc_lbvh_node once per thread.
 #pragma once
 #include <stdint.h>
 
@@ -62,7 +62,7 @@ PC_HD void pc_lbvh_node(const KeyT *keys, int64_t n, int64_t i, int64_t *first, 
     *split = g;
 }
 
-// ---- planned record layout and single-query walk (host + device), see DESIGN.md section 8 ---------------------------------
+// ---- record layout and single-query walk (host + device), see DESIGN.md section 3 ---------------------------------------
 // One 64-byte record per inner node i, four float4: [min0 | max0 | min1 | max1] = the boxes of its two children; the
 // otherwise unused .w words hold the children: min.w = child reference, max.w = number of points when the child is a leaf.
 // A child whose range holds <= PC_LBVH_LEAF points is a LEAF: the reference is PC_REF_LEAF | (index of its first point in

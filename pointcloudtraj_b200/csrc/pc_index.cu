@@ -16,11 +16,10 @@
 #include "radix_sort.cuh"
 #include "build_kernels.cuh"
 #include "query_kernels.cuh"
-#include "lbvh_kernels.cuh"
 #include "range_kernels.cuh"
 #include "clearance_kernels.cuh"
 
-#define PC_VERSION_STRING "pcindex 0.1 (sm_100a)"
+#define PC_VERSION_STRING "pcindex 0.2 (sm_100a)"
 #define PC_PIPE_LANES 3                 // concurrent H2D / kernel / D2H chunks for PC_HOST calls
 #define PC_HOST_CHUNK (3 << 20)         // queries per pipelined chunk (scripts/e2e_sweep.py: 3 Mi with a 1/4, 1/2 ramp is the
                                         // optimum for 10 M batches; smaller chunks are sparser subsets -> less coherent packets)
@@ -40,7 +39,7 @@ struct pc_lane {
     uint32_t *keys_a = nullptr, *keys_b = nullptr, *vals_a = nullptr, *vals_b = nullptr; int64_t sort_cap = 0;
     uint32_t *tile_hist = nullptr; int64_t hist_cap = 0;
     uint32_t *digit_total = nullptr;
-    unsigned long long *counter = nullptr;                   // work counter of the persistent query kernel
+    unsigned long long *counter = nullptr;                   // [1]: queries that still need a search after the ordering pass
     double per_cell = 0.0;                                   // last ordered batch: estimated queries per 1/256-extent cell
     cudaEvent_t done = nullptr;
     cudaStream_t order_stream = nullptr;                     // high-priority stream for the ordering pass of pipelined batches
@@ -57,7 +56,8 @@ struct pc_index {
 
     // cloud / index
     int64_t cap = 0;          // points the arena can hold
-    int64_t n = 0, n_leaves = 0, P = 2;
+    int64_t n = 0, n_nodes = 0;   // points, inner-node records (n - 1, or 0 when the cloud is a single leaf)
+    uint32_t root = PC_REF_LEAF, root_count = 0;
     int key_bytes = 4;
     float *d_xyz = nullptr;   // staging copy of the caller's cloud for PC_HOST builds (cap * 4 floats)
     uint32_t *d_bbox = nullptr;
@@ -65,9 +65,8 @@ struct pc_index {
     uint32_t *vals_a = nullptr, *vals_b = nullptr;
     uint32_t *tile_hist = nullptr; int64_t hist_cap = 0;
     uint32_t *digit_total = nullptr;
-    float4 *tree = nullptr; int64_t tree_cap = 0;   // one allocation: boxes [0, 4P) then leaf records [4P, 6P)
-    float4 *points = nullptr;                       // = tree + 4P of the current build
-    float4 *nodes = nullptr;                        // = tree
+    float4 *tree = nullptr; int64_t tree_cap = 0;   // one allocation: records [0, 4 n_nodes) then points [4 n_nodes, + n + PC_LEAF)
+    float4 *points = nullptr;                       // = tree + 4 n_nodes of the current build
     cudaEvent_t ev_b0 = nullptr, ev_b1 = nullptr, ev_ready = nullptr, ev_in = nullptr;
     uint32_t *h_bbox = nullptr;                      // pinned host copy of d_bbox, valid once ev_b1 has completed
     bool build_timed = false;
@@ -83,24 +82,17 @@ struct pc_index {
     float *tiny_q = nullptr, *tiny_f = nullptr; int32_t *tiny_i = nullptr;          // host addresses
     float *tiny_q_dev = nullptr, *tiny_f_dev = nullptr; int32_t *tiny_i_dev = nullptr;   // the same memory as the device sees it
 
-    // experimental prefix-split tree (lbvh_kernels.cuh), only with PC_LBVH=1 in the environment at pc_index_create
-    bool use_lbvh = false, lbvh_ready = false;
-    float4 *lbvh_rec = nullptr;            // (cap - 1) records of 4 float4
-    int32_t *lbvh_parent = nullptr;
-    int *lbvh_arrived = nullptr;
-    uint32_t lbvh_root = PC_REF_LEAF;
-
     int64_t launches = 0;
     bool profile = false, profiled = false;
-    // tuning knobs (environment: PC_QUERY_KERNEL, PC_SORT_BITS, PC_MIN_IDLE), see DESIGN.md "Query kernel variants"
-    int query_kernel = 3;     // 1 = thread per query, 2 = persistent lane refill, 3 = warp packets of 32 (ordered batches) /
-                              // warp per query (small unordered ones), 4 = packets of 64
+    // tuning knobs (environment: PC_QUERY_KERNEL, PC_SORT_BITS), see DESIGN.md "Query kernel variants"
+    int query_kernel = 3;     // 1 = thread per query, 3 = warp packets of 32 (ordered batches) / warp per query (small
+                              // unordered ones), 4 = packets of 64
     bool query_kernel_auto = true;   // no PC_QUERY_KERNEL in the environment: 3, or 4 for dense batches
     int sort_bits = 24;       // radix-sorted key width of the batch ordering pass (0 = never order)
     bool sort_bits_auto = true;   // no PC_SORT_BITS in the environment: pick 24 or 32 from the batch density
-    int min_idle = 8;         // persistent kernel: refill once this many lanes are idle
     int next_lane = 0;        // PC_HOST_ASYNC: lane of the next batch
     int shard_rank = 0, shard_n = 1;   // pc_batch_shard
+    int radius_arith = PC_ARITH_FP64;  // pc_index_set_radius_arith
     int coop_group = 0;                     // lanes per query of the small-batch kernel: 0 = by batch size, else 32 / 16 / 8 (PC_COOP_GROUP)
     int64_t coop_g32_max = 24576, coop_g16_max = 65536;  // batch sizes up to which 32 / 16 lanes per query are used (measured:
                                                          // narrower groups gain 5-12 % above these sizes, lose below)
@@ -144,13 +136,6 @@ static int pc_grow(pc_index *ix, T **ptr, int64_t *cap, int64_t want, int64_t mi
     return PC_OK;
 }
 
-static int64_t pc_pow2_ge(int64_t v)
-{
-    int64_t p = 2;
-    while (p < v) p <<= 1;
-    return p;
-}
-
 static int pc_key_bits_per_axis(int64_t n)
 {
     // 10 bits per axis (30-bit keys, 4 radix passes) up to 4 Mi points; beyond that one more bit per axis for
@@ -171,24 +156,15 @@ static int pc_reserve_cloud(pc_index *ix, int64_t n)
     cudaFree(ix->tree); cudaFree(ix->tile_hist);
     ix->tree = nullptr; ix->tree_cap = 0;
     ix->d_xyz = nullptr; ix->keys_a = ix->keys_b = nullptr; ix->vals_a = ix->vals_b = nullptr;
-    ix->points = ix->nodes = nullptr; ix->tile_hist = nullptr; ix->cap = 0; ix->hist_cap = 0;
+    ix->points = nullptr; ix->tile_hist = nullptr; ix->cap = 0; ix->hist_cap = 0;
     ix->key_bytes = pc_key_bits_per_axis(cap) > 10 ? 8 : 4;
     PC_CUDA(ix, cudaMalloc((void **)&ix->d_xyz, (size_t)cap * 4 * sizeof(float)));
     PC_CUDA(ix, cudaMalloc(&ix->keys_a, (size_t)cap * ix->key_bytes));
     PC_CUDA(ix, cudaMalloc(&ix->keys_b, (size_t)cap * ix->key_bytes));
     PC_CUDA(ix, cudaMalloc((void **)&ix->vals_a, (size_t)cap * sizeof(uint32_t)));
     PC_CUDA(ix, cudaMalloc((void **)&ix->vals_b, (size_t)cap * sizeof(uint32_t)));
-    int64_t leaves = (cap + PC_LEAF - 1) / PC_LEAF;
-    int64_t P = pc_pow2_ge(leaves);
-    ix->tree_cap = 4 * P + PC_LEAF * P + 2 * PC_LEAF;      // + padding points for leaf scans that start anywhere (lbvh)
+    ix->tree_cap = 4 * cap + cap + 2 * PC_LEAF;            // one 64-byte record and one point per point, + pad points
     PC_CUDA(ix, cudaMalloc((void **)&ix->tree, (size_t)ix->tree_cap * sizeof(float4)));
-    if (ix->use_lbvh) {
-        cudaFree(ix->lbvh_rec); cudaFree(ix->lbvh_parent); cudaFree(ix->lbvh_arrived);
-        ix->lbvh_rec = nullptr; ix->lbvh_parent = nullptr; ix->lbvh_arrived = nullptr; ix->lbvh_ready = false;
-        PC_CUDA(ix, cudaMalloc((void **)&ix->lbvh_rec, (size_t)cap * 4 * sizeof(float4)));
-        PC_CUDA(ix, cudaMalloc((void **)&ix->lbvh_parent, (size_t)cap * sizeof(int32_t)));
-        PC_CUDA(ix, cudaMalloc((void **)&ix->lbvh_arrived, (size_t)cap * sizeof(int)));
-    }
     ix->hist_cap = (int64_t)RS_RADIX * (rs_num_tiles<8>(cap) + 1);
     PC_CUDA(ix, cudaMalloc((void **)&ix->tile_hist, (size_t)ix->hist_cap * sizeof(uint32_t)));
     ix->cap = cap;
@@ -215,16 +191,14 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         TRY(cudaGetDeviceProperties(&prop, device));
         if (prop.major < 10) { rc = pc_fail(nullptr, PC_ECUDA, "pc_index_create: device is sm_%d%d, this library is built for sm_100a only", prop.major, prop.minor); break; }
         ix->sm_count = prop.multiProcessorCount;
-        if (const char *v = getenv("PC_QUERY_KERNEL")) { ix->query_kernel_auto = false; int b_ = atoi(v); ix->query_kernel = (b_ >= 1 && b_ <= 4) ? b_ : 3; }
+        if (const char *v = getenv("PC_QUERY_KERNEL")) { ix->query_kernel_auto = false; int b_ = atoi(v); ix->query_kernel = (b_ == 1 || b_ == 4) ? b_ : 3; }
         if (const char *v = getenv("PC_SORT_BITS")) { ix->sort_bits_auto = false; int b_ = atoi(v); ix->sort_bits = b_ <= 0 ? 0 : (b_ <= 16 ? 16 : (b_ <= 24 ? 24 : 32)); }
         if (const char *v = getenv("PC_HOST_RAMP")) ix->host_ramp = atoi(v) != 0;
         if (const char *v = getenv("PC_HOST_CHUNK_QUERIES")) { long long b_ = atoll(v); if (b_ >= 1024) ix->host_chunk = b_; }
-        if (const char *v = getenv("PC_LBVH")) ix->use_lbvh = atoi(v) != 0;
         if (const char *v = getenv("PC_COOP_GROUP")) { int b_ = atoi(v); ix->coop_group = (b_ == 32 || b_ == 16 || b_ == 8) ? b_ : 0; }
         if (const char *v = getenv("PC_COOP_MAX_BATCH")) { long long b_ = atoll(v); ix->coop_max = b_ < 0 ? 0 : b_; }
         if (const char *v = getenv("PC_SORT_MIN_BATCH")) { long long b_ = atoll(v); ix->sort_min = b_ < 1 ? 1 : b_; }
         if (const char *v = getenv("PC_TINY_BATCH_QUERIES")) { long long b_ = atoll(v); ix->tiny_batch = b_ < 0 ? 0 : (b_ > PC_TINY_BATCH ? PC_TINY_BATCH : b_); }
-        if (const char *v = getenv("PC_MIN_IDLE")) { int b_ = atoi(v); ix->min_idle = b_ < 1 ? 1 : (b_ > 32 ? 32 : b_); }
         if (cuda_stream) { ix->stream = (cudaStream_t)cuda_stream; ix->own_stream = false; }
         else { TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking)); ix->own_stream = true; }
         TRY(cudaEventCreate(&ix->ev_b0));
@@ -296,7 +270,6 @@ extern "C" void pc_index_destroy(pc_index *ix)
     cudaFree(ix->d_xyz); cudaFree(ix->d_bbox); cudaFree(ix->keys_a); cudaFree(ix->keys_b);
     cudaFree(ix->vals_a); cudaFree(ix->vals_b); cudaFree(ix->tile_hist); cudaFree(ix->digit_total);
     cudaFree(ix->tree); cudaFree(ix->scratch);
-    cudaFree(ix->lbvh_rec); cudaFree(ix->lbvh_parent); cudaFree(ix->lbvh_arrived);
     if (ix->ev_b0) cudaEventDestroy(ix->ev_b0);
     if (ix->ev_b1) cudaEventDestroy(ix->ev_b1);
     if (ix->ev_ready) cudaEventDestroy(ix->ev_ready);
@@ -375,7 +348,7 @@ extern "C" int pc_index_build(pc_index *ix, const float *xyz, int64_t n, int64_t
         return pc_fail(ix, PC_EINVAL, "pc_index_build: bad argument (n=%lld stride=%lld space=%d)", (long long)n, (long long)stride_floats, space);
     if (n > ((int64_t)1 << 31) - 16) return pc_fail(ix, PC_EINVAL, "pc_index_build: at most 2^31-16 points");
     PC_CUDA(ix, cudaSetDevice(ix->device));
-    if (n == 0) { ix->n = 0; ix->n_leaves = 0; ix->P = 2; ix->build_timed = false; ix->lbvh_ready = false; return PC_OK; }
+    if (n == 0) { ix->n = 0; ix->n_nodes = 0; ix->root = PC_REF_LEAF; ix->root_count = 0; ix->build_timed = false; return PC_OK; }
     if (n > ix->cap) {
         PC_CUDA(ix, cudaStreamSynchronize(ix->stream));
         int rc = pc_reserve_cloud(ix, n);
@@ -416,52 +389,31 @@ extern "C" int pc_index_build(pc_index *ix, const float *xyz, int64_t n, int64_t
     }
     if (rc != PC_OK) return rc;
 
-    const int64_t n_leaves = (n + PC_LEAF - 1) / PC_LEAF;
-    const int64_t P = pc_pow2_ge(n_leaves);
-    ix->nodes = ix->tree;
-    ix->points = ix->tree + 4 * P;
+    // the radix tree over the sorted keys: records [0, 4 (n-1)), then the points in curve order.  The sort's spare buffers
+    // (the ones that do NOT hold the sorted result) serve as parent links and arrival counters of the bottom-up fit.
+    const int64_t n_nodes = n > PC_LEAF ? n - 1 : 0;
+    ix->points = ix->tree + 4 * n_nodes;
     {
-        int64_t slots = (n_leaves + 4) * PC_LEAF;       // up to 3 empty pad leaves after the last one
-        int grid = (int)((slots + PC_BUILD_THREADS - 1) / PC_BUILD_THREADS);
-        pc_leaf_kernel<<<grid, PC_BUILD_THREADS, 0, st>>>(src, stride, order, n, n_leaves, P, ix->points, ix->nodes);
+        int32_t *parent = (int32_t *)(order == ix->vals_a ? ix->vals_b : ix->vals_a);
+        int *arrived = (int *)(sorted_keys == ix->keys_a ? ix->keys_b : ix->keys_a);
+        const int grid = (int)((n + PC_LEAF + PC_BUILD_THREADS - 1) / PC_BUILD_THREADS);
+        if (bits <= 10)
+            pc_tree_nodes_kernel<uint32_t><<<grid, PC_BUILD_THREADS, 0, st>>>(src, stride, order, (const uint32_t *)sorted_keys, n, ix->tree, ix->points, parent, arrived);
+        else
+            pc_tree_nodes_kernel<uint64_t><<<grid, PC_BUILD_THREADS, 0, st>>>(src, stride, order, (const uint64_t *)sorted_keys, n, ix->tree, ix->points, parent, arrived);
         ix->launches++;
         PC_CHECK_LAUNCH(ix);
-    }
-    int top = 0;
-    while (((int64_t)1 << top) < P) top++;
-    int64_t cnt = n_leaves;
-    for (int lvl0 = 0; lvl0 < top;) {
-        int nl = top - lvl0 < PC_UP_LEVELS ? top - lvl0 : PC_UP_LEVELS;
-        // four CTAs more than the children need: the empty pad nodes after the last real node of EVERY produced level
-        // (up to index cnt_s + 3) must be written, and index k of level s lives in CTA (k << s) / 256 <= (cnt + 255) / 256 + 3
-        int grid = (int)((cnt + 2 * PC_UP_THREADS - 1) / (2 * PC_UP_THREADS)) + 4;
-        pc_upper_kernel<<<grid, PC_UP_THREADS, 0, st>>>(ix->nodes, P, lvl0, cnt, nl);
-        ix->launches++;
-        PC_CHECK_LAUNCH(ix);
-        for (int s = 0; s < nl; s++) cnt = (cnt + 1) >> 1;
-        lvl0 += nl;
-    }
-    ix->lbvh_ready = false;
-    if (ix->use_lbvh && ix->lbvh_rec) {
-        // experimental second tree (lbvh_kernels.cuh): ranges / splits / child links from the sorted keys, then the bottom-up fit
-        if (n > PC_LBVH_LEAF) {
-            const int grid = (int)((n - 1 + 255) / 256);
-            PC_CUDA(ix, cudaMemsetAsync(ix->lbvh_arrived, 0, (size_t)(n - 1) * sizeof(int), st));
-            if (bits <= 10)
-                pc_lbvh_nodes_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t *)sorted_keys, n, n_leaves, ix->lbvh_rec, ix->lbvh_parent, ix->points);
-            else
-                pc_lbvh_nodes_kernel<uint64_t><<<grid, 256, 0, st>>>((const uint64_t *)sorted_keys, n, n_leaves, ix->lbvh_rec, ix->lbvh_parent, ix->points);
-            pc_lbvh_fit_kernel<<<grid, 256, 0, st>>>(ix->lbvh_rec, ix->points, ix->lbvh_parent, ix->lbvh_arrived, n);
-            ix->launches += 2;
+        if (n_nodes > 0) {
+            pc_tree_fit_kernel<<<(int)((n_nodes + PC_BUILD_THREADS - 1) / PC_BUILD_THREADS), PC_BUILD_THREADS, 0, st>>>(ix->tree, ix->points, parent, arrived, n);
+            ix->launches++;
             PC_CHECK_LAUNCH(ix);
-            ix->lbvh_root = 0;
-            ix->lbvh_ready = true;
         }
     }
     PC_CUDA(ix, cudaMemcpyAsync(ix->h_bbox, ix->d_bbox, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PC_CUDA(ix, cudaEventRecord(ix->ev_b1, st));
     PC_CUDA(ix, cudaEventRecord(ix->ev_ready, st));
-    ix->n = n; ix->n_leaves = n_leaves; ix->P = P; ix->build_timed = true; ix->bbox_from_bcast = false;
+    ix->n = n; ix->n_nodes = n_nodes; ix->build_timed = true; ix->bbox_from_bcast = false;
+    ix->root = n_nodes > 0 ? 0u : PC_REF_LEAF; ix->root_count = n_nodes > 0 ? 0u : (uint32_t)n;
     if (space == PC_HOST) PC_CUDA(ix, cudaStreamSynchronize(st));
     return PC_OK;
 }
@@ -481,8 +433,8 @@ extern "C" int pc_index_view_get(const pc_index *ixc, pc_index_view *out)
     pc_index *ix = const_cast<pc_index *>(ixc);
     if (!ix || !out) return PC_EINVAL;
     memset(out, 0, sizeof *out);
-    out->n_points = ix->n; out->n_leaves = ix->n_leaves; out->leaf_base = ix->P;
-    out->points = ix->points; out->nodes = ix->nodes;
+    out->n_points = ix->n; out->n_nodes = ix->n_nodes; out->root = ix->root; out->root_count = ix->root_count;
+    out->points = ix->points; out->records = ix->tree;
     if (ix->n > 0) {
         uint32_t h[6];
         PC_CUDA(ix, cudaSetDevice(ix->device));
@@ -497,8 +449,7 @@ extern "C" int pc_index_view_get(const pc_index *ixc, pc_index_view *out)
 static pc_tree pc_tree_of(const pc_index *ix)
 {
     pc_tree T;
-    T.nodes = ix->nodes; T.points = ix->points; T.n_points = ix->n; T.P = (uint32_t)ix->P;
-    T.lbvh = ix->lbvh_ready ? ix->lbvh_rec : nullptr; T.lbvh_root = ix->lbvh_root;
+    T.rec = ix->tree; T.points = ix->points; T.n_points = ix->n; T.root = ix->root; T.root_count = ix->root_count;
     return T;
 }
 
@@ -532,7 +483,6 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
     // sort_bits (16 / 24 / 32) = radix-sorted key width = how many of the top curve bits order the batch; queries that
     // need no search (sensing-range early-outs) are answered by the key kernel and never enter the sort
     int bits = ix->sort_bits;
-    int shard_level = 5;                                  // curve cells per axis = 2^level dealt to the ranks (pc_batch_shard)
     L.per_cell = 0.0;
     if (ix->sort_bits_auto && ((ix->build_timed && cudaEventQuery(ix->ev_b1) == cudaSuccess) || ix->bbox_from_bcast)) {
         // 24 bits (8 per axis) order the batch well when its cells hold a handful of queries; a batch that is dense
@@ -548,23 +498,13 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
         const double per_cell = vol > 0.f ? (double)m * cell * cell * cell / vol : 0.0;
         bits = per_cell > 16.0 ? 32 : 24;
         L.per_cell = per_cell;
-        // pc_batch_shard: the finest curve cells (<= 128 per axis) that still hold ~512 queries each
-        if (vol > 0.f) {
-            shard_level = 2;
-            for (int lv = 7; lv >= 2; lv--) {
-                const double c = emax / (double)(1 << lv);
-                double v = 1.0;
-                for (int a = 0; a < 3; a++) v *= ext[a] > c ? ext[a] : c;
-                if ((double)m * c * c * c / v >= 512.0) { shard_level = lv; break; }
-            }
-        }
     }
     const int drop = 30 - bits > 0 ? 30 - bits : 0;     // 24-bit sort = top 24 curve bits, 32-bit sort = all 30
     const int grid = (int)((m + 255) / 256);
     if (A.kind == PC_Q_RADIUS)
-        pc_query_key_kernel<PC_KIND_RADIUS><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n, 30 - 3 * shard_level);
+        pc_query_key_kernel<PC_KIND_RADIUS><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n);
     else
-        pc_query_key_kernel<PC_KIND_NEAREST><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n, 30 - 3 * shard_level);
+        pc_query_key_kernel<PC_KIND_NEAREST><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n);
     ix->launches++;
     PC_CHECK_LAUNCH(ix);
     // only the L.counter[1] compacted entries (device-side count <= m) are sorted
@@ -626,7 +566,7 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
     const unsigned long long *m_eff = nullptr;
     const bool prof = ix->profile && &L == &ix->lane[0];
     if (prof) PC_CUDA(ix, cudaEventRecord(L.t0, L.stream));
-    // counter[0]: work counter of the persistent kernel, counter[1]: queries that need a search after the ordering pass
+    // counter[1]: queries that need a search after the ordering pass
     PC_CUDA(ix, cudaMemsetAsync(L.counter, 0, 2 * sizeof(unsigned long long), L.os));
     if (pc_want_sort(ix, A.flags, m)) {
         int rc = pc_sort_queries(ix, L, A, d_q, m, qstride, d_idx, d_f, &perm);
@@ -639,45 +579,31 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
     }
     if (prof) PC_CUDA(ix, cudaEventRecord(L.t1, L.stream));
     pc_tree T = pc_tree_of(ix);
-    const int64_t want = (m + PC_QUERY_THREADS - 1) / PC_QUERY_THREADS;
     // dense batches (>= 3 queries per cell of 1/256 of the cloud's extent): 64-query packets, two queries per lane
     // (profiles/r1_sweep5*: +10 % radius, +18 % nearest at 10 M queries; -3 % at 2 M, hence the threshold)
     const bool two_per_lane = ix->query_kernel == 4 || (ix->query_kernel == 3 && ix->query_kernel_auto && L.per_cell >= 3.0);
-    if (two_per_lane && perm) {
-        // Morton-ordered batch, two queries per lane: one warp walks the tree once for 64 neighbouring queries
-        const int grid = (int)((m + 2 * PC_QUERY_THREADS - 1) / (2 * PC_QUERY_THREADS));
-        if (T.lbvh) {                // experimental prefix-split tree (PC_LBVH=1)
+    if (ix->query_kernel >= 3 && perm) {
+        // curve-ordered batch: one warp walks the tree once for its 32 or 64 neighbouring queries
+        const int per_cta = (two_per_lane ? 2 : 1) * PC_QUERY_THREADS;
+        const int grid = (int)((m + per_cta - 1) / per_cta);
+        if (two_per_lane) {
             if (A.kind == PC_Q_NEAREST)
-                pc_query_packet2_lbvh_kernel<PC_KIND_NEAREST><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
+                pc_query_packet_kernel<PC_KIND_NEAREST, 2><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
             else
-                pc_query_packet2_lbvh_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
+                pc_query_packet_kernel<PC_KIND_RADIUS, 2><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
         } else if (A.kind == PC_Q_NEAREST)
-            pc_query_packet2_kernel<PC_KIND_NEAREST><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
+            pc_query_packet_kernel<PC_KIND_NEAREST, 1><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
         else
-            pc_query_packet2_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
-    } else if (ix->query_kernel >= 3 && perm) {
-        // Morton-ordered batch: one warp walks the tree once for its 32 neighbouring queries
-        const int grid = (int)want;
-        if (A.kind == PC_Q_NEAREST)
-            pc_query_packet_kernel<PC_KIND_NEAREST><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
-        else
-            pc_query_packet_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
+            pc_query_packet_kernel<PC_KIND_RADIUS, 1><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
     } else if (ix->query_kernel >= 3 && !perm && m <= ix->coop_max) {
         // small unordered batch: one warp per query (a thread-per-query search is a chain of dependent loads)
         pc_launch_coop(ix, A, T, d_q, m, qstride, d_idx, d_f, L.stream);
-    } else if (ix->query_kernel != 2) {
-        const int grid = (int)want;
+    } else {
+        const int grid = (int)((m + PC_QUERY_THREADS - 1) / PC_QUERY_THREADS);
         if (A.kind == PC_Q_NEAREST)
             pc_query_simple_kernel<PC_KIND_NEAREST><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
         else
             pc_query_simple_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
-    } else {
-        // persistent grid: up to 8 CTAs of 4 warps per SM (<= 64 registers/thread), fewer when the batch is small
-        const int grid = (int)(want < (int64_t)ix->sm_count * 8 ? want : (int64_t)ix->sm_count * 8);
-        if (A.kind == PC_Q_NEAREST)
-            pc_query_persist_kernel<PC_KIND_NEAREST><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f, L.counter, ix->min_idle);
-        else
-            pc_query_persist_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f, L.counter, ix->min_idle);
     }
     ix->launches++;
     PC_CHECK_LAUNCH(ix);
@@ -688,8 +614,17 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
 extern "C" int pc_batch_shard(pc_index *ix, int rank, int n_ranks)
 {
     if (!ix || n_ranks < 1 || rank < 0 || rank >= n_ranks) return pc_fail(ix, PC_EINVAL, "pc_batch_shard: bad argument");
+    if (n_ranks > 1 && ix->sort_bits == 0)
+        return pc_fail(ix, PC_EINVAL, "pc_batch_shard: the share is selected by the ordering pass, which PC_SORT_BITS=0 disabled");
     ix->shard_rank = rank;
     ix->shard_n = n_ranks;
+    return PC_OK;
+}
+
+extern "C" int pc_index_set_radius_arith(pc_index *ix, int mode)
+{
+    if (!ix || (mode != PC_ARITH_FP64 && mode != PC_ARITH_PCL_FLOAT)) return pc_fail(ix, PC_EINVAL, "pc_index_set_radius_arith: bad argument");
+    ix->radius_arith = mode;
     return PC_OK;
 }
 
@@ -852,6 +787,7 @@ static int pc_make_radius_dev(pc_index *ix, const pc_radius_params *p, int flags
     R->search_margin = p->search_margin; R->max_radius = p->max_radius; R->sample_range = p->sample_range;
     R->sx = p->start[0]; R->sy = p->start[1]; R->sz = p->start[2];
     R->bounded = (flags & PC_RADIUS_FULL_NN) ? 0 : 1;
+    R->pcl_float = ix->radius_arith == PC_ARITH_PCL_FLOAT ? 1 : 0;
     R->bound_thr = FLT_MAX;
     if (R->bounded) {
         // radius = min(sqrt(d2) - margin, max_radius): every d > max_radius + margin gives max_radius, so the search

@@ -20,6 +20,8 @@ extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64
 {
     int rc = pc_check_query_args(ix, "pc_range_batch", q_xyz, m, q_stride, space);
     if (rc != PC_OK) return rc;
+    if (space != PC_HOST && space != PC_DEVICE)            // the ASYNC spaces are for nearest / radius batches only
+        return pc_fail(ix, PC_EINVAL, "pc_range_batch: space must be PC_HOST or PC_DEVICE");
     if (!out_offsets || (m > 0 && !range) || cap < 0 || (cap > 0 && !out_idx))
         return pc_fail(ix, PC_EINVAL, "pc_range_batch: bad argument");
     PC_CUDA(ix, cudaSetDevice(ix->device));
@@ -57,12 +59,8 @@ extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64
         return PC_OK;
     }
     pc_tree T = pc_tree_of(ix);
-    const int grid = (int)((m + PC_QUERY_THREADS - 1) / PC_QUERY_THREADS);
-    // one warp per query (PC_QUERY_KERNEL=1: the first implementation, one thread per query, kept for comparison)
-    const bool coop = ix->query_kernel != 1;
-    const int cgrid = (int)((m + PC_RCOOP_WARPS - 1) / PC_RCOOP_WARPS);
-    if (coop) pc_range_coop_kernel<false><<<cgrid, 32 * PC_RCOOP_WARPS, 0, st>>>(T, d_q, m, qs, d_r, range_is_scalar ? 1 : 0, d_cnt, nullptr, nullptr);
-    else pc_range_count_kernel<<<grid, PC_QUERY_THREADS, 0, st>>>(T, d_q, m, qs, d_r, range_is_scalar ? 1 : 0, d_cnt);
+    const int cgrid = (int)((m + PC_RCOOP_WARPS - 1) / PC_RCOOP_WARPS);      // one warp per query
+    pc_range_coop_kernel<false><<<cgrid, 32 * PC_RCOOP_WARPS, 0, st>>>(T, d_q, m, qs, d_r, range_is_scalar ? 1 : 0, d_cnt, nullptr, nullptr);
     pc_scan_tile_sums<<<(int)n_tiles, PC_SCAN_THREADS, 0, st>>>(d_cnt, m, d_tile);
     pc_scan_tile_offsets<<<1, PC_SCAN_THREADS, 0, st>>>(d_tile, n_tiles);
     pc_scan_write_offsets<<<(int)n_tiles, PC_SCAN_THREADS, 0, st>>>(d_cnt, m, d_tile, d_off);
@@ -84,8 +82,7 @@ extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64
         if ((rc = pc_grow(ix, &L.d_i32, &L.i32_cap, total)) != PC_OK) return rc;
         d_out = L.d_i32;
     }
-    if (coop) pc_range_coop_kernel<true><<<cgrid, 32 * PC_RCOOP_WARPS, 0, st>>>(T, d_q, m, qs, d_r, range_is_scalar ? 1 : 0, nullptr, d_off, d_out);
-    else pc_range_fill_kernel<<<grid, PC_QUERY_THREADS, 0, st>>>(T, d_q, m, qs, d_r, range_is_scalar ? 1 : 0, d_off, d_out);
+    pc_range_coop_kernel<true><<<cgrid, 32 * PC_RCOOP_WARPS, 0, st>>>(T, d_q, m, qs, d_r, range_is_scalar ? 1 : 0, nullptr, d_off, d_out);
     ix->launches++;
     PC_CHECK_LAUNCH(ix);
     if (space == PC_HOST) {

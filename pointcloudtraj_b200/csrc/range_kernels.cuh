@@ -5,81 +5,9 @@
 // evaluated in fp64 in its operation order; unlike the reference the far side of a split is never skipped, so a
 // point at exactly `range` is always reported (the reference misses it from one side, kdtree.c:283 -- SURVEY 8c-5).
 // Two passes over the same traversal: count, (scan on the device), fill; every list is then sorted by original
-// index so the output is canonical.
+// index so the output is canonical.  One WARP per query in both passes.
 #pragma once
 #include "query_kernels.cuh"
-
-template <bool FILL>
-__device__ __forceinline__ void pc_range_leaf(const float4 *__restrict__ pts, int64_t first_slot, int64_t n_points,
-                                              float qx, float qy, float qz, double qxd, double qyd, double qzd,
-                                              float thr, double r2, int32_t *__restrict__ out, int64_t &count)
-{
-    float4 p[PC_LEAF];
-#pragma unroll
-    for (int i = 0; i < PC_LEAF; i++) p[i] = __ldg(pts + i);
-#pragma unroll
-    for (int i = 0; i < PC_LEAF; i++) {
-        float dx = p[i].x - qx, dy = p[i].y - qy, dz = p[i].z - qz;
-        float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-        if (d <= thr && first_slot + i < n_points) {           // the tail of the last leaf repeats the last point
-            double e = pc_exact_d2(p[i].x, p[i].y, p[i].z, qxd, qyd, qzd);
-            if (e <= r2) {
-                if (FILL) out[count] = __float_as_int(p[i].w);
-                count++;
-            }
-        }
-    }
-}
-
-template <bool FILL>
-__device__ __forceinline__ int64_t pc_range_traverse(const pc_tree &T, float qx, float qy, float qz, double range,
-                                                     int32_t *__restrict__ out)
-{
-    const double qxd = (double)qx, qyd = (double)qy, qzd = (double)qz;
-    const double r2 = __dmul_rn(range, range);
-    if (!(r2 == r2)) return 0;   // NaN range
-    const float thr = fminf(__fmul_ru(__double2float_ru(r2), PC_THR_SLACK), FLT_MAX);
-    uint32_t stack_node[PC_STACK];
-    int sp = 0;
-    uint32_t node = 1;
-    int64_t count = 0;
-    for (;;) {
-        const float4 *pair = T.nodes + 4ull * node;
-        float4 lo0, hi0, lo1, hi1;
-        pc_load_box(pair, lo0, hi0);
-        pc_load_box(pair + 2, lo1, hi1);
-        const bool in0 = pc_box_d2(lo0, hi0, qx, qy, qz) <= thr;
-        const bool in1 = pc_box_d2(lo1, hi1, qx, qy, qz) <= thr;
-        const uint32_t c0 = 2u * node;
-        bool descended = false;
-        if (c0 >= T.P) {
-            if (in0) pc_range_leaf<FILL>(T.points + (size_t)(c0 - T.P) * PC_LEAF, (int64_t)(c0 - T.P) * PC_LEAF, T.n_points,
-                                         qx, qy, qz, qxd, qyd, qzd, thr, r2, out, count);
-            if (in1) pc_range_leaf<FILL>(T.points + (size_t)(c0 + 1 - T.P) * PC_LEAF, (int64_t)(c0 + 1 - T.P) * PC_LEAF, T.n_points,
-                                         qx, qy, qz, qxd, qyd, qzd, thr, r2, out, count);
-        } else {
-            if (in0 && in1) { stack_node[sp++] = c0 + 1; node = c0; descended = true; }
-            else if (in0) { node = c0; descended = true; }
-            else if (in1) { node = c0 + 1; descended = true; }
-        }
-        if (descended) continue;
-        if (sp == 0) break;
-        node = stack_node[--sp];
-    }
-    return count;
-}
-
-__global__ void __launch_bounds__(PC_QUERY_THREADS)
-pc_range_count_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstride,
-                      const double *__restrict__ range, int range_is_scalar, int64_t *__restrict__ counts)
-{
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= m) return;
-    const float *qq = q + k * qstride;
-    int64_t c = 0;
-    if (T.n_points > 0) c = pc_range_traverse<false>(T, qq[0], qq[1], qq[2], range[range_is_scalar ? 0 : k], nullptr);
-    counts[k] = c;
-}
 
 // in-place heap sort of one query's list (ascending original index); lists are short (tens to hundreds)
 __device__ __forceinline__ void pc_sort_list(int32_t *__restrict__ a, int64_t n)
@@ -110,26 +38,13 @@ __device__ __forceinline__ void pc_sort_list(int32_t *__restrict__ a, int64_t n)
     }
 }
 
-__global__ void __launch_bounds__(PC_QUERY_THREADS)
-pc_range_fill_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstride,
-                     const double *__restrict__ range, int range_is_scalar,
-                     const int64_t *__restrict__ offsets, int32_t *__restrict__ out_idx)
-{
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= m) return;
-    const int64_t begin = offsets[k], want = offsets[k + 1] - begin;
-    if (want == 0 || T.n_points == 0) return;
-    const float *qq = q + k * qstride;
-    pc_range_traverse<true>(T, qq[0], qq[1], qq[2], range[range_is_scalar ? 0 : k], out_idx + begin);
-    pc_sort_list(out_idx + begin, want);
-}
-
 // ---- one WARP per range query -----------------------------------------------------------------------------------------
-// Same frontier walk as pc_query_coop_kernel (query_kernels.cuh), without a bound to tighten: the open nodes sit on a LIFO
-// frontier in shared memory, every step each lane takes one of them and either tests its two child boxes (survivors are
-// pushed with ballot-computed positions) or scans its leaf (hits are appended with ballot-computed positions).  The count
-// pass and the fill pass are the same walk; the fill pass then sorts its list by original index with a bitonic network in
-// the same shared memory (lists up to 1024 hits; longer ones fall back to the single-thread heap sort).
+// Same frontier walk as pc_query_coop_kernel (query_kernels.cuh), without a bound to tighten: the open inner nodes sit on a
+// LIFO frontier in shared memory, every step each lane takes one of them and tests its two child boxes; a child that is a
+// leaf is scanned on the spot (only its own `count` points: its neighbours' points belong to other leaves) and the hits are
+// appended at ballot-computed positions, inner children are pushed.  The count pass and the fill pass are the same walk; the
+// fill pass then sorts its list by original index with a bitonic network in the same shared memory (lists up to 1024 hits;
+// longer ones fall back to a single-thread heap sort).
 #define PC_RCOOP_CAP 1024
 #define PC_RCOOP_WARPS 4
 
@@ -159,61 +74,81 @@ pc_range_coop_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstr
     }
     const float thr = fminf(__fmul_ru(__double2float_ru(r2), PC_THR_SLACK), FLT_MAX);
     uint32_t *F = s_front[w];
-    int size = 1;
-    if (T.P >= 64) {
-        const int64_t per = (int64_t)(T.P >> 5), n_leaves = (T.n_points + PC_LEAF - 1) / PC_LEAF;
-        size = (int)((n_leaves + per - 1) / per);
-        if (lane < size) F[lane] = 32u + (uint32_t)lane;
-    } else if (lane == 0) F[0] = 1u;
-    __syncwarp();
     const uint32_t lt = (1u << lane) - 1u;
     int64_t total = 0;
+    int size = 0;
+    if (T.root & PC_REF_LEAF) {
+        // the whole cloud is one leaf: one point per lane
+        bool hit = false;
+        int32_t id = 0;
+        if (lane < (int)T.root_count) {
+            const float4 p = __ldg(T.points + lane);
+            const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+            if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr) hit = pc_exact_d2(p.x, p.y, p.z, qxd, qyd, qzd) <= r2;
+            id = __float_as_int(p.w);
+        }
+        const uint32_t mask = __ballot_sync(PC_FULL_MASK, hit);
+        if (FILL && hit) out_idx[begin + __popc(mask & lt)] = id;
+        total = __popc(mask);
+    } else {
+        if (lane == 0) F[0] = T.root;
+        size = 1;
+    }
+    __syncwarp();
     while (size > 0) {
-        const int take = (size + 64 <= PC_RCOOP_CAP) ? min(size, 32) : 1;
+        // every lane takes one node and pushes at most two; close to the capacity: one node per step (depth-first, at most
+        // one more entry per tree level)
+        const int take = (size + 64 + PC_STACK <= PC_RCOOP_CAP) ? min(size, 32) : 1;
         const bool active = lane < take;
         uint32_t node = 0;
         if (active) node = F[size - 1 - lane];
         size -= take;
         __syncwarp();
-        const bool leaf = active && node >= T.P;
-        bool in0 = false, in1 = false;
-        if (active && !leaf) {
-            const float4 *pair = T.nodes + 4ull * node;
+        bool push0 = false, push1 = false, leaf0 = false, leaf1 = false;
+        uint32_t r0 = 0, r1 = 0, c0 = 0, c1 = 0;
+        if (active) {
+            const float4 *pair = T.rec + 4ull * node;
             float4 lo0, hi0, lo1, hi1;
             pc_load_box(pair, lo0, hi0);
             pc_load_box(pair + 2, lo1, hi1);
-            in0 = pc_box_d2(lo0, hi0, qx, qy, qz) <= thr;
-            in1 = pc_box_d2(lo1, hi1, qx, qy, qz) <= thr;
+            const bool in0 = pc_box_d2(lo0, hi0, qx, qy, qz) <= thr;
+            const bool in1 = pc_box_d2(lo1, hi1, qx, qy, qz) <= thr;
+            r0 = __float_as_uint(lo0.w); r1 = __float_as_uint(lo1.w);
+            c0 = __float_as_uint(hi0.w); c1 = __float_as_uint(hi1.w);
+            leaf0 = in0 && (r0 & PC_REF_LEAF); leaf1 = in1 && (r1 & PC_REF_LEAF);
+            push0 = in0 && !(r0 & PC_REF_LEAF); push1 = in1 && !(r1 & PC_REF_LEAF);
         }
-        if (__ballot_sync(PC_FULL_MASK, leaf)) {
-            bool hit[PC_LEAF];
-            int32_t id[PC_LEAF];
+        if (__ballot_sync(PC_FULL_MASK, leaf0 || leaf1)) {
+            bool hit[2 * PC_LEAF];
+            int32_t id[2 * PC_LEAF];
 #pragma unroll
-            for (int i = 0; i < PC_LEAF; i++) { hit[i] = false; id[i] = 0; }
-            if (leaf) {
-                const int64_t slot0 = (int64_t)(node - T.P) * PC_LEAF;
-                const float4 *pts = T.points + slot0;
+            for (int c = 0; c < 2; c++) {
+                const bool leaf = c ? leaf1 : leaf0;
+                const uint32_t cnt = leaf ? (c ? c1 : c0) : 0u;
+                const float4 *pts = T.points + ((c ? r1 : r0) & ~PC_REF_LEAF);
 #pragma unroll
                 for (int i = 0; i < PC_LEAF; i++) {
-                    const float4 p = __ldg(pts + i);
-                    const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
-                    const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                    if (d <= thr && slot0 + i < T.n_points)      // the tail of the last leaf repeats the last point
-                        hit[i] = pc_exact_d2(p.x, p.y, p.z, qxd, qyd, qzd) <= r2;
-                    id[i] = __float_as_int(p.w);
+                    hit[c * PC_LEAF + i] = false; id[c * PC_LEAF + i] = 0;
+                    if ((uint32_t)i < cnt) {
+                        const float4 p = __ldg(pts + i);
+                        const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+                        const float d = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        if (d <= thr) hit[c * PC_LEAF + i] = pc_exact_d2(p.x, p.y, p.z, qxd, qyd, qzd) <= r2;
+                        id[c * PC_LEAF + i] = __float_as_int(p.w);
+                    }
                 }
             }
 #pragma unroll
-            for (int i = 0; i < PC_LEAF; i++) {
+            for (int i = 0; i < 2 * PC_LEAF; i++) {
                 const uint32_t mask = __ballot_sync(PC_FULL_MASK, hit[i]);
                 if (FILL && hit[i]) out_idx[begin + total + __popc(mask & lt)] = id[i];
                 total += __popc(mask);
             }
         }
-        const uint32_t m0 = __ballot_sync(PC_FULL_MASK, in0), m1 = __ballot_sync(PC_FULL_MASK, in1);
+        const uint32_t m0 = __ballot_sync(PC_FULL_MASK, push0), m1 = __ballot_sync(PC_FULL_MASK, push1);
         const int n0 = __popc(m0);
-        if (in0) F[size + __popc(m0 & lt)] = 2u * node;
-        if (in1) F[size + n0 + __popc(m1 & lt)] = 2u * node + 1u;
+        if (push0) F[size + __popc(m0 & lt)] = r0;
+        if (push1) F[size + n0 + __popc(m1 & lt)] = r1;
         size += n0 + __popc(m1);
         __syncwarp();
     }
@@ -225,6 +160,7 @@ pc_range_coop_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstr
     if (want <= PC_RCOOP_CAP) {
         int N = 32;
         while (N < want) N <<= 1;
+        __syncwarp();
         for (int i = lane; i < N; i += 32) F[i] = i < want ? (uint32_t)out_idx[begin + i] : 0x7fffffffu;
         __syncwarp();
         for (int k2 = 2; k2 <= N; k2 <<= 1) {

@@ -6,8 +6,8 @@ safeRegionRrtStar::radiusSearch (Planner/src/corridor_finder.cpp:113-133), ``cle
 checkSafeTrajectory (Planner/src/sim_planning_demo.cpp:729-781).
 
 Inputs are numpy arrays (PC_HOST: results come back as numpy arrays, the call returns when they are
-resident) or torch CUDA tensors (PC_DEVICE: results are torch tensors, the call is asynchronous on
-the handle's stream).  All computation happens in libpcindex.so; nothing here computes distances.
+resident) or torch CUDA tensors (PC_DEVICE: results are torch tensors; the call is asynchronous when the
+handle was created on torch's stream, and blocking when it has a private stream).  All computation happens in libpcindex.so; nothing here computes distances.
 """
 from __future__ import annotations
 
@@ -28,6 +28,9 @@ class PointCloudIndex:
         ``torch.cuda.current_stream().cuda_stream`` to order the calls with torch work."""
         self._L = L.load()
         h = C.c_void_p()
+        # torch tensors are produced and consumed on torch's current stream; a handle with a PRIVATE stream (stream=None) is
+        # not ordered with it, so torch-mode calls on such a handle synchronise on both sides (see _torch_fence)
+        self._private_stream = stream is None
         if stream is not None and int(stream) == 0:
             stream = 1      # cudaStreamLegacy: NULL means "create a private stream" in the C ABI
         rc = self._L.pc_index_create(C.byref(h), int(device), int(max_points), C.c_void_p(stream or 0))
@@ -70,6 +73,16 @@ class PointCloudIndex:
             raise TypeError(f"{name}: expected float32 (n, 3|4)")
         return C.c_void_p(a.ctypes.data), a.shape[0], a.shape[1], L.PC_HOST, a, False
 
+    def _torch_fence(self, torch_mode, after=False):
+        """Handle created without a stream + torch tensors: wait for torch's stream before the call (inputs, output pre-fills)
+        and for the handle's stream after it (results), so that correctness never depends on the caller passing a stream."""
+        if torch_mode and self._private_stream:
+            if after:
+                self.sync()
+            else:
+                import torch
+                torch.cuda.current_stream(self.device).synchronize()
+
     NOT_MINE_IDX = -2 ** 31        # shard mode: pre-fill of entries owned by other ranks (float outputs: NaN)
 
     def _out(self, m, dtype, torch_mode, ref=None):
@@ -86,8 +99,10 @@ class PointCloudIndex:
     # ---- index ------------------------------------------------------------------------------------
     def build(self, xyz):
         """Rebuild the index from scratch (kd_clear + n x kd_insert3); point i keeps identity i."""
-        p, n, stride, space, keep, _ = self._rows(xyz, "xyz")
+        p, n, stride, space, keep, tm = self._rows(xyz, "xyz")
+        self._torch_fence(tm)
         self._check(self._L.pc_index_build(self._h, p, n, stride, space))
+        self._torch_fence(tm, after=True)
         self._cloud_keepalive = keep
         return self
 
@@ -116,6 +131,10 @@ class PointCloudIndex:
         self._check(self._L.pc_batch_shard(self._h, int(rank), int(n_ranks)))
         self._shard_n = int(n_ranks)
 
+    def set_radius_arith(self, mode):
+        """PC_ARITH_FP64 (default) or PC_ARITH_PCL_FLOAT: arithmetic of the radiusSearch epilogue (pc_index.h)."""
+        self._check(self._L.pc_index_set_radius_arith(self._h, int(mode)))
+
     def profile(self, on=True):
         self._check(self._L.pc_profile_enable(self._h, 1 if on else 0))
 
@@ -131,7 +150,9 @@ class PointCloudIndex:
         p, m, stride, space, keep, tm = self._rows(q, "q")
         idx, pi = self._out(m, np.int32, tm, keep) if want_idx else (None, C.c_void_p(0))
         d2, pd = self._out(m, np.float32, tm, keep) if want_d2 else (None, C.c_void_p(0))
+        self._torch_fence(tm)
         self._check(self._L.pc_nearest_batch(self._h, p, m, stride, space, flags, pi, pd))
+        self._torch_fence(tm, after=True)
         return idx, d2
 
     def radius(self, q, params: L.PcRadiusParams, flags=L.PC_RADIUS_BOUNDED, want_idx=False):
@@ -139,7 +160,9 @@ class PointCloudIndex:
         p, m, stride, space, keep, tm = self._rows(q, "q")
         r, pr = self._out(m, np.float32, tm, keep)
         idx, pi = self._out(m, np.int32, tm, keep) if want_idx else (None, C.c_void_p(0))
+        self._torch_fence(tm)
         self._check(self._L.pc_radius_batch(self._h, p, m, stride, space, flags, C.byref(params), pr, pi))
+        self._torch_fence(tm, after=True)
         return (r, idx) if want_idx else r
 
     def radius_async(self, q_pinned, out_pinned, params: L.PcRadiusParams, flags=L.PC_RADIUS_BOUNDED):

@@ -199,14 +199,14 @@ def test_one_million_points_properties(ix):
 
 
 def test_five_million_points_64bit_keys():
-    """C4-sized cloud: above 4 Mi points the build switches to 63-bit Morton keys (uint64 radix sort, 5 passes)."""
+    """C4-sized cloud: above 4 Mi points the build switches to 63-bit Hilbert keys (uint64 radix sort, 5 passes)."""
     pts, half = synth.forest_cloud(5_000_000, seed=2, variant="J", return_half=True)
     h = PointCloudIndex(max_points=len(pts), device=0)
     try:
         h.build(pts)
         assert h.size == len(pts)
         v = h.view()
-        assert v.n_leaves == (len(pts) + 3) // 4 and v.leaf_base >= v.n_leaves
+        assert v.n_nodes == len(pts) - 1 and v.root == 0 and v.records and v.points == v.records + 64 * v.n_nodes
         assert np.allclose(np.array(v.bbox_lo[:]), pts.min(0)) and np.allclose(np.array(v.bbox_hi[:]), pts.max(0))
         sel = np.random.default_rng(1).permutation(len(pts))[:400_000]
         idx, d2 = h.nearest(pts[sel])
