@@ -31,9 +31,33 @@ CLOUD_SEED = 1
 PARAMS = dict(search_margin=0.25, max_radius=1.5, sample_range=30.0)   # clean_demo.launch:31-34
 BYTES_PER_QUERY = 16            # algorithmic: 12 B query (xyz float32) in + 4 B radius out
 FRAME_POINTS = 300_000          # C3 frame for the build-ms metric
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on the default workload, from the
-# `ncu --set full` capture summarised in profiles/r1_full_final.txt (547.9 MB + 104.1 MB); re-measure when the kernel changes
-NCU_TRAFFIC_BYTES = {10_000_000: 653_199_616}
+# ncu figures of ONE launch of the dominant kernel on the default workload (dram bytes, warp instructions) live in
+# profiles/ncu_dominant_kernel.json, written by `scripts/ncu_summary.py traffic` from an `ncu --set full` capture together
+# with a hash of the kernel sources it was taken on; figures taken on other sources are reported as stale (null)
+NCU_FILE = os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")
+KERNEL_SOURCES = ["common.cuh", "lbvh.cuh", "build_kernels.cuh", "query_kernels.cuh", "radix_sort.cuh"]
+
+
+def kernel_source_hash():
+    import hashlib
+    h = hashlib.sha1()
+    for f in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "pointcloudtraj_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def ncu_figures(queries):
+    """-> (dict or None, note): the committed ncu figures if they were captured on the current kernel sources and batch size."""
+    try:
+        d = json.load(open(NCU_FILE))
+    except Exception:
+        return None, "profiles/ncu_dominant_kernel.json missing"
+    if d.get("source_sha1") != kernel_source_hash():
+        return None, f"stale: captured at commit {d.get('commit')} on other kernel sources"
+    if int(d.get("queries", 0)) != int(queries):
+        return None, f"captured for {d.get('queries')} queries per launch"
+    return d, f"profiles/{d.get('summary_file')} (ncu --set full at commit {d.get('commit')}, per launch)"
 
 
 def parse():
@@ -49,15 +73,21 @@ def parse():
     return ap.parse_args()
 
 
-def workload_config(args, extra=None):
-    cfg = {"workload": "C2: 1M-point synthetic forest map (jittered lattice, seed 1), radiusSearch batches of "
-                       f"{args.queries} uniform in-box RRT* samples per GPU, clean_demo params "
-                       "(search_margin 0.25, max_radius 1.5, sample_range 30)",
-           "points": N_POINTS, "queries_per_step_per_gpu": args.queries,
-           "l2_policy": "inputs+outputs per step (16 B/query x 1e7 = 160 MB) exceed the 126 MB L2"}
-    if extra:
-        cfg.update(extra)
-    return cfg
+def workload_config(args):
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": "C2: 1M-point synthetic forest map (jittered lattice, seed 1), radiusSearch batches of "
+                        f"{args.queries} uniform in-box RRT* samples per GPU, clean_demo params "
+                        "(search_margin 0.25, max_radius 1.5, sample_range 30)",
+            "points": N_POINTS, "queries_per_step_per_gpu": args.queries,
+            "l2_policy": "inputs+outputs per step (16 B/query x 1e7 = 160 MB) exceed the 126 MB L2"}
+
+
+def host_threads():
+    """All the host threads this process may use -- NOT OMP_NUM_THREADS, which torch.distributed.run sets to 1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def make_cloud():
@@ -114,7 +144,7 @@ def cpu_radius(tree, kind, q, start):
     import oracle
     P = oracle.RadiusParams.make(start=start, **PARAMS)
     if kind == "reference":
-        return tree.radius_batch(P, q, nthreads=0)
+        return tree.radius_batch(P, q, nthreads=host_threads())
     return tree.radius_batch(P, q)[0]
 
 
@@ -127,7 +157,7 @@ def cpu_baseline(pts, q, start, sample):
     t0 = time.perf_counter()
     r = cpu_radius(tree, kind, qs, start)
     dt = time.perf_counter() - t0
-    cores = tree.max_threads() if kind == "reference" else 1
+    cores = host_threads() if kind == "reference" else 1
     return {"value": len(qs) / dt, "unit": UNIT, "cores": cores, "kind": kind,
             "sample": f"first {len(qs)} queries of the step batch on the same 1M-point cloud "
                       f"(kd_insert3 build {t_build * 1e3:.0f} ms single-threaded, not included)",
@@ -142,7 +172,9 @@ def run_reference(args):
     pts, half = make_cloud()
     start = (0.0, 0.0, 2.0)
     tree, kind = cpu_reference_tree(pts)
-    cores = tree.max_threads() if kind == "reference" else 1
+    cores = host_threads() if kind == "reference" else 1
+    if kind == "reference" and (os.cpu_count() or 1) > 1 and cores <= 1:
+        print("[bench] WARNING: the reference arm sees one host thread (restricted CPU affinity)", file=sys.stderr)
     m = args.ref_sample
     qs = [synth.rrt_queries(m, half, seed=100 + s) for s in range(args.warmup + args.steps)]
     for s in range(args.warmup):
@@ -155,8 +187,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, {"reference_step_sample": m}),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind,
+            "config": workload_config(args),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "reference_step_sample": m,
+                             "host_cpus": os.cpu_count(), "omp_num_threads_env_ignored": os.environ.get("OMP_NUM_THREADS"),
                              "sample": f"{m} queries per step (bounded sample of the {args.queries}-query batch), "
                                        "kd_nearest3 + radiusSearch epilogue, OpenMP over queries"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -368,6 +401,77 @@ def run_b200(args):
     same = all(bool((r.to(dev) == t_r).all().item()) for r in r_pins)
     clocks = sampler.stop() if sampler else None     # sampled across the device-timed and the end-to-end regions
 
+    # host roof of the buffer API: what the host side of the PCIe fabric delivers when every rank moves one step's bytes
+    # (12 B/query in, 4 B/query out, pinned memory, both directions at once) with NO kernel in between
+    cp_in, cp_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    d_q2, d_r2 = torch.empty_like(t_q), torch.empty_like(t_r)
+
+    def copy_step():
+        with torch.cuda.stream(cp_in):
+            d_q2.copy_(q_pin, non_blocking=True)
+        with torch.cuda.stream(cp_out):
+            r_pins[0].copy_(d_r2, non_blocking=True)
+
+    for _ in range(2):
+        copy_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        copy_step()
+    torch.cuda.synchronize()
+    host_roof_s = max_over_ranks(time.perf_counter() - t0)
+    host_roof_gbs = world * 16 * M * e2e_steps / host_roof_s / 1e9
+    del d_q2, d_r2
+
+    # strong scaling (N > 1): ONE batch of N x M queries, the same on every rank, split with pc_batch_shard -- each rank
+    # answers the queries whose curve cell hashes to it -- against the time rank 0 needs for the whole batch alone
+    strong = None
+    if world > 1:
+        Mt = M * world
+        q_all = torch.empty((Mt, 3), dtype=torch.float32, device=dev)
+        if rank == 0:
+            for r in range(world):
+                q_all[r * M:(r + 1) * M].copy_(torch.from_numpy(synth.rrt_queries(M, half, seed=1000 + r)), non_blocking=False)
+        dist.broadcast(q_all, 0)
+        r_all = torch.full((Mt,), float("nan"), dtype=torch.float32, device=dev)
+
+        def step_big():
+            rc = lib.pc_radius_batch(ix._h, C.c_void_p(q_all.data_ptr()), Mt, 3, PC_DEVICE, 0, C.byref(P), C.c_void_p(r_all.data_ptr()), None)
+            if rc != 0:
+                raise RuntimeError(lib.pc_last_error(ix._h).decode())
+
+        def timed(n_rep, active):
+            for _ in range(2):
+                if active:
+                    step_big()
+            barrier()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for _ in range(n_rep):
+                if active:
+                    step_big()
+            b_.record()
+            torch.cuda.synchronize()
+            return max_over_ranks(a_.elapsed_time(b_) * 1e-3) / n_rep
+
+        t1 = timed(5, rank == 0)                       # rank 0 alone, the others idle
+        ref_all = r_all.clone()
+        dist.broadcast(ref_all, 0)
+        ix.batch_shard(rank, world)
+        r_all.fill_(float("nan"))
+        tn = timed(5, True)
+        ix.batch_shard(0, 1)
+        # every query answered by exactly one rank (early-outs by all), and with rank 0's value
+        mine = ~torch.isnan(r_all)
+        cover = mine.to(torch.int32)
+        dist.all_reduce(cover)
+        okv = torch.tensor([int(bool((r_all[mine] == ref_all[mine]).all().item()))], device=dev)
+        dist.all_reduce(okv, op=dist.ReduceOp.MIN)
+        strong = {"total_queries": Mt, "one_gpu_ms": t1 * 1e3, "n_gpu_ms": tn * 1e3, "value": Mt / tn, "unit": UNIT,
+                  "efficiency_vs_one_gpu": t1 / (world * tn), "split": "pc_batch_shard (hashed curve cells), same batch on every rank",
+                  "every_query_answered": bool((cover >= 1).all().item()), "matches_one_gpu": bool(okv.item())}
+        del q_all, r_all, ref_all
+
     # C3: index rebuild of a 300k-point frame (ms/frame), device-resident frame (rank 0 holds the cloud)
     fms = [0.0] * 12
     if rank == 0:
@@ -388,30 +492,43 @@ def run_b200(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         k_ms = float(np.mean(search_ms))
         achieved = BYTES_PER_QUERY * M / (k_ms * 1e-3) / 1e9
+        ncu, ncu_note = ncu_figures(M)
+        sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+        sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+        issue_capacity = sm_count * 4 * sm_mhz * 1e6 * k_ms * 1e-3          # warp instructions the 4 schedulers per SM can issue
+        roofline_issue = None
+        if ncu and ncu.get("inst_executed"):
+            roofline_issue = {"bound": "issue", "achieved": ncu["inst_executed"], "peak": issue_capacity, "unit": "warp instructions per launch",
+                              "frac": ncu["inst_executed"] / issue_capacity, "source": ncu_note,
+                              "how": "smsp__inst_executed.sum of one launch (ncu) / (SMs x 4 schedulers x SM clock x live kernel time)"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": workload_config(args, {"sensing_range_early_out_fraction": early_frac,
-                                                 "note": "the map (+-36.6 m) is larger than the 31.5 m sensing range around start, so this share of the "
-                                                         "uniform samples takes radiusSearch's early-out (corridor_finder.cpp:115-116), as in the reference"}),
+                "config": workload_config(args),
+                "workload_stats": {"sensing_range_early_out_fraction": early_frac,
+                                   "note": "the map (+-36.6 m) is larger than the 31.5 m sensing range around start, so this share of the "
+                                           "uniform samples takes radiusSearch's early-out (corridor_finder.cpp:115-116), as in the reference"},
                 "device_mode": "PC_DEVICE_ASYNC: steps rotate over 3 internal streams (ordering pass of step k+1 overlaps the search of step k)",
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": NCU_TRAFFIC_BYTES.get(M), "traffic_source": "profiles/r1_full_final.txt (ncu --set full, bytes per launch)",
-                             "kernel": "pc_query_packet2_kernel<RADIUS> (64-query warp packets)", "kernel_ms": k_ms,
+                             "traffic": (ncu or {}).get("dram_bytes"), "traffic_source": ncu_note,
+                             "kernel": "pc_query_packet_kernel<RADIUS, 2> (64-query warp packets over the prefix-split tree)", "kernel_ms": k_ms,
                              "batch_order_ms": float(np.mean(order_ms)),
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                              "algorithmic_bytes_per_query": BYTES_PER_QUERY,
-                             "limiter": "not HBM: the 32 MB index is L2-resident; ncu (profiles/r1_full_final.txt) shows issue slots "
-                                        "77 % busy, L1/TEX 58 %, DRAM 6 % -- the kernel is instruction-issue bound"},
+                             "limiter": "not HBM: the index is L2-resident and the kernel is instruction-issue bound -- see roofline_issue"},
+                "roofline_issue": roofline_issue,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 12 * M, "d2h_bytes_per_step": 4 * M,
                         "steps": e2e_steps, "matches_device_result": same,
-                        "mode": "PC_HOST_ASYNC, 3 batches in flight, one wait at the end", "blocking_call_value": e2e_blocking},
+                        "mode": "PC_HOST_ASYNC, 3 batches in flight, one wait at the end", "blocking_call_value": e2e_blocking,
+                        "host_roof_gbs": host_roof_gbs, "host_roof_queries_per_s": host_roof_gbs * 1e9 / 16,
+                        "frac_of_host_roof": e2e_val / (host_roof_gbs * 1e9 / 16),
+                        "host_roof_how": "all ranks copy one step's 12 B/query in and 4 B/query out from / to pinned memory at once, no kernels"},
                 "gpu_launches": launches, "clocks": clocks,
                 "index_build_ms_per_frame": {"points": FRAME_POINTS, "median": float(np.median(fms[2:])), "min": float(min(fms))},
                 "all_queries_searched": {"value": all_searched_qps, "unit": UNIT, "note": "per GPU, same batch with sample_range = -1 (no early-outs), one stream"},
                 "index_build_ms_1M": float(np.median(build_ms[1:])), "index_broadcast_ms": bcast_ms,
                 "host_cpu_binding": (f"{len(numa_cpus)} CPUs next to the GPU (NVML affinity)" if numa_cpus else None),
-                "replicas_match_root": replica_ok}
+                "replicas_match_root": replica_ok, "strong": strong}
         if not args.no_cpu_baseline and world == 1:
             cb, r_cpu = cpu_baseline(pts, q_host, start, args.cpu_sample)
             cb["gpu_matches_cpu_sample"] = bool((r_cpu.astype(np.float32) == t_r[: len(r_cpu)].cpu().numpy()).all())

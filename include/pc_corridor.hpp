@@ -49,6 +49,8 @@ public:
         params_.max_radius = max_radius_;
         params_.sample_range = sample_range_;
     }
+    // PC_ARITH_FP64 (default) or PC_ARITH_PCL_FLOAT: the arithmetic of the radius epilogue (pc_index.h)
+    int setRadiusArith(int mode) { return pc_index_set_radius_arith(ix_, mode); }
     void setStartPt(const double startPt[3]) { for (int a = 0; a < 3; a++) params_.start[a] = startPt[a]; }
     void setPt(const double startPt[3], double local_range) { setStartPt(startPt); params_.sample_range = local_range; }
 

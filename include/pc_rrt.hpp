@@ -409,6 +409,7 @@ public:
     std::vector<double> radius;
     bool path_exist_status = true;
     size_t nodeCount() const { return node_list_.size(); }
+    const std::vector<RrtNode *> &nodeList() const { return node_list_; }      // getTree (corridor_finder.h:136-139)
     int64_t cloud_queries = 0, radius_calls = 0, node_tree_calls = 0;
 
     // optional: batched nearest-vertex provider for the snapshot phase of expandBatched / refineBatched.

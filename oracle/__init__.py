@@ -337,7 +337,7 @@ def planner_lib():
         L.rp_check_traj_pt_col.argtypes = [_f64p]
         L.rp_bezier_pos.argtypes = [C.c_int, _f64p, d, _f64p]
         L.rp_check_safe_trajectory.argtypes = [C.c_int, _i32p, _f64p, _f64p, C.c_longlong, d, d, _f32p, C.c_longlong,
-                                               C.POINTER(C.c_longlong)]
+                                               C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_float)]
         _planner = L
     return _planner
 
@@ -411,12 +411,15 @@ class PlannerReference:
         return out
 
     def check_safe_trajectory(self, order, T, coef, t_now, stop_time, cap=8192):
-        """Returns (collides, pts float32 (k, 3)): the reference's return value and the sample points it visited."""
+        """Returns (collides, pts float32 (k, 3), k): the reference's return value and the sample points it visited.
+        self.last_searched / self.last_min_d2: how many of them reached the cloud query, and the smallest float32 squared
+        distance those saw (logged by the stand-in pcl::search::KdTree)."""
         order = np.ascontiguousarray(order, np.int32); T = np.ascontiguousarray(T, np.float64)
         coef = np.ascontiguousarray(coef, np.float64)
         pts = np.zeros((cap, 3), np.float32)
-        n = C.c_longlong(0)
+        n, ns, md = C.c_longlong(0), C.c_longlong(0), C.c_float(0)
         hit = self._L.rp_check_safe_trajectory(order.shape[0], _ptr(order, _i32p), _ptr(T, _f64p), _ptr(coef, _f64p),
                                                coef.shape[1] if coef.ndim == 2 else 0, float(t_now), float(stop_time),
-                                               _ptr(pts, _f32p), cap, C.byref(n))
+                                               _ptr(pts, _f32p), cap, C.byref(n), C.byref(ns), C.byref(md))
+        self.last_searched, self.last_min_d2 = int(ns.value), np.float32(md.value)
         return bool(hit), pts[: min(n.value, cap)].copy(), int(n.value)

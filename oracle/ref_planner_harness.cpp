@@ -160,9 +160,14 @@ void rp_bezier_pos(int order, const double *coef_row, double u, double *out3)
 // checkSafeTrajectory (sim_planning_demo.cpp:729-781) on one piecewise trajectory.  coef: row-major, row i = segment i's
 // [x|y|z] blocks, ld doubles per row.  t_now = (odom stamp - trajectory start).  Returns the reference's return value
 // (1: a sample collides); the float32 sample points it visited (up to and including the colliding one) go to out_pts.
+// *n_searched = how many of those samples reached the cloud query (the others took radiusSearch's early-outs);
+// *min_d2 = the smallest squared distance (float32, as PCL's interface returns it) any of them saw, +inf if none.
 int rp_check_safe_trajectory(int n_seg, const int *order, const double *T, const double *coef, long long ld,
-                             double t_now, double stop_time, float *out_pts, long long cap, long long *n_pts)
+                             double t_now, double stop_time, float *out_pts, long long cap, long long *n_pts,
+                             long long *n_searched, float *min_d2)
 {
+    pcl::search::shim_stats().log_d2.clear();
+    pcl::search::shim_stats().log_on = true;
     _is_traj_exist = true;
     _segment_num = n_seg;
     _poly_orderList.assign(order, order + n_seg);
@@ -176,6 +181,13 @@ int rp_check_safe_trajectory(int n_seg, const int *order, const double *T, const
     _odom.header.stamp = ros::Time(t_now);
     _stop_time = stop_time;
     const bool hit = checkSafeTrajectory(stop_time);
+    pcl::search::shim_stats().log_on = false;
+    if (n_searched) *n_searched = (long long)pcl::search::shim_stats().log_d2.size();
+    if (min_d2) {
+        float m = INFINITY;
+        for (float v : pcl::search::shim_stats().log_d2) m = v < m ? v : m;
+        *min_d2 = m;
+    }
     const long long n = (long long)traj_stop_pts_pcd.points.size();
     for (long long k = 0; k < n && k < cap; k++) {
         out_pts[3 * k] = traj_stop_pts_pcd.points[(size_t)k].x;

@@ -4,7 +4,7 @@
 #include "../point_cloud.h"
 namespace pcl { namespace search {
 // counters the harness reads (number of cloud queries issued by the planner code)
-struct ShimStats { long long queries = 0, builds = 0; };
+struct ShimStats { long long queries = 0, builds = 0; bool log_on = false; std::vector<float> log_d2; };
 inline ShimStats &shim_stats() { static ShimStats s; return s; }
 
 template <typename PointT>
@@ -51,6 +51,7 @@ public:
         d2 += dx * dx; d2 += dy * dy; d2 += dz * dz;
         k_indices.push_back((int)((size_t)data - 1));
         k_sqr_distances.push_back((float)d2);
+        if (shim_stats().log_on) shim_stats().log_d2.push_back((float)d2);
         return 1;
     }
 private:

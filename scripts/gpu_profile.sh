@@ -2,7 +2,7 @@
 # Run on the GPU box (gpurun -- 'bash scripts/gpu_profile.sh TAG'): plain bench run, then the ncu launch list of the
 # same command, then one --set full capture of the dominant kernel.  Outputs land in gpurun_out/.
 TAG=${1:-rX}
-KREGEX=${2:-pc_query_packet2_kernel}
+KREGEX=${2:-pc_query_packet_kernel}
 CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
 mkdir -p gpurun_out
 $CMD > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err || { echo "plain run failed"; tail -5 gpurun_out/${TAG}_plain.err; exit 1; }

@@ -74,5 +74,28 @@ def full(path):
         print()
 
 
+def traffic(path, summary_file="", queries="10000000"):
+    """Write profiles/ncu_dominant_kernel.json (read by bench.py): dram bytes and warp instructions of one launch of the
+    LAST kernel in the capture, with the hash of the kernel sources and the commit it was taken on."""
+    import json
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, r = rows[0], rows[-1]
+    val = lambda m: float(r[hdr.index(m)].replace(",", ""))
+    units = rows[1]
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    rd = val("dram__bytes_read.sum") * scale[units[hdr.index("dram__bytes_read.sum")]]
+    wr = val("dram__bytes_write.sum") * scale[units[hdr.index("dram__bytes_write.sum")]]
+    commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    d = {"kernel": r[hdr.index("Kernel Name")], "queries": int(queries), "dram_bytes_read": rd, "dram_bytes_write": wr,
+         "dram_bytes": rd + wr, "inst_executed": val("smsp__inst_executed.sum"), "duration_ns_under_ncu": val("gpu__time_duration.sum"),
+         "source_sha1": bench.kernel_source_hash(), "commit": commit, "summary_file": summary_file}
+    json.dump(d, open(bench.NCU_FILE, "w"), indent=1)
+    print(json.dumps(d, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])

@@ -119,20 +119,12 @@ def test_clearance_vs_oracle(ix, horizon, n_traj):
     r_mr = np.array([r["min_radius"] for r in ref])
     assert (ns == r_ns).all()                                     # the repeated-addition time walk is reproduced exactly
     assert ns.max() >= min(int(horizon / 0.02) - 1, 400) and (r_fh >= 0).any() and (r_fh < 0).any()
-    # tolerance (DESIGN.md "Clearance tolerance"): the sampled position may differ by one float32 ulp where libm's pow
-    # and the multiplication-built power differ; 1e-6 relative on the obstacle distance
+    # exact: the kernel's powers are the correctly rounded u^j (double-double), like libm's pow in the oracle, so the float32
+    # sample positions, every radius and therefore the first colliding sample are identical (DESIGN.md "Clearance")
     fin = np.isfinite(r_mr)                                         # trajectories without samples report +inf
     assert (np.isinf(mr) == ~fin).all()
-    tol = 1e-6 * (np.abs(r_mr[fin]) + 0.25)
-    assert (np.abs(mr[fin].astype(np.float64) - r_mr[fin]) <= tol + 1e-7).all()
-    exact = mr == r_mr.astype(np.float32)
-    assert exact.mean() > 0.99
-    # the first colliding sample is identical unless a sample sits within tolerance of the collision threshold
-    differ = np.nonzero(fh != r_fh)[0]
-    for t in differ:
-        rad = ref[t]["radius"]
-        assert np.abs(rad).min() < 1e-6
-    assert differ.size <= 1
+    assert (mr[fin] == r_mr[fin].astype(np.float32)).all()
+    assert (fh == r_fh).all()
 
 
 def test_clearance_edge_cases(ix):
