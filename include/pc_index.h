@@ -181,12 +181,13 @@ void pc_comm_destroy(pc_comm *c);
  * handle's stream.  After it returns every rank answers queries against the same index. */
 int  pc_index_broadcast(pc_index *ix, pc_comm *c, int root);
 /* Spatial sharding of query batches: after pc_batch_shard(ix, rank, n_ranks) every pc_nearest_batch / pc_radius_batch on
- * this handle expects the SAME full batch on every rank and answers only this rank's share: the cells of the Hilbert curve
- * (at a level chosen so that a cell holds a few hundred queries) are dealt to the ranks by a hash of the cell index.  Entries of other ranks' queries are left
- * untouched in the output arrays (pre-fill them, e.g. out_idx with INT32_MIN, to tell them apart); sensing-range
- * early-outs of pc_radius_batch are written by every rank.  A rank's share is as dense in space as the whole batch and
- * spread over the whole map, which keeps the search efficient and balanced when one batch is split over many GPUs.
- * n_ranks = 1 switches back. */
+ * this handle expects the SAME full batch on every rank and answers only this rank's share: the cubic cells of the index's
+ * curve frame (at a level chosen on the device from the index's bounding box and the batch size, so that a cell holds a few
+ * hundred queries and all ranks agree) are dealt to the ranks by a hash of the cell coordinates.  Every query is answered by
+ * exactly one rank; entries of other ranks' queries are left untouched in the output arrays (pre-fill them, e.g. out_idx
+ * with INT32_MIN, to tell them apart).  A rank's share is as dense in space as the whole batch and spread over the whole
+ * map, which keeps the search efficient and balanced when one batch is split over many GPUs.  n_ranks = 1 switches back.
+ * Needs the ordering pass (PC_EINVAL when PC_SORT_BITS=0 disabled it). */
 int  pc_batch_shard(pc_index *ix, int rank, int n_ranks);
 /* contiguous slice [begin, end) of m units owned by `rank` (queries or trajectories) */
 void pc_shard_range(int64_t m, int rank, int n_ranks, int64_t *begin, int64_t *end);

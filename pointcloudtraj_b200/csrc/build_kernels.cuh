@@ -84,8 +84,15 @@ __device__ __forceinline__ pc_frame pc_make_frame(const uint32_t *bbox, int bits
 template <typename KeyT>
 __global__ void __launch_bounds__(PC_BUILD_THREADS)
 pc_keygen_kernel(const float *__restrict__ xyz, int64_t n, int stride, const uint32_t *__restrict__ bbox, int bits,
-                 KeyT *__restrict__ keys, uint32_t *__restrict__ vals)
+                 KeyT *__restrict__ keys, uint32_t *__restrict__ vals, uint32_t *__restrict__ ghist, int hist_passes)
 {
+    // ghist (nullable): digit histograms of all hist_passes sort passes (onesweep path of radix_sort.cuh), counted while the
+    // key is in a register
+    __shared__ uint32_t s_hist[8][256];
+    if (ghist) {
+        for (int j = threadIdx.x; j < hist_passes * 256; j += PC_BUILD_THREADS) (&s_hist[0][0])[j] = 0;
+        __syncthreads();
+    }
     const pc_frame f = pc_make_frame(bbox, bits);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float *p = xyz + i * stride;
@@ -97,6 +104,17 @@ pc_keygen_kernel(const float *__restrict__ xyz, int64_t n, int stride, const uin
         else keys[i] = (KeyT)pc_morton63(p[0], p[1], p[2], f);
 #endif
         vals[i] = (uint32_t)i;
+        if (ghist) {
+            const KeyT k = keys[i];
+            for (int p = 0; p < hist_passes; p++) atomicAdd(&s_hist[p][(uint32_t)(k >> (8 * p)) & 255u], 1u);
+        }
+    }
+    if (ghist) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < hist_passes * 256; j += PC_BUILD_THREADS) {
+            const uint32_t c = (&s_hist[0][0])[j];
+            if (c) atomicAdd(&ghist[j], c);
+        }
     }
 }
 

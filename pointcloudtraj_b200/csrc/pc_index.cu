@@ -93,6 +93,8 @@ struct pc_index {
     int next_lane = 0;        // PC_HOST_ASYNC: lane of the next batch
     int shard_rank = 0, shard_n = 1;   // pc_batch_shard
     int radius_arith = PC_ARITH_FP64;  // pc_index_set_radius_arith
+    bool onesweep = true;              // PC_ONESWEEP=0: the three-kernel-per-pass radix sort (radix_sort.cuh)
+    int sort_items = 16;               // keys per thread of the batch-ordering sort (PC_SORT_ITEMS = 8 | 16)
     int coop_group = 0;                     // lanes per query of the small-batch kernel: 0 = by batch size, else 32 / 16 / 8 (PC_COOP_GROUP)
     int64_t coop_g32_max = 24576, coop_g16_max = 65536;  // batch sizes up to which 32 / 16 lanes per query are used (measured:
                                                          // narrower groups gain 5-12 % above these sizes, lose below)
@@ -136,6 +138,21 @@ static int pc_grow(pc_index *ix, T **ptr, int64_t *cap, int64_t want, int64_t mi
     return PC_OK;
 }
 
+// scratch words a sort of n pairs needs: the three-kernel path's tile histograms or the onesweep path's tickets + digit
+// histograms + per-pass tile status, whichever is larger
+static int64_t pc_sort_scratch_words(int64_t n, int items, int passes)
+{
+    const int64_t tiles = (n + (int64_t)RS_THREADS * items - 1) / ((int64_t)RS_THREADS * items);
+    const int64_t a = (int64_t)RS_RADIX * (tiles + 1), b = os_scratch_words(tiles, passes);
+    return a > b ? a : b;
+}
+
+// one sort front end: onesweep unless switched off (PC_ONESWEEP=0) or the status words would overflow
+template <typename KeyT, int ITEMS>
+static int pc_sort_pairs(pc_index *ix, KeyT *keys_a, uint32_t *vals_a, KeyT *keys_b, uint32_t *vals_b, int64_t n, int begin_bit, int end_bit,
+                         uint32_t *scratch, uint32_t *digit_total, cudaStream_t st, const unsigned long long *n_dev = nullptr,
+                         bool hist_done = false);
+
 static int pc_key_bits_per_axis(int64_t n)
 {
     // 10 bits per axis (30-bit keys, 4 radix passes) up to 4 Mi points; beyond that one more bit per axis for
@@ -165,7 +182,7 @@ static int pc_reserve_cloud(pc_index *ix, int64_t n)
     PC_CUDA(ix, cudaMalloc((void **)&ix->vals_b, (size_t)cap * sizeof(uint32_t)));
     ix->tree_cap = 4 * cap + cap + 2 * PC_LEAF;            // one 64-byte record and one point per point, + pad points
     PC_CUDA(ix, cudaMalloc((void **)&ix->tree, (size_t)ix->tree_cap * sizeof(float4)));
-    ix->hist_cap = (int64_t)RS_RADIX * (rs_num_tiles<8>(cap) + 1);
+    ix->hist_cap = pc_sort_scratch_words(cap, 8, ix->key_bytes == 8 ? 8 : 4);
     PC_CUDA(ix, cudaMalloc((void **)&ix->tile_hist, (size_t)ix->hist_cap * sizeof(uint32_t)));
     ix->cap = cap;
     return PC_OK;
@@ -194,6 +211,8 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         if (const char *v = getenv("PC_QUERY_KERNEL")) { ix->query_kernel_auto = false; int b_ = atoi(v); ix->query_kernel = (b_ == 1 || b_ == 4) ? b_ : 3; }
         if (const char *v = getenv("PC_SORT_BITS")) { ix->sort_bits_auto = false; int b_ = atoi(v); ix->sort_bits = b_ <= 0 ? 0 : (b_ <= 16 ? 16 : (b_ <= 24 ? 24 : 32)); }
         if (const char *v = getenv("PC_HOST_RAMP")) ix->host_ramp = atoi(v) != 0;
+        if (const char *v = getenv("PC_ONESWEEP")) ix->onesweep = atoi(v) != 0;
+        if (const char *v = getenv("PC_SORT_ITEMS")) ix->sort_items = atoi(v) == 8 ? 8 : 16;
         if (const char *v = getenv("PC_HOST_CHUNK_QUERIES")) { long long b_ = atoll(v); if (b_ >= 1024) ix->host_chunk = b_; }
         if (const char *v = getenv("PC_COOP_GROUP")) { int b_ = atoi(v); ix->coop_group = (b_ == 32 || b_ == 16 || b_ == 8) ? b_ : 0; }
         if (const char *v = getenv("PC_COOP_MAX_BATCH")) { long long b_ = atoll(v); ix->coop_max = b_ < 0 ? 0 : b_; }
@@ -328,13 +347,16 @@ static int pc_build_sorted(pc_index *ix, const float *src, int stride, int64_t n
     cudaStream_t st = ix->stream;
     const int grid = (int)((n + PC_BUILD_THREADS - 1) / PC_BUILD_THREADS < (int64_t)ix->sm_count * 8
                                ? (n + PC_BUILD_THREADS - 1) / PC_BUILD_THREADS : (int64_t)ix->sm_count * 8);
-    pc_keygen_kernel<KeyT><<<grid, PC_BUILD_THREADS, 0, st>>>(src, n, stride, ix->d_bbox, bits, (KeyT *)ix->keys_a, ix->vals_a);
-    ix->launches++;
-    PC_CHECK_LAUNCH(ix);
     int key_bits = 3 * bits;
     int end_bit = ((key_bits + 7) / 8) * 8;
-    int which = rs_sort_pairs<KeyT, ITEMS>((KeyT *)ix->keys_a, ix->vals_a, (KeyT *)ix->keys_b, ix->vals_b, n, 0, end_bit,
-                                           ix->tile_hist, ix->digit_total, st, &ix->launches);
+    const bool fused_hist = ix->onesweep && n < OS_MAX_N;      // the key kernel also counts the sort's digit histograms
+    if (fused_hist) os_clear(ix->tile_hist, n, ITEMS, end_bit / 8, st);
+    pc_keygen_kernel<KeyT><<<grid, PC_BUILD_THREADS, 0, st>>>(src, n, stride, ix->d_bbox, bits, (KeyT *)ix->keys_a, ix->vals_a,
+                                                              fused_hist ? os_ghist(ix->tile_hist) : nullptr, end_bit / 8);
+    ix->launches++;
+    PC_CHECK_LAUNCH(ix);
+    int which = pc_sort_pairs<KeyT, ITEMS>(ix, (KeyT *)ix->keys_a, ix->vals_a, (KeyT *)ix->keys_b, ix->vals_b, n, 0, end_bit,
+                                           ix->tile_hist, ix->digit_total, st, nullptr, fused_hist);
     PC_CHECK_LAUNCH(ix);
     *order_out = which ? ix->vals_b : ix->vals_a;
     *keys_out = which ? ix->keys_b : ix->keys_a;
@@ -418,6 +440,15 @@ extern "C" int pc_index_build(pc_index *ix, const float *xyz, int64_t n, int64_t
     return PC_OK;
 }
 
+template <typename KeyT, int ITEMS>
+static int pc_sort_pairs(pc_index *ix, KeyT *keys_a, uint32_t *vals_a, KeyT *keys_b, uint32_t *vals_b, int64_t n, int begin_bit, int end_bit,
+                         uint32_t *scratch, uint32_t *digit_total, cudaStream_t st, const unsigned long long *n_dev, bool hist_done)
+{
+    if (ix->onesweep && n < OS_MAX_N)
+        return os_sort_pairs<KeyT, ITEMS>(keys_a, vals_a, keys_b, vals_b, n, begin_bit, end_bit, scratch, ix->sm_count, st, &ix->launches, n_dev, hist_done);
+    return rs_sort_pairs<KeyT, ITEMS>(keys_a, vals_a, keys_b, vals_b, n, begin_bit, end_bit, scratch, digit_total, st, &ix->launches, n_dev);
+}
+
 extern "C" int pc_index_last_build_ms(pc_index *ix, float *ms)
 {
     if (!ix || !ms) return PC_EINVAL;
@@ -477,8 +508,7 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
         PC_CUDA(ix, cudaMalloc((void **)&L.vals_b, (size_t)c * 4));
         L.sort_cap = c;
     }
-    int64_t need_hist = (int64_t)RS_RADIX * (rs_num_tiles<16>(m) + 1);
-    int rc = pc_grow(ix, &L.tile_hist, &L.hist_cap, need_hist);
+    int rc = pc_grow(ix, &L.tile_hist, &L.hist_cap, pc_sort_scratch_words(m, 8, 4));
     if (rc != PC_OK) return rc;
     // sort_bits (16 / 24 / 32) = radix-sorted key width = how many of the top curve bits order the batch; queries that
     // need no search (sensing-range early-outs) are answered by the key kernel and never enter the sort
@@ -501,15 +531,19 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
     }
     const int drop = 30 - bits > 0 ? 30 - bits : 0;     // 24-bit sort = top 24 curve bits, 32-bit sort = all 30
     const int grid = (int)((m + 255) / 256);
+    const int items = ix->sort_items;
+    const bool fused_hist = ix->onesweep && m < OS_MAX_N;
+    uint32_t *gh = fused_hist ? os_ghist(L.tile_hist) : nullptr;
+    if (fused_hist) os_clear(L.tile_hist, m, items, bits / 8, L.os);
     if (A.kind == PC_Q_RADIUS)
-        pc_query_key_kernel<PC_KIND_RADIUS><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n);
+        pc_query_key_kernel<PC_KIND_RADIUS><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n, gh, bits / 8);
     else
-        pc_query_key_kernel<PC_KIND_NEAREST><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n);
+        pc_query_key_kernel<PC_KIND_NEAREST><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n, gh, bits / 8);
     ix->launches++;
     PC_CHECK_LAUNCH(ix);
     // only the L.counter[1] compacted entries (device-side count <= m) are sorted
-    int which = rs_sort_pairs<uint32_t, 16>(L.keys_a, L.vals_a, L.keys_b, L.vals_b, m, 0, bits, L.tile_hist, L.digit_total, L.os,
-                                            &ix->launches, L.counter + 1);
+    int which = items == 8 ? pc_sort_pairs<uint32_t, 8>(ix, L.keys_a, L.vals_a, L.keys_b, L.vals_b, m, 0, bits, L.tile_hist, L.digit_total, L.os, L.counter + 1, fused_hist)
+                           : pc_sort_pairs<uint32_t, 16>(ix, L.keys_a, L.vals_a, L.keys_b, L.vals_b, m, 0, bits, L.tile_hist, L.digit_total, L.os, L.counter + 1, fused_hist);
     PC_CHECK_LAUNCH(ix);
     *perm = which ? L.vals_b : L.vals_a;
     return PC_OK;
@@ -788,6 +822,11 @@ static int pc_make_radius_dev(pc_index *ix, const pc_radius_params *p, int flags
     R->sx = p->start[0]; R->sy = p->start[1]; R->sz = p->start[2];
     R->bounded = (flags & PC_RADIUS_FULL_NN) ? 0 : 1;
     R->pcl_float = ix->radius_arith == PC_ARITH_PCL_FLOAT ? 1 : 0;
+    {
+        const double T = p->sample_range + p->max_radius, t2 = T * T;
+        R->range_lo2 = T > 0.0 ? t2 * (1.0 - 1e-12) : -1.0;       // T <= 0: always the exact expression
+        R->range_hi2 = T > 0.0 ? t2 * (1.0 + 1e-12) : INFINITY;
+    }
     R->bound_thr = FLT_MAX;
     if (R->bounded) {
         // radius = min(sqrt(d2) - margin, max_radius): every d > max_radius + margin gives max_radius, so the search

@@ -15,6 +15,7 @@
 #pragma once
 #include "common.cuh"
 #include "build_kernels.cuh"
+#include "radix_sort.cuh"
 
 #define PC_QUERY_THREADS 128
 #define PC_STACK 96                            // tree depth <= key bits (<= 63) + position bits of coincident points (<= 31)
@@ -155,6 +156,7 @@ struct pc_radius_dev {
     float bound_thr;    // fp32 threshold on d2 for the bounded search (FLT_MAX when unbounded)
     int bounded;        // PC_RADIUS_BOUNDED: out_idx = -1 wherever the radius clamps to max_radius
     int pcl_float;      // PC_ARITH_PCL_FLOAT: d2 rounded to float32 and float32 sqrt, as PCL's interface makes the reference compute
+    double range_lo2, range_hi2;   // (sample_range + max_radius)^2 * (1 -+ 1e-12): outside this band the early-out needs no sqrt
 };
 
 // radiusSearch epilogue on a finished search (corridor_finder.cpp:131-132); nothing found inside the bound => clamp
@@ -175,6 +177,10 @@ __device__ __forceinline__ bool pc_radius_early_out(double px, double py, double
     if (R.sample_range < 0.0) return false;
     double dx = __dsub_rn(px, R.sx), dy = __dsub_rn(py, R.sy), dz = __dsub_rn(pz, R.sz);
     double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    // sqrt is monotone and correctly rounded (relative error < 2^-53), so away from the boundary the comparison of the
+    // squares decides; only a point within 1e-12 (relative) of the sensing sphere takes the reference's own expression
+    if (s > R.range_hi2) return true;
+    if (s < R.range_lo2) return false;
     return __dsqrt_rn(s) > __dadd_rn(R.sample_range, R.max_radius);
 }
 
@@ -443,7 +449,9 @@ pc_query_coop_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, in
 // here, once, coalesced: such queries get their result now; the others are compacted into (key, slot) pairs and
 // n_search counts them -- only those are sorted and searched.
 //
-// pc_batch_shard: the cells of the curve at a batch-dependent level are dealt to the ranks by a hash of the cell index.  A
+// pc_batch_shard: the cubic cells of the curve's frame at a batch-dependent level are dealt to the ranks by a hash of the
+// cell coordinates; a query that another rank owns is dropped right after its 12 bytes were read (no early-out test, no
+// curve key), so the pass over the full batch that every rank makes stays cheap.  A
 // rank's share is then as dense in space as the whole batch (dense packets) and spread over the whole map (equal cost per
 // rank).  The level is computed HERE, from the index's bounding box and the batch size only -- both identical on every
 // rank that holds a replica -- so all ranks agree on the owner of every query whatever the state of their host-side caches:
@@ -475,15 +483,22 @@ __global__ void __launch_bounds__(256)
 pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const uint32_t *__restrict__ bbox, int drop_bits,
                     pc_radius_dev R, int32_t *__restrict__ out_idx, float *__restrict__ out_f,
                     uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, unsigned long long *__restrict__ n_search,
-                    int shard_rank, int shard_n)
+                    int shard_rank, int shard_n, uint32_t *__restrict__ ghist, int hist_passes)
 {
+    // ghist (nullable): digit histograms of the hist_passes 8-bit passes that will sort the compacted keys (radix_sort.cuh,
+    // onesweep path) -- counted here, while the key is in a register, instead of by a separate pass over the keys
+    __shared__ uint32_t s_hist[4][RS_RADIX];
+    if (ghist) {
+        for (int j = threadIdx.x; j < hist_passes * RS_RADIX; j += 256) (&s_hist[0][0])[j] = 0;
+        __syncthreads();
+    }
     __shared__ uint32_t s_warp[8];
     __shared__ unsigned long long s_base;
     __shared__ int s_shard_shift;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (shard_n > 1) {
-        if (threadIdx.x == 0) s_shard_shift = 30 - 3 * pc_shard_level(bbox, m);
+        if (threadIdx.x == 0) s_shard_shift = 10 - pc_shard_level(bbox, m);      // cell coordinate bits dropped per axis
         __syncthreads();
     }
     bool search = false;
@@ -492,14 +507,21 @@ pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
         const pc_frame f = pc_make_frame(bbox, 10);
         const float *p = q + i * qstride;
         const float x = p[0], y = p[1], z = p[2];
+        const uint32_t cx = pc_cell_coord(x, f.lo[0], f.inv_cell, f.max_cell), cy = pc_cell_coord(y, f.lo[1], f.inv_cell, f.max_cell),
+                       cz = pc_cell_coord(z, f.lo[2], f.inv_cell, f.max_cell);
         search = true;
-        if (KIND == PC_KIND_RADIUS && pc_radius_early_out((double)x, (double)y, (double)z, R)) {
-            search = false;
-            pc_write_trivial<KIND>(R, (uint32_t)i, out_idx, out_f);
+        if (shard_n > 1) {
+            const int sh = s_shard_shift;
+            const uint32_t cell = ((cx >> sh) * 73856093u) ^ ((cy >> sh) * 19349663u) ^ ((cz >> sh) * 83492791u);
+            search = (int)(((cell * 2654435761u) >> 15) % (uint32_t)shard_n) == shard_rank;
         }
-        key = pc_hilbert30(x, y, z, f);
-        if (shard_n > 1 && (int)((((key >> s_shard_shift) * 2654435761u) >> 15) % (uint32_t)shard_n) != shard_rank) search = false;
-        key >>= drop_bits;
+        if (search) {
+            if (KIND == PC_KIND_RADIUS && pc_radius_early_out((double)x, (double)y, (double)z, R)) {
+                search = false;
+                pc_write_trivial<KIND>(R, (uint32_t)i, out_idx, out_f);
+            }
+            key = pc_hilbert30_cells(cx, cy, cz) >> drop_bits;
+        }
     }
     // compact the queries that still need a search: only those are sorted and searched.  One atomic per CTA; the slot a
     // query lands in depends on CTA scheduling, which changes the composition of packets but never a result.
@@ -516,5 +538,13 @@ pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
         const unsigned long long pos = s_base + s_warp[warp] + __popc(mask & pc_lanemask_lt());
         keys[pos] = key;
         vals[pos] = (uint32_t)i;
+        if (ghist) for (int p = 0; p < hist_passes; p++) atomicAdd(&s_hist[p][(key >> (8 * p)) & (RS_RADIX - 1)], 1u);
+    }
+    if (ghist) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < hist_passes * RS_RADIX; j += 256) {
+            const uint32_t c = (&s_hist[0][0])[j];
+            if (c) atomicAdd(&ghist[j], c);
+        }
     }
 }

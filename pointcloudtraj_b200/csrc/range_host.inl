@@ -116,7 +116,7 @@ extern "C" int pc_sphere_gather(pc_index *ix, const double center[3], double rad
         PC_CUDA(ix, cudaMalloc((void **)&L.vals_b, (size_t)want * 4));
         L.sort_cap = want;
     }
-    if ((rc = pc_grow(ix, &L.tile_hist, &L.hist_cap, (int64_t)RS_RADIX * (rs_num_tiles<16>(want > 0 ? want : 1) + 1))) != PC_OK) return rc;
+    if ((rc = pc_grow(ix, &L.tile_hist, &L.hist_cap, pc_sort_scratch_words(want > 0 ? want : 1, 16, 4))) != PC_OK) return rc;
     const float cx = (float)center[0], cy = (float)center[1], cz = (float)center[2];   // PCL searches with a float32 point
     const double r2 = radius * radius;
     float thr = (float)r2;
@@ -135,7 +135,7 @@ extern "C" int pc_sphere_gather(pc_index *ix, const double center[3], double rad
     // ascending original index: sort the appended ids (values are not needed; the key buffer doubles as value buffer)
     int bits = 8;
     while (bits < 32 && ((unsigned long long)n >> bits) != 0) bits += 8;
-    int which = rs_sort_pairs<uint32_t, 16>(L.keys_a, L.vals_a, L.keys_b, L.vals_b, (int64_t)total, 0, bits, L.tile_hist, L.digit_total, st, &ix->launches);
+    int which = pc_sort_pairs<uint32_t, 16>(ix, L.keys_a, L.vals_a, L.keys_b, L.vals_b, (int64_t)total, 0, bits, L.tile_hist, L.digit_total, st);
     PC_CHECK_LAUNCH(ix);
     const uint32_t *sorted = which ? L.keys_b : L.keys_a;
     PC_CUDA(ix, cudaMemcpyAsync(out_idx, sorted, (size_t)total * sizeof(int32_t), space == PC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));

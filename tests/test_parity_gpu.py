@@ -283,6 +283,35 @@ def test_spatial_batch_sharding(ix, n_ranks):
     assert (idx == ref_idx).all()                                     # sharding switched off again
 
 
+def test_shard_ownership_is_rank_invariant_right_after_an_async_build():
+    """Two replicas built independently from device memory: one is queried at once (its host copy of the bounding box has
+    not arrived yet), the other after a sync.  The owner of every query is computed on the device from rank-invariant inputs,
+    so the two still partition the batch."""
+    torch = pytest.importorskip("torch")
+    pts, half = synth.forest_cloud(300_000, seed=6, variant="J", return_half=True)
+    q = torch.from_numpy(synth.rrt_queries(500_000, half, seed=12)).cuda()
+    t_pts = torch.from_numpy(pts).cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+    a = PointCloudIndex(max_points=len(pts), stream=stream)
+    b = PointCloudIndex(max_points=len(pts), stream=stream)
+    try:
+        b.build(t_pts)
+        b.sync()
+        b.batch_shard(1, 2)
+        a.batch_shard(0, 2)
+        a.build(t_pts)                       # asynchronous: returns before the bounding box reaches the host
+        ia, _ = a.nearest(q)
+        ib, _ = b.nearest(q)
+        torch.cuda.synchronize()
+        mine_a = (ia != PointCloudIndex.NOT_MINE_IDX).cpu().numpy()
+        mine_b = (ib != PointCloudIndex.NOT_MINE_IDX).cpu().numpy()
+        assert (mine_a ^ mine_b).all()
+        assert 0.4 < mine_a.mean() < 0.6
+    finally:
+        a.close()
+        b.close()
+
+
 def test_async_device_batches(ix):
     """PC_DEVICE_ASYNC: device batches rotate over the internal streams; results valid after sync and equal to PC_DEVICE."""
     torch = pytest.importorskip("torch")
