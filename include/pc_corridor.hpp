@@ -12,7 +12,8 @@
 //   checkSafeTrajectory  Planner/src/sim_planning_demo.cpp:729-781 (a free function there; it only needs the cloud)
 //   firstCollision  Planner/src/status_inspector.cpp:33-46   ground-truth collision check of executed positions
 //   observe         Planner/src/camera_sensor.cpp:133-145    LiDAR-mode observation (all points within max_dist)
-//   NodeSnapshotIndex   corridor_finder.cpp:428-437          batched findNearstVertex against a frozen node set
+//   NodeSnapshotIndex   corridor_finder.cpp:428-437, 462-464 batched findNearstVertex / treeRewire neighbourhoods against a frozen node set
+//   exportCorridor      sim_planning_demo.cpp:571-592        (Path, Radius) -> PolynomialTrajectoryExtra.path_* / radii
 //
 // No Eigen/PCL/ROS dependency: points are plain double[3] / float arrays (pcl::PointXYZ is x,y,z,pad float32 =
 // stride 4; Eigen::Vector3d::data() is double[3]).
@@ -116,9 +117,9 @@ public:
         int64_t first = -1;
         if (nearest_dist) nearest_dist->resize((size_t)m);
         for (int64_t k = 0; k < m; k++) {
-            const double d = std::sqrt((double)d2[(size_t)k]);            // sqrt(points_distances[0]) < col_rad
-            if (nearest_dist) (*nearest_dist)[(size_t)k] = (float)d;
-            if (first < 0 && d < col_rad) first = k;
+            const float d = std::sqrt(d2[(size_t)k]);      // sqrt(points_distances[0]) < col_rad: a std::vector<float>, float sqrt
+            if (nearest_dist) (*nearest_dist)[(size_t)k] = d;
+            if (first < 0 && (double)d < col_rad) first = k;
         }
         return first;
     }
@@ -151,6 +152,30 @@ private:
     pc_radius_params params_;
 };
 
+// Corridor export: the (Path, Radius) pair of safeRegionRrtStar::getPath as the planner packs it into the path_x / path_y /
+// path_z / radii arrays of quadrotor_msgs/PolynomialTrajectoryExtra (Planner/src/sim_planning_demo.cpp:571-592,
+// Utils/quadrotor_msgs/msg/PolynomialTrajectoryExtra.msg): k + 1 entries, entry 0 REPEATS the first sphere (:582-585), entries
+// 1 .. k are the spheres from the root to the goal.  Plain arrays of doubles (float64[] in the message).
+struct CorridorExport {
+    std::vector<double> path_x, path_y, path_z, radii;
+    size_t size() const { return radii.size(); }
+};
+
+// path: k x 3 sphere centres (row-major), radius: k radii -- the outputs of tracePath (pc::SafeRegionRrtStarDriver::path /
+// ::radius, or the reference's getPath()); k == 0 gives an empty export
+inline CorridorExport exportCorridor(const double *path, const double *radius, int64_t k)
+{
+    CorridorExport e;
+    if (k <= 0) return e;
+    e.path_x.resize((size_t)k + 1); e.path_y.resize((size_t)k + 1); e.path_z.resize((size_t)k + 1); e.radii.resize((size_t)k + 1);
+    e.path_x[0] = path[0]; e.path_y[0] = path[1]; e.path_z[0] = path[2]; e.radii[0] = radius[0];
+    for (int64_t i = 0; i < k; i++) {
+        e.path_x[(size_t)i + 1] = path[3 * i]; e.path_y[(size_t)i + 1] = path[3 * i + 1]; e.path_z[(size_t)i + 1] = path[3 * i + 2];
+        e.radii[(size_t)i + 1] = radius[i];
+    }
+    return e;
+}
+
 // The RRT* NODE tree's nearest-vertex queries for a whole batch of samples: the reference asks kd_nearestf on
 // the node kd-tree once per sample (corridor_finder.cpp:428-437); in the speculative-batch driver the K samples of a batch
 // see the same frozen node set, so the set is indexed once (a few thousand centres: ~0.1 ms) and the K queries are one
@@ -166,11 +191,32 @@ public:
     NodeSnapshotIndex(const NodeSnapshotIndex &) = delete;
     NodeSnapshotIndex &operator=(const NodeSnapshotIndex &) = delete;
 
+    // index the frozen node set once per batch ...
+    int build(const float *node_pos, int64_t n_nodes) { return pc_index_build(ix_, node_pos, n_nodes, 3, PC_HOST); }
+    // ... then findNearstVertex for k samples (kd_nearestf, corridor_finder.cpp:428-437) ...
+    int nearest(const float *samples, int64_t k, int32_t *out_nearest, float *out_d2 = nullptr)
+    {
+        return pc_nearest_batch(ix_, samples, k, 3, PC_HOST, PC_QUERY_AUTO, out_nearest, out_d2);
+    }
+    // ... and the neighbourhoods treeRewire asks for (kd_nearest_rangef(pos, 2 * radius), corridor_finder.cpp:462-464): for
+    // centre j all snapshot nodes within ranges[j], as CSR lists of node indices in ascending (= insertion) order
+    int range(const float *centers, const float *ranges, int64_t k, std::vector<int64_t> &offsets, std::vector<int32_t> &idx)
+    {
+        offsets.assign((size_t)k + 1, 0);
+        std::vector<double> r((size_t)k);
+        for (int64_t j = 0; j < k; j++) r[(size_t)j] = (double)ranges[j];
+        // one call when the lists fit the capacity kept from earlier batches, a second one with the exact size otherwise
+        if ((int64_t)idx.size() < 32 * k) idx.resize((size_t)(32 * k) + 1);
+        int rc = pc_range_batch(ix_, centers, k, 3, PC_HOST, r.data(), 0, offsets.data(), idx.data(), (int64_t)idx.size());
+        if (rc != PC_ECAP) return rc;
+        idx.resize((size_t)offsets[(size_t)k] + (size_t)offsets[(size_t)k] / 2 + 1);
+        return pc_range_batch(ix_, centers, k, 3, PC_HOST, r.data(), 0, offsets.data(), idx.data(), (int64_t)idx.size());
+    }
     int nearest(const float *node_pos, int64_t n_nodes, const float *samples, int64_t k, int32_t *out_nearest, float *out_d2 = nullptr)
     {
-        int rc = pc_index_build(ix_, node_pos, n_nodes, 3, PC_HOST);
+        int rc = build(node_pos, n_nodes);
         if (rc != PC_OK) return rc;
-        return pc_nearest_batch(ix_, samples, k, 3, PC_HOST, PC_QUERY_AUTO, out_nearest, out_d2);
+        return nearest(samples, k, out_nearest, out_d2);
     }
     const char *lastError() const { return pc_last_error(ix_); }
 

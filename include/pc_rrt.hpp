@@ -233,20 +233,26 @@ public:
     {
         in_expansion_ = false;
         std::vector<double> centers((size_t)K * 3), radii((size_t)K), samples((size_t)K * 3);
-        std::vector<float> node_pos, sample_pos((size_t)K * 3);
+        std::vector<float> node_pos, sample_pos((size_t)K * 3), center_pos((size_t)K * 3), ranges((size_t)K);
         std::vector<int32_t> nearest_idx((size_t)K);
+        std::vector<int64_t> range_off;
+        std::vector<int32_t> range_idx;
+        std::vector<RrtNode *> snapshot, batch_nodes, found;
         int it = 0;
         while (it < max_iterations && it < max_samples) {
             const int k_now = std::min(K, std::min(max_iterations, max_samples) - it);
             int n = 0;
             for (int j = 0; j < k_now; j++) genSample(&samples[(size_t)j * 3]);
-            if (snapshot_nearest_) {
+            if (snapshot_nearest_ || snapshot_range_) {
                 // the K nearest-vertex queries of a batch go against the SAME frozen node set, so they are one
                 // batched exact-NN call on the node centres (float positions, like kd_nearestf)
-                node_pos.resize(node_list_.size() * 3);
-                for (size_t i = 0; i < node_list_.size(); i++) for (int a = 0; a < 3; a++) node_pos[3 * i + a] = (float)node_list_[i]->coord[a];
+                snapshot = node_list_;
+                node_pos.resize(snapshot.size() * 3);
+                for (size_t i = 0; i < snapshot.size(); i++) for (int a = 0; a < 3; a++) node_pos[3 * i + a] = (float)snapshot[i]->coord[a];
+            }
+            if (snapshot_nearest_) {
                 for (size_t i = 0; i < (size_t)k_now * 3; i++) sample_pos[i] = (float)samples[i];
-                snapshot_nearest_(node_pos.data(), (int)node_list_.size(), sample_pos.data(), k_now, nearest_idx.data());
+                snapshot_nearest_(node_pos.data(), (int)snapshot.size(), sample_pos.data(), k_now, nearest_idx.data());
                 node_tree_calls++;
             }
             for (int j = 0; j < k_now; j++) {
@@ -261,12 +267,44 @@ public:
                 cloud_queries += n;
                 radius_calls++;
             }
+            const bool gpu_range = snapshot_range_ && n > 0;
+            if (gpu_range) {
+                // SURVEY 8f-2, second half: the 2 x radius neighbourhoods treeRewire asks the node tree for
+                // (kd_nearest_rangef, corridor_finder.cpp:462-464) -- one batched range call against the same snapshot for all
+                // candidates; the nodes this batch itself inserts are added from a short list below.  Invalidated nodes stay
+                // in place until the batch is done (their snapshot entries must stay alive), as they do in the reference
+                // until invalidSet reaches cach_size.
+                for (int j = 0; j < n; j++) {
+                    for (int a = 0; a < 3; a++) center_pos[(size_t)j * 3 + a] = (float)centers[(size_t)j * 3 + a];
+                    ranges[(size_t)j] = (float)radii[(size_t)j] * 2.0f;
+                }
+                snapshot_range_(node_pos.data(), (int)snapshot.size(), center_pos.data(), ranges.data(), n, range_off, range_idx);
+                node_tree_calls++;
+                batch_nodes.clear();
+            }
+            defer_remove_ = true;          // with either provider, so that both see the same node tree
             for (int j = 0; j < n; j++) {
                 // the tree may have grown since the snapshot: connect to the vertex that is nearest NOW
                 RrtNode *nearest = findNearestVertex(&centers[(size_t)j * 3]);
                 if (!nearest || !nearest->valid) continue;
-                tryInsert(&centers[(size_t)j * 3], radii[(size_t)j], nearest);
+                if (gpu_range) {
+                    found.clear();
+                    for (int64_t t = range_off[(size_t)j]; t < range_off[(size_t)j + 1]; t++) found.push_back(snapshot[(size_t)range_idx[(size_t)t]]);
+                    const float *c = &center_pos[(size_t)j * 3];
+                    const double r2 = (double)ranges[(size_t)j] * (double)ranges[(size_t)j];
+                    for (RrtNode *b : batch_nodes) {              // inserted by this batch, in insertion order
+                        double s2 = 0.0;
+                        for (int a = 0; a < 3; a++) { const double d = (double)(float)b->coord[a] - (double)c[a]; s2 += d * d; }
+                        if (s2 <= r2) found.push_back(b);
+                    }
+                    found_override_ = &found;
+                }
+                RrtNode *added = tryInsert(&centers[(size_t)j * 3], radii[(size_t)j], nearest);
+                found_override_ = nullptr;
+                if (gpu_range && added) batch_nodes.push_back(added);
             }
+            defer_remove_ = false;
+            if ((int)invalid_set_.size() >= cach_size) removeInvalid();
             it += k_now;
         }
         removeInvalid();
@@ -416,6 +454,12 @@ public:
     // node_pos: n_nodes x 3 float centres in node-list order; out_nearest[j] = index of the node nearest to sample j.
     using SnapshotNearestFn = std::function<void(const float *node_pos, int n_nodes, const float *samples, int k, int32_t *out_nearest)>;
     void setSnapshotNearest(SnapshotNearestFn fn) { snapshot_nearest_ = std::move(fn); }
+    // optional: batched range provider for the insertion phase of expandBatched / refineBatched: for candidate j all snapshot
+    // nodes with d2 <= ranges[j]^2 (fp64 on the float32 positions, inclusive: kd_nearest_rangef), CSR lists of node indices in
+    // ascending order
+    using SnapshotRangeFn = std::function<void(const float *node_pos, int n_nodes, const float *centers, const float *ranges, int k,
+                                               std::vector<int64_t> &offsets, std::vector<int32_t> &idx)>;
+    void setSnapshotRange(SnapshotRangeFn fn) { snapshot_range_ = std::move(fn); }
     const NodeKdTree &nodeTree() const { return node_tree_; }
 
     double safety_margin = 0, search_margin = 0, max_radius = 0, sample_range = 0;
@@ -489,12 +533,12 @@ private:
     bool checkEnd(const RrtNode *n) const { return dist(n->coord, end_pt) + 0.1 < n->radius; }
 
     // the body of the expansion loop after the cloud query (corridor_finder.cpp:730-755)
-    void tryInsert(const double c[3], double r, RrtNode *nearest)
+    RrtNode *tryInsert(const double c[3], double r, RrtNode *nearest)
     {
-        if (c[2] < z_l || (float)r < safety_margin) return;
+        if (c[2] < z_l || (float)r < safety_margin) return nullptr;
         RrtNode *n = new RrtNode(c, (float)r, (float)inf(), (float)dist(c, end_pt));
         treeRewire(n, nearest);
-        if (!n->valid) { delete n; return; }          // (the reference leaks these nodes)
+        if (!n->valid) { delete n; return nullptr; }  // (the reference leaks these nodes)
         if (checkEnd(n)) {
             if (!inform_status) best_end_ptr = n;
             end_list_.push_back(n);
@@ -504,7 +548,8 @@ private:
         insertIntoTree(n);
         recordNode(n);
         treePrune(n);
-        if ((int)invalid_set_.size() >= cach_size) removeInvalid();
+        if ((int)invalid_set_.size() >= cach_size && !defer_remove_) removeInvalid();
+        return n;
     }
 
     // corridor_finder.cpp:661-667
@@ -533,7 +578,8 @@ private:
         const float range = newPtr->radius * 2.0f;
         const float pos[3] = { (float)newPtr->coord[0], (float)newPtr->coord[1], (float)newPtr->coord[2] };
         std::vector<RrtNode *> found;
-        if (quirks_) node_tree_.rangeReferenceOrder(pos, range, found);
+        if (found_override_) found = *found_override_;          // answered by the batched snapshot range provider
+        else if (quirks_) node_tree_.rangeReferenceOrder(pos, range, found);
         else node_tree_.range(pos, range, found);
         std::vector<RrtNode *> nearPtrList;
         bool isInvalid = false;
@@ -710,6 +756,9 @@ private:
 
     RadiusBatchFn radius_;
     SnapshotNearestFn snapshot_nearest_;
+    SnapshotRangeFn snapshot_range_;
+    const std::vector<RrtNode *> *found_override_ = nullptr;
+    bool defer_remove_ = false;
     std::default_random_engine eng_;
     U rand_x, rand_y, rand_z, rand_bias, rand_x_in, rand_y_in, rand_z_in;
     U rand_u = U(0.0, 1.0), rand_v = U(0.0, 1.0), rand_phi = U(0.0, 2 * M_PI);

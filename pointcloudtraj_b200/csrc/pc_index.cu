@@ -530,7 +530,8 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
         L.per_cell = per_cell;
     }
     const int drop = 30 - bits > 0 ? 30 - bits : 0;     // 24-bit sort = top 24 curve bits, 32-bit sort = all 30
-    const int grid = (int)((m + 255) / 256);
+    const int64_t key_ctas = (m + 255) / 256;
+    const int grid = (int)(key_ctas < (int64_t)ix->sm_count * 8 ? key_ctas : (int64_t)ix->sm_count * 8);
     const int items = ix->sort_items;
     const bool fused_hist = ix->onesweep && m < OS_MAX_N;
     uint32_t *gh = fused_hist ? os_ghist(L.tile_hist) : nullptr;

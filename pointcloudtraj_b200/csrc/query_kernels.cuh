@@ -455,7 +455,8 @@ pc_query_coop_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, in
 // rank's share is then as dense in space as the whole batch (dense packets) and spread over the whole map (equal cost per
 // rank).  The level is computed HERE, from the index's bounding box and the batch size only -- both identical on every
 // rank that holds a replica -- so all ranks agree on the owner of every query whatever the state of their host-side caches:
-// the finest cells (<= 128 per axis) that still hold ~512 queries each.
+// the finest cells (<= 128 per axis) that still hold >= 128 queries (two packets) each -- finer cells balance the ranks
+// better, coarser ones keep more packets inside one cell.
 // Measured on C5 with 8 GPUs: array slices 37 ms; contiguous stretches of the curve 41 ms and round-robin 32^3 cells 43 ms
 // (both unbalanced: 18..42 ms per rank -- on a flat map the low bits of the cell index encode the z layer); hashed cells:
 // profiles/r1_c5_strong_scaling.jsonl.
@@ -473,7 +474,7 @@ __device__ __forceinline__ int pc_shard_level(const uint32_t *__restrict__ bbox,
         double v = 1.0;
 #pragma unroll
         for (int a = 0; a < 3; a++) v *= (double)ext[a] > c ? (double)ext[a] : c;
-        if ((double)m * c * c * c / v >= 512.0) return lv;
+        if ((double)m * c * c * c / v >= 128.0) return lv;
     }
     return 2;
 }
@@ -486,59 +487,59 @@ pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
                     int shard_rank, int shard_n, uint32_t *__restrict__ ghist, int hist_passes)
 {
     // ghist (nullable): digit histograms of the hist_passes 8-bit passes that will sort the compacted keys (radix_sort.cuh,
-    // onesweep path) -- counted here, while the key is in a register, instead of by a separate pass over the keys
+    // onesweep path) -- counted here, while the key is in a register, instead of by a separate pass over the keys.  The
+    // grid is a few CTAs per SM, each striding over the batch, so that a CTA flushes its histograms to global memory once.
     __shared__ uint32_t s_hist[4][RS_RADIX];
-    if (ghist) {
-        for (int j = threadIdx.x; j < hist_passes * RS_RADIX; j += 256) (&s_hist[0][0])[j] = 0;
-        __syncthreads();
-    }
     __shared__ uint32_t s_warp[8];
     __shared__ unsigned long long s_base;
     __shared__ int s_shard_shift;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (shard_n > 1) {
-        if (threadIdx.x == 0) s_shard_shift = 10 - pc_shard_level(bbox, m);      // cell coordinate bits dropped per axis
-        __syncthreads();
-    }
-    bool search = false;
-    uint32_t key = 0;
-    if (i < m) {
-        const pc_frame f = pc_make_frame(bbox, 10);
-        const float *p = q + i * qstride;
-        const float x = p[0], y = p[1], z = p[2];
-        const uint32_t cx = pc_cell_coord(x, f.lo[0], f.inv_cell, f.max_cell), cy = pc_cell_coord(y, f.lo[1], f.inv_cell, f.max_cell),
-                       cz = pc_cell_coord(z, f.lo[2], f.inv_cell, f.max_cell);
-        search = true;
-        if (shard_n > 1) {
-            const int sh = s_shard_shift;
-            const uint32_t cell = ((cx >> sh) * 73856093u) ^ ((cy >> sh) * 19349663u) ^ ((cz >> sh) * 83492791u);
-            search = (int)(((cell * 2654435761u) >> 15) % (uint32_t)shard_n) == shard_rank;
-        }
-        if (search) {
-            if (KIND == PC_KIND_RADIUS && pc_radius_early_out((double)x, (double)y, (double)z, R)) {
-                search = false;
-                pc_write_trivial<KIND>(R, (uint32_t)i, out_idx, out_f);
+    if (ghist) for (int j = threadIdx.x; j < hist_passes * RS_RADIX; j += 256) (&s_hist[0][0])[j] = 0;
+    if (shard_n > 1 && threadIdx.x == 0) s_shard_shift = 10 - pc_shard_level(bbox, m);      // cell coordinate bits dropped per axis
+    __syncthreads();
+    const pc_frame f = pc_make_frame(bbox, 10);
+    for (int64_t base = (int64_t)blockIdx.x * 256; base < m; base += (int64_t)gridDim.x * 256) {
+        const int64_t i = base + threadIdx.x;
+        bool search = false;
+        uint32_t key = 0;
+        if (i < m) {
+            const float *p = q + i * qstride;
+            const float x = p[0], y = p[1], z = p[2];
+            const uint32_t cx = pc_cell_coord(x, f.lo[0], f.inv_cell, f.max_cell), cy = pc_cell_coord(y, f.lo[1], f.inv_cell, f.max_cell),
+                           cz = pc_cell_coord(z, f.lo[2], f.inv_cell, f.max_cell);
+            search = true;
+            if (shard_n > 1) {
+                const int sh = s_shard_shift;
+                uint32_t h = (cx >> sh) | ((cy >> sh) << 10) | ((cz >> sh) << 20);       // the cell, then a murmur-style finaliser
+                h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+                search = (int)(h % (uint32_t)shard_n) == shard_rank;
             }
-            key = pc_hilbert30_cells(cx, cy, cz) >> drop_bits;
+            if (search) {
+                if (KIND == PC_KIND_RADIUS && pc_radius_early_out((double)x, (double)y, (double)z, R)) {
+                    search = false;
+                    pc_write_trivial<KIND>(R, (uint32_t)i, out_idx, out_f);
+                }
+                key = pc_hilbert30_cells(cx, cy, cz) >> drop_bits;
+            }
         }
-    }
-    // compact the queries that still need a search: only those are sorted and searched.  One atomic per CTA; the slot a
-    // query lands in depends on CTA scheduling, which changes the composition of packets but never a result.
-    const uint32_t mask = __ballot_sync(PC_FULL_MASK, search);
-    if (lane == 0) s_warp[warp] = __popc(mask);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tot = 0;
-        for (int w = 0; w < 8; w++) { const uint32_t c = s_warp[w]; s_warp[w] = tot; tot += c; }
-        s_base = tot ? atomicAdd(n_search, (unsigned long long)tot) : 0ull;
-    }
-    __syncthreads();
-    if (search) {
-        const unsigned long long pos = s_base + s_warp[warp] + __popc(mask & pc_lanemask_lt());
-        keys[pos] = key;
-        vals[pos] = (uint32_t)i;
-        if (ghist) for (int p = 0; p < hist_passes; p++) atomicAdd(&s_hist[p][(key >> (8 * p)) & (RS_RADIX - 1)], 1u);
+        // compact the queries that still need a search: only those are sorted and searched.  One atomic per 256 queries; the
+        // slot a query lands in depends on CTA scheduling, which changes the composition of packets but never a result.
+        const uint32_t mask = __ballot_sync(PC_FULL_MASK, search);
+        if (lane == 0) s_warp[warp] = __popc(mask);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (int w = 0; w < 8; w++) { const uint32_t c = s_warp[w]; s_warp[w] = tot; tot += c; }
+            s_base = tot ? atomicAdd(n_search, (unsigned long long)tot) : 0ull;
+        }
+        __syncthreads();
+        if (search) {
+            const unsigned long long pos = s_base + s_warp[warp] + __popc(mask & pc_lanemask_lt());
+            keys[pos] = key;
+            vals[pos] = (uint32_t)i;
+            if (ghist) for (int p = 0; p < hist_passes; p++) atomicAdd(&s_hist[p][(key >> (8 * p)) & (RS_RADIX - 1)], 1u);
+        }
+        __syncthreads();            // s_warp / s_base are rewritten by the next round
     }
     if (ghist) {
         __syncthreads();

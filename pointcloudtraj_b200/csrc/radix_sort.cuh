@@ -225,6 +225,9 @@ static int rs_sort_pairs(KeyT *keys_a, uint32_t *vals_a, KeyT *keys_b, uint32_t 
 
 // ---- onesweep -----------------------------------------------------------------------------------------------------------------
 #define OS_MAX_PASSES 8
+#ifndef OS_MIN_CTAS
+#define OS_MIN_CTAS 4                    // resident CTAs per SM the pass kernel is compiled for (<= 64 registers per thread)
+#endif
 #define OS_FLAG_LOCAL 0x40000000u        // the word holds the tile's own count of this digit
 #define OS_FLAG_INCL  0x80000000u        // the word holds the inclusive prefix over tiles 0 .. this one
 #define OS_VALUE_MASK 0x3fffffffu
@@ -263,7 +266,7 @@ os_histogram(const KeyT *__restrict__ keys, int64_t n, const unsigned long long 
 }
 
 template <typename KeyT, int ITEMS>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, OS_MIN_CTAS)
 os_pass(const KeyT *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
         KeyT *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, const unsigned long long *__restrict__ n_dev,
         int shift, const uint32_t *__restrict__ ghist, volatile uint32_t *status, uint32_t *ticket)

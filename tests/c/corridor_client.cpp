@@ -2,7 +2,8 @@
 // setParam, setPt, setInput (rebuild per frame), radiusSearch (single + batch), checkTrajPtCol.
 // usage: corridor_client <in.bin> <out.bin>   in: int64 n, int64 m, double params[4] (safety, search, max_radius, range),
 //                                              double start[3], float pts[n*4] (PointXYZ layout), double q[m*3]
-//                                             out: double radius_single[m], float radius_batch[m], uint8 col[m]
+//                                             out: double radius_single[m], float radius_batch[m], uint8 col[m],
+//                                                  int64 first_collision (col_rad 0.3), float nearest_dist[m]
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -57,6 +58,8 @@ int main(int argc, char **argv)
     fwrite(r1.data(), 8, (size_t)m, o);
     fwrite(r2.data(), 4, (size_t)m, o);
     fwrite(col.data(), 1, (size_t)m, o);
+    fwrite(&first_col, 8, 1, o);
+    fwrite(nd.data(), 4, (size_t)m, o);
     fclose(o);
     return 0;
 }

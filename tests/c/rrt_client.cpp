@@ -4,8 +4,10 @@
 //   B  CPU oracle, one query per iteration (po_radius_search of oracle/planner_oracle.c)   -- TEST-ONLY checker
 //   C  GPU, speculative batches of K       (pc_radius_batch on the float32-cast centres)
 //   D  as C + the batch's nearest-vertex queries on the GPU (pc::NodeSnapshotIndex), checked against the CPU node tree
+//   E  as C + the 2 x radius neighbourhoods of treeRewire (kd_nearest_rangef, corridor_finder.cpp:462-464) answered for the
+//      whole batch by ONE pc_range_batch on the snapshot index: must reproduce C bit for bit
 // A and B must produce bit-identical corridors (replay mode); C is validated by the pytest against the oracle.
-// usage: rrt_client <in.bin> <out.bin>      file formats: rrt_io.hpp; output = the records of A, then B, then C, then D
+// usage: rrt_client <in.bin> <out.bin>      file formats: rrt_io.hpp; output = the records of A, then B, then C, then D, then E
 #include <cstdlib>
 #include "pc_corridor.hpp"
 #include "rrt_io.hpp"
@@ -84,6 +86,31 @@ int main(int argc, char **argv)
         }
     });
     rrt_run(o, D, in, true, gpu_cloud);
+
+    pc::SafeRegionRrtStarDriver E([&](const double *c, int m, double *out) {
+        qf.resize((size_t)m * 3); rf.resize((size_t)m);
+        for (size_t i = 0; i < qf.size(); i++) qf[i] = (float)c[i];
+        if (cloud.radiusSearch(qf.data(), m, 3, rf.data()) != PC_OK) exit(8);
+        for (int i = 0; i < m; i++) out[i] = rf[(size_t)i];
+    });
+    pc::NodeSnapshotIndex nodes_e(0, 1 << 16);
+    E.setSnapshotRange([&](const float *node_pos, int n_nodes, const float *centers, const float *ranges, int k,
+                           std::vector<int64_t> &offsets, std::vector<int32_t> &idx) {
+        if (nodes_e.build(node_pos, n_nodes) != PC_OK || nodes_e.range(centers, ranges, k, offsets, idx) != PC_OK) {
+            fprintf(stderr, "snapshot range: %s\n", nodes_e.lastError());
+            exit(11);
+        }
+    });
+    rrt_run(o, E, in, true, gpu_cloud);
+    // the corridor as the planner publishes it (PolynomialTrajectoryExtra.path_* / radii): first sphere repeated
+    {
+        const pc::CorridorExport ex = pc::exportCorridor(E.path.data(), E.radius.data(), (int64_t)E.radius.size());
+        const size_t k = E.radius.size();
+        if (ex.size() != (k ? k + 1 : 0)) return 12;
+        for (size_t i = 0; i < k; i++)
+            if (ex.path_x[i + 1] != E.path[3 * i] || ex.path_y[i + 1] != E.path[3 * i + 1] || ex.path_z[i + 1] != E.path[3 * i + 2] || ex.radii[i + 1] != E.radius[i]) return 12;
+        if (k && (ex.path_x[0] != E.path[0] || ex.path_y[0] != E.path[1] || ex.path_z[0] != E.path[2] || ex.radii[0] != E.radius[0])) return 12;
+    }
     fclose(o);
     kdo_free(kt[0]); kdo_free(kt[1]);
     return 0;

@@ -89,3 +89,12 @@ def test_corridor_wrapper_matches_radius_search_oracle(tmp_path):
     assert (r_batch == ref_b.astype(np.float32)).all()
     assert (col.astype(bool) == (ref_b < 0)).all()
     assert (ref == prm[2] - prm[1]).any() and (ref < 0).any() and (ref == prm[2]).any()
+    # the ground-truth collision arbiter (status_inspector.cpp:33-46) against the oracle's exact nearest distances:
+    # sqrt (float32, as the reference computes it from PCL's float distances) of d2 < col_rad, first such position
+    first_col, = struct.unpack_from("<q", raw, 13 * m)
+    nd = np.frombuffer(raw, np.float32, m, 13 * m + 8)
+    _, od2 = ko.nearest(q.astype(np.float32))
+    od = np.sqrt(od2.astype(np.float32))
+    assert (nd == od).all()
+    hits = np.nonzero(od.astype(np.float64) < 0.3)[0]
+    assert first_col == (hits[0] if len(hits) else -1) and len(hits) > 0
