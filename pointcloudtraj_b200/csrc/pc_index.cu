@@ -18,6 +18,7 @@
 #include "query_kernels.cuh"
 #include "range_kernels.cuh"
 #include "clearance_kernels.cuh"
+#include "grid_kernels.cuh"
 
 #define PC_VERSION_STRING "pcindex 0.2 (sm_100a)"
 #define PC_PIPE_LANES 3                 // concurrent H2D / kernel / D2H chunks for PC_HOST calls
@@ -93,6 +94,12 @@ struct pc_index {
     int next_lane = 0;        // PC_HOST_ASYNC: lane of the next batch
     int shard_rank = 0, shard_n = 1;   // pc_batch_shard
     int radius_arith = PC_ARITH_FP64;  // pc_index_set_radius_arith
+    // experiment (PC_GRID=1): the voxel grid of grid_kernels.cuh next to the tree, used by bounded radius batches
+    bool use_grid = false, grid_ready = false;
+    double grid_cell = 0.5;            // requested cell edge in metres (PC_GRID_CELL)
+    pc_grid grid;
+    uint32_t *grid_cell_start = nullptr; int64_t grid_cells_cap = 0;
+    float4 *grid_points = nullptr; int64_t grid_points_cap = 0;
     bool onesweep = true;              // PC_ONESWEEP=0: the three-kernel-per-pass radix sort (radix_sort.cuh)
     int sort_items = 16;               // keys per thread of the batch-ordering sort (PC_SORT_ITEMS = 8 | 16)
     int coop_group = 0;                     // lanes per query of the small-batch kernel: 0 = by batch size, else 32 / 16 / 8 (PC_COOP_GROUP)
@@ -212,6 +219,8 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         if (const char *v = getenv("PC_SORT_BITS")) { ix->sort_bits_auto = false; int b_ = atoi(v); ix->sort_bits = b_ <= 0 ? 0 : (b_ <= 16 ? 16 : (b_ <= 24 ? 24 : 32)); }
         if (const char *v = getenv("PC_HOST_RAMP")) ix->host_ramp = atoi(v) != 0;
         if (const char *v = getenv("PC_ONESWEEP")) ix->onesweep = atoi(v) != 0;
+        if (const char *v = getenv("PC_GRID")) ix->use_grid = atoi(v) != 0;
+        if (const char *v = getenv("PC_GRID_CELL")) { double c_ = atof(v); if (c_ > 0.0) ix->grid_cell = c_; }
         if (const char *v = getenv("PC_SORT_ITEMS")) ix->sort_items = atoi(v) == 8 ? 8 : 16;
         if (const char *v = getenv("PC_HOST_CHUNK_QUERIES")) { long long b_ = atoll(v); if (b_ >= 1024) ix->host_chunk = b_; }
         if (const char *v = getenv("PC_COOP_GROUP")) { int b_ = atoi(v); ix->coop_group = (b_ == 32 || b_ == 16 || b_ == 8) ? b_ : 0; }
@@ -288,7 +297,7 @@ extern "C" void pc_index_destroy(pc_index *ix)
     if (ix->tiny_i) cudaFreeHost(ix->tiny_i);
     cudaFree(ix->d_xyz); cudaFree(ix->d_bbox); cudaFree(ix->keys_a); cudaFree(ix->keys_b);
     cudaFree(ix->vals_a); cudaFree(ix->vals_b); cudaFree(ix->tile_hist); cudaFree(ix->digit_total);
-    cudaFree(ix->tree); cudaFree(ix->scratch);
+    cudaFree(ix->tree); cudaFree(ix->scratch); cudaFree(ix->grid_cell_start); cudaFree(ix->grid_points);
     if (ix->ev_b0) cudaEventDestroy(ix->ev_b0);
     if (ix->ev_b1) cudaEventDestroy(ix->ev_b1);
     if (ix->ev_ready) cudaEventDestroy(ix->ev_ready);
@@ -433,6 +442,43 @@ extern "C" int pc_index_build(pc_index *ix, const float *xyz, int64_t n, int64_t
     }
     PC_CUDA(ix, cudaMemcpyAsync(ix->h_bbox, ix->d_bbox, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PC_CUDA(ix, cudaEventRecord(ix->ev_b1, st));
+    ix->grid_ready = false;
+    if (ix->use_grid) {
+        // experiment: the voxel grid over the same cloud (its build is NOT part of the timed index build above; it needs the
+        // bounding box on the host, hence the sync)
+        PC_CUDA(ix, cudaStreamSynchronize(st));
+        pc_grid G;
+        double ext[3], vol = 1.0, emax = 0.0;
+        for (int a = 0; a < 3; a++) {
+            G.lo[a] = pc_ordered_to_float(ix->h_bbox[a]);
+            ext[a] = (double)pc_ordered_to_float(ix->h_bbox[3 + a]) - (double)G.lo[a];
+            emax = ext[a] > emax ? ext[a] : emax;
+        }
+        double h = ix->grid_cell;
+        for (;;) {                                   // at most 2^24 cells
+            vol = 1.0;
+            for (int a = 0; a < 3; a++) vol *= floor(ext[a] / h) + 1.0;
+            if (vol <= 16777216.0) break;
+            h *= 1.26;
+        }
+        G.h = (float)h; G.inv_h = 1.0f / G.h; G.eps = (float)(emax + h) * 9.6e-7f;        // 8 ulp of the largest coordinate offset
+        int64_t cells = 1;
+        for (int a = 0; a < 3; a++) { G.n[a] = (int)floor(ext[a] / h) + 1; cells *= G.n[a]; }
+        int rcg;
+        if ((rcg = pc_grow(ix, &ix->grid_cell_start, &ix->grid_cells_cap, cells + 2)) != PC_OK) return rcg;
+        if ((rcg = pc_grow(ix, &ix->grid_points, &ix->grid_points_cap, n)) != PC_OK) return rcg;
+        G.cell_start = ix->grid_cell_start; G.points = ix->grid_points;
+        if (ix->key_bytes != 4 || n >= OS_MAX_N) return pc_fail(ix, PC_ENOTIMPL, "PC_GRID: clouds up to 4 Mi points");
+        pc_grid_key_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(src, n, stride, G, (uint32_t *)ix->keys_a, ix->vals_a);
+        int kb = 8;
+        while (kb < 32 && (cells >> kb) != 0) kb += 8;
+        int w = pc_sort_pairs<uint32_t, 8>(ix, (uint32_t *)ix->keys_a, ix->vals_a, (uint32_t *)ix->keys_b, ix->vals_b, n, 0, kb, ix->tile_hist, ix->digit_total, st);
+        pc_grid_cells_kernel<<<(int)((cells + 1 + 255) / 256), 256, 0, st>>>((const uint32_t *)(w ? ix->keys_b : ix->keys_a), n, cells, ix->grid_cell_start);
+        pc_grid_gather_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(src, stride, w ? ix->vals_b : ix->vals_a, n, ix->grid_points);
+        PC_CHECK_LAUNCH(ix);
+        ix->grid = G;
+        ix->grid_ready = true;
+    }
     PC_CUDA(ix, cudaEventRecord(ix->ev_ready, st));
     ix->n = n; ix->n_nodes = n_nodes; ix->build_timed = true; ix->bbox_from_bcast = false;
     ix->root = n_nodes > 0 ? 0u : PC_REF_LEAF; ix->root_count = n_nodes > 0 ? 0u : (uint32_t)n;
@@ -617,7 +663,11 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
     // dense batches (>= 3 queries per cell of 1/256 of the cloud's extent): 64-query packets, two queries per lane
     // (profiles/r1_sweep5*: +10 % radius, +18 % nearest at 10 M queries; -3 % at 2 M, hence the threshold)
     const bool two_per_lane = ix->query_kernel == 4 || (ix->query_kernel == 3 && ix->query_kernel_auto && L.per_cell >= 3.0);
-    if (ix->query_kernel >= 3 && perm) {
+    if (ix->grid_ready && perm && A.kind == PC_Q_RADIUS && A.R.bounded) {
+        // experiment (PC_GRID=1): ring search over the voxel grid instead of the tree walk
+        const int grid = (int)((m + PC_QUERY_THREADS - 1) / PC_QUERY_THREADS);
+        pc_radius_grid_kernel<<<grid, PC_QUERY_THREADS, 0, L.stream>>>(ix->grid, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
+    } else if (ix->query_kernel >= 3 && perm) {
         // curve-ordered batch: one warp walks the tree once for its 32 or 64 neighbouring queries
         const int per_cta = (two_per_lane ? 2 : 1) * PC_QUERY_THREADS;
         const int grid = (int)((m + per_cta - 1) / per_cta);

@@ -21,6 +21,14 @@
 #define PC_STACK 96                            // tree depth <= key bits (<= 63) + position bits of coincident points (<= 31)
 #define PC_THR_SLACK 1.00000095367431640625f   // 1 + 2^-20
 #define PC_NO_NODE 0xffffffffu
+#ifndef PC_PACKET_MIN_CTAS
+#define PC_PACKET_MIN_CTAS 8        // resident CTAs per SM the packet kernels are compiled for (<= 64 registers: -2 % search
+                                    // time against 7 CTAs at 72 registers, profiles/r2_variants_ab.txt)
+#endif
+#ifndef PC_PACKET_PREFETCH
+#define PC_PACKET_PREFETCH 0        // 1: when a record arrives, pull the records of its two children towards L1 (measured:
+                                    // +10 % search time -- the extra requests cost more than the latency they hide)
+#endif
 
 struct pc_tree {
     const float4 *__restrict__ rec;      // inner node i -> rec[4i .. 4i+3] = [min0 | max0 | min1 | max1], children in the .w words
@@ -261,6 +269,16 @@ __device__ __forceinline__ void pc_packet_traverse(const pc_tree &T, const float
         float4 lo0, hi0, lo1, hi1;
         pc_load_box(pair, lo0, hi0);
         pc_load_box(pair + 2, lo1, hi1);
+#if PC_PACKET_PREFETCH
+        {   // the next visit is one of the two children (or a stack entry): start their records' trip from L2 now, while the
+            // box tests and votes below run (a leaf reference fetches a line of the points instead, also the next access)
+            const uint32_t c0 = __float_as_uint(lo0.w), c1 = __float_as_uint(lo1.w);
+            const float4 *a0 = (c0 & PC_REF_LEAF) ? T.points + (c0 & ~PC_REF_LEAF) : T.rec + 4ull * c0;
+            const float4 *a1 = (c1 & PC_REF_LEAF) ? T.points + (c1 & ~PC_REF_LEAF) : T.rec + 4ull * c1;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a0));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a1));
+        }
+#endif
         float d0[NQ], d1[NQ];
         bool want0 = false, want1 = false;
 #pragma unroll
@@ -306,7 +324,7 @@ __device__ __forceinline__ void pc_packet_traverse(const pc_tree &T, const float
 }
 
 template <int KIND, int NQ>
-__global__ void __launch_bounds__(PC_QUERY_THREADS)
+__global__ void __launch_bounds__(PC_QUERY_THREADS, PC_PACKET_MIN_CTAS)
 pc_query_packet_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, int64_t m, int qstride,
                        const uint32_t *__restrict__ perm, const unsigned long long *__restrict__ m_eff,
                        int32_t *__restrict__ out_idx, float *__restrict__ out_f)

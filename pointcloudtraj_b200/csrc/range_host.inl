@@ -36,8 +36,9 @@ extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64
     const int64_t b_off = space == PC_HOST ? pc_align_up((m + 1) * (int64_t)sizeof(int64_t), 256) : 0;
     const int64_t b_cnt = pc_align_up((m + 1) * (int64_t)sizeof(int64_t), 256);
     const int64_t b_tile = pc_align_up((n_tiles + 1) * (int64_t)sizeof(int64_t), 256);
+    const int64_t b_long = pc_align_up((m + 1) * (int64_t)sizeof(int64_t), 256);      // queue of lists too long for the in-warp sort
     void *base = nullptr;
-    if ((rc = pc_scratch(ix, b_q + b_r + b_off + b_cnt + b_tile, &base)) != PC_OK) return rc;
+    if ((rc = pc_scratch(ix, b_q + b_r + b_off + b_cnt + b_tile + b_long, &base)) != PC_OK) return rc;
     char *p = (char *)base;
     const float *d_q = q_xyz; const double *d_r = range; int64_t *d_off = out_offsets;
     if (space == PC_HOST) {
@@ -50,7 +51,9 @@ extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64
         }
     }
     int64_t *d_cnt = (int64_t *)p; p += b_cnt;
-    int64_t *d_tile = (int64_t *)p;
+    int64_t *d_tile = (int64_t *)p; p += b_tile;
+    unsigned long long *d_long_count = (unsigned long long *)p;
+    int64_t *d_long_list = (int64_t *)p + 1;
 
     int64_t total = 0;
     if (m == 0) {
@@ -60,7 +63,7 @@ extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64
     }
     pc_tree T = pc_tree_of(ix);
     const int cgrid = (int)((m + PC_RCOOP_WARPS - 1) / PC_RCOOP_WARPS);      // one warp per query
-    pc_range_coop_kernel<false><<<cgrid, 32 * PC_RCOOP_WARPS, 0, st>>>(T, d_q, m, qs, d_r, range_is_scalar ? 1 : 0, d_cnt, nullptr, nullptr);
+    pc_range_coop_kernel<false><<<cgrid, 32 * PC_RCOOP_WARPS, 0, st>>>(T, d_q, m, qs, d_r, range_is_scalar ? 1 : 0, d_cnt, nullptr, nullptr, nullptr, nullptr);
     pc_scan_tile_sums<<<(int)n_tiles, PC_SCAN_THREADS, 0, st>>>(d_cnt, m, d_tile);
     pc_scan_tile_offsets<<<1, PC_SCAN_THREADS, 0, st>>>(d_tile, n_tiles);
     pc_scan_write_offsets<<<(int)n_tiles, PC_SCAN_THREADS, 0, st>>>(d_cnt, m, d_tile, d_off);
@@ -82,9 +85,22 @@ extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64
         if ((rc = pc_grow(ix, &L.d_i32, &L.i32_cap, total)) != PC_OK) return rc;
         d_out = L.d_i32;
     }
-    pc_range_coop_kernel<true><<<cgrid, 32 * PC_RCOOP_WARPS, 0, st>>>(T, d_q, m, qs, d_r, range_is_scalar ? 1 : 0, nullptr, d_off, d_out);
+    PC_CUDA(ix, cudaMemsetAsync(d_long_count, 0, sizeof(unsigned long long), st));
+    pc_range_coop_kernel<true><<<cgrid, 32 * PC_RCOOP_WARPS, 0, st>>>(T, d_q, m, qs, d_r, range_is_scalar ? 1 : 0, nullptr, d_off, d_out, d_long_count, d_long_list);
     ix->launches++;
     PC_CHECK_LAUNCH(ix);
+    if (total > PC_RCOOP_CAP) {          // only then can a list be longer than the in-warp sort takes
+        static bool attr_set[64] = { false };
+        if (ix->device >= 64 || !attr_set[ix->device]) {
+            PC_CUDA(ix, cudaFuncSetAttribute(pc_range_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_RLONG_CAP * (int)sizeof(uint32_t)));
+            if (ix->device < 64) attr_set[ix->device] = true;
+        }
+        const int64_t max_long = total / PC_RCOOP_CAP < m ? total / PC_RCOOP_CAP : m;
+        const int lgrid = (int)(max_long < (int64_t)ix->sm_count ? (max_long > 0 ? max_long : 1) : (int64_t)ix->sm_count);
+        pc_range_sort_long_kernel<<<lgrid, PC_RLONG_THREADS, PC_RLONG_CAP * sizeof(uint32_t), st>>>(d_long_count, d_long_list, d_off, d_out);
+        ix->launches++;
+        PC_CHECK_LAUNCH(ix);
+    }
     if (space == PC_HOST) {
         PC_CUDA(ix, cudaMemcpyAsync(out_idx, d_out, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         PC_CUDA(ix, cudaStreamSynchronize(st));

@@ -43,8 +43,9 @@ __device__ __forceinline__ void pc_sort_list(int32_t *__restrict__ a, int64_t n)
 // LIFO frontier in shared memory, every step each lane takes one of them and tests its two child boxes; a child that is a
 // leaf is scanned on the spot (only its own `count` points: its neighbours' points belong to other leaves) and the hits are
 // appended at ballot-computed positions, inner children are pushed.  The count pass and the fill pass are the same walk; the
-// fill pass then sorts its list by original index with a bitonic network in the same shared memory (lists up to 1024 hits;
-// longer ones fall back to a single-thread heap sort).
+// fill pass then sorts its list by original index with a bitonic network in the same shared memory (lists up to 1024 hits);
+// longer lists are queued and sorted afterwards by pc_range_sort_long_kernel, one CTA per list (up to 32768 hits in shared
+// memory; beyond that a single-thread heap sort -- a query that returns more than that is a job for pc_sphere_gather).
 #define PC_RCOOP_CAP 1024
 #define PC_RCOOP_WARPS 4
 
@@ -52,7 +53,8 @@ template <bool FILL>
 __global__ void __launch_bounds__(32 * PC_RCOOP_WARPS)
 pc_range_coop_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstride,
                      const double *__restrict__ range, int range_is_scalar,
-                     int64_t *__restrict__ counts, const int64_t *__restrict__ offsets, int32_t *__restrict__ out_idx)
+                     int64_t *__restrict__ counts, const int64_t *__restrict__ offsets, int32_t *__restrict__ out_idx,
+                     unsigned long long *__restrict__ long_count, int64_t *__restrict__ long_list)
 {
     __shared__ uint32_t s_front[PC_RCOOP_WARPS][PC_RCOOP_CAP];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -175,7 +177,44 @@ pc_range_coop_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstr
         }
         for (int i = lane; i < want; i += 32) out_idx[begin + i] = (int32_t)F[i];
     } else if (lane == 0) {
-        pc_sort_list(out_idx + begin, want);
+        long_list[atomicAdd(long_count, 1ull)] = k;            // sorted by pc_range_sort_long_kernel
+    }
+}
+
+// lists the fill pass could not sort inside a warp's shared memory: one CTA per queued list, bitonic network over up to
+// PC_RLONG_CAP ids in (dynamic) shared memory
+#define PC_RLONG_CAP 32768
+#define PC_RLONG_THREADS 1024
+
+__global__ void __launch_bounds__(PC_RLONG_THREADS)
+pc_range_sort_long_kernel(const unsigned long long *__restrict__ long_count, const int64_t *__restrict__ long_list,
+                          const int64_t *__restrict__ offsets, int32_t *__restrict__ out_idx)
+{
+    extern __shared__ uint32_t s_ids[];
+    const unsigned long long n_long = *long_count;
+    for (unsigned long long li = blockIdx.x; li < n_long; li += gridDim.x) {
+        const int64_t k = long_list[li];
+        const int64_t begin = offsets[k], want = offsets[k + 1] - begin;
+        if (want > PC_RLONG_CAP) {
+            if (threadIdx.x == 0) pc_sort_list(out_idx + begin, want);
+            continue;
+        }
+        int N = 2048;
+        while (N < want) N <<= 1;
+        for (int i = threadIdx.x; i < N; i += PC_RLONG_THREADS) s_ids[i] = i < want ? (uint32_t)out_idx[begin + i] : 0x7fffffffu;
+        __syncthreads();
+        for (int k2 = 2; k2 <= N; k2 <<= 1) {
+            for (int j = k2 >> 1; j > 0; j >>= 1) {
+                for (int t = threadIdx.x; t < (N >> 1); t += PC_RLONG_THREADS) {
+                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                    const uint32_t a = s_ids[i], b = s_ids[l];
+                    if ((a > b) == ((i & k2) == 0)) { s_ids[i] = b; s_ids[l] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        for (int i = threadIdx.x; i < want; i += PC_RLONG_THREADS) out_idx[begin + i] = (int32_t)s_ids[i];
+        __syncthreads();
     }
 }
 

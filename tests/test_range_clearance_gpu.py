@@ -85,6 +85,21 @@ def test_range_forest_vs_oracle_and_capacity(ix):
     assert e.value.code == -4
 
 
+def test_range_long_lists(ix):
+    """Lists beyond the in-warp sort (1024 hits) are sorted by one CTA each (up to 32768 hits), beyond that by the slow path:
+    every size class gives the brute-force set in ascending order."""
+    pts, half = synth.forest_cloud(150_000, seed=6, variant="J", return_half=True)
+    ix.build(pts)
+    q = synth.rrt_queries(24, half, seed=5)
+    radii = np.array([0.5, 2.0, 4.0, 6.0, 9.0, 12.0, 40.0, 5.0] * 3)
+    off, idx = ix.range(q, radii)
+    brute = _brute_range(pts, q, radii)
+    sizes = np.diff(off)
+    assert (sizes > 32768).any() and ((sizes > 1024) & (sizes <= 32768)).any() and (sizes <= 1024).any()
+    for k in range(len(q)):
+        assert len(brute[k]) == sizes[k] and (idx[off[k]:off[k + 1]] == brute[k]).all()
+
+
 # ---- clearance ---------------------------------------------------------------------------------------
 def _clearance_oracle(ko, P, tr, t_now, horizon, dt=0.02):
     first, order, T, off, coef = tr["traj_first_seg"], tr["seg_order"], tr["seg_T"], tr["seg_coef_off"], tr["coef"]
