@@ -200,6 +200,9 @@ int64_t pc_launch_count(const pc_index *ix, int reset);
  * (0 when the batch was not reordered) and of the search kernel, in ms. */
 int  pc_profile_enable(pc_index *ix, int on);
 int  pc_profile_last_batch(pc_index *ix, float *order_ms, float *search_ms);
+/* Detail of that ordering pass (ms): out[0] clearing the sort scratch, out[1] the key kernel (curve keys, sensing-range
+ * early-outs, compaction, digit histograms), out[2] the radix-sort passes. */
+int  pc_profile_last_order_detail(pc_index *ix, float out[3]);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,7 @@ ABI_SYMBOLS = [
     "pc_host_alloc", "pc_host_free",
     "pc_comm_unique_id", "pc_comm_init", "pc_comm_destroy", "pc_index_broadcast", "pc_shard_range",
     "pc_launch_count", "pc_profile_enable", "pc_profile_last_batch", "pc_batch_shard", "pc_index_set_radius_arith",
+    "pc_profile_last_order_detail",
 ]
 
 
@@ -110,5 +111,6 @@ def load():
     L.pc_index_set_radius_arith.argtypes = [vp, i32]
     L.pc_profile_enable.argtypes = [vp, i32]
     L.pc_profile_last_batch.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.pc_profile_last_order_detail.argtypes = [vp, C.POINTER(C.c_float)]
     _lib = L
     return L

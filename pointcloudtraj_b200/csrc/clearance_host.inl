@@ -79,7 +79,7 @@ extern "C" int pc_clearance_batch(pc_index *ix, const pc_traj *traj, int64_t n_t
         d_mr = (float *)p; p += b_out;
         d_ns = (int32_t *)p;
     }
-    pc_clearance_kernel<<<(int)n_traj, PC_CLR_THREADS, 0, st>>>(pc_tree_of(ix), R, d_traj, n_traj, d_order, d_T, d_coff, d_coef,
+    pc_clearance_kernel<<<(int)((n_traj + PC_CLR_THREADS / 32 - 1) / (PC_CLR_THREADS / 32)), PC_CLR_THREADS, 0, st>>>(pc_tree_of(ix), R, d_traj, n_traj, d_order, d_T, d_coff, d_coef,
                                                                dt, horizon, d_fh, d_mr, d_ns);
     ix->launches++;
     PC_CHECK_LAUNCH(ix);

@@ -1,13 +1,13 @@
 // clearance_kernels.cuh -- trajectory clearance: Bezier sampling fused with the nearest-obstacle query and a
-// per-trajectory reduction.  One CTA per trajectory.
+// per-trajectory reduction.  One warp per trajectory.
 //
 // Replaces checkSafeTrajectory (Planner/src/sim_planning_demo.cpp:729-781), getPosFromBezier (:715-727) and
 // safeRegionRrtStar::checkTrajPtCol (Planner/src/corridor_finder.cpp:412-416).
 //
 // The reference's time walk accumulates `t += 0.02` / `t_accu += 0.02` in doubles, so sample times are the
-// result of REPEATED addition (not k * dt).  To reproduce them bit for bit, thread 0 of the CTA runs the walk
+// result of REPEATED addition (not k * dt).  To reproduce them bit for bit, lane 0 of the trajectory's warp runs the walk
 // sequentially and publishes a schedule of (segment, t) pairs in shared memory, PC_CLR_CHUNK samples at a time;
-// all threads then evaluate the samples of the chunk in parallel.
+// the warp then evaluates the samples of the chunk 32 at a time.
 // Powers u^j: the reference calls libm's pow (sim_planning_demo.cpp:724), whose result is the correctly rounded power in
 // all but ~2^-15 of the cases (glibc's pow carries ~68 bits internally).  Here u^j is built by repeated multiplication in
 // double-double arithmetic (error-free products with fma, relative error < 2^-100 after 12 steps) and rounded to double
@@ -17,7 +17,7 @@
 #include "query_kernels.cuh"
 
 #define PC_CLR_THREADS 128
-#define PC_CLR_CHUNK 512
+#define PC_CLR_CHUNK 128
 #define PC_MAX_ORDER 12
 
 __constant__ double pc_binom[PC_MAX_ORDER + 1][PC_MAX_ORDER + 1];
@@ -57,6 +57,11 @@ __device__ __forceinline__ void pc_bezier_pos(const double *__restrict__ c, int 
     }
 }
 
+// One WARP per trajectory (four per CTA).  Lane 0 replays the reference's time walk for the next PC_CLR_CHUNK samples into
+// the warp's slice of shared memory, then the warp evaluates them 32 at a time: Bezier position in fp64, float32 cast, and the
+// packet walk for the 32 consecutive samples (a few centimetres apart -- ideal packets).  No CTA-wide barrier: while one warp's
+// lane 0 walks (a chain of dependent fp64 additions), the other warps of the SM evaluate.  (Round 1 ran one CTA per trajectory
+// with thread 0 walking while 127 threads waited at a barrier: issue slots 37 % busy, profiles/r2_full_pc_clearance_kernel.txt.)
 __global__ void __launch_bounds__(PC_CLR_THREADS)
 pc_clearance_kernel(pc_tree T, pc_radius_dev R, const pc_traj_dev *__restrict__ traj, int64_t n_traj,
                     const int32_t *__restrict__ seg_order, const double *__restrict__ seg_T,
@@ -64,50 +69,46 @@ pc_clearance_kernel(pc_tree T, pc_radius_dev R, const pc_traj_dev *__restrict__ 
                     double dt, double horizon,
                     int32_t *__restrict__ out_first_hit, float *__restrict__ out_min_radius, int32_t *__restrict__ out_n_samples)
 {
-    __shared__ double s_t[PC_CLR_CHUNK];
-    __shared__ int32_t s_seg[PC_CLR_CHUNK];
-    __shared__ int s_count, s_done;
-    __shared__ int s_first_hit;
-    __shared__ double s_warp_min[PC_CLR_THREADS / 32];
-
-    const int64_t tr = blockIdx.x;
+    __shared__ double s_t[PC_CLR_THREADS / 32][PC_CLR_CHUNK];
+    __shared__ int32_t s_seg[PC_CLR_THREADS / 32][PC_CLR_CHUNK];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t tr = (int64_t)blockIdx.x * (PC_CLR_THREADS / 32) + w;
     if (tr >= n_traj) return;
     const pc_traj_dev tj = traj[tr];
     const int32_t seg0 = tj.first_seg, nseg = tj.num_seg;
 
-    // walk state (thread 0 only), sim_planning_demo.cpp:735-749
+    // walk state (lane 0 only), sim_planning_demo.cpp:735-749
     int i = 0;
     double tt = 0.0, t_accu = 0.0;
-    if (threadIdx.x == 0) {
+    if (lane == 0) {
         double t_s = tj.t_now > 0.0 ? tj.t_now : 0.0;
         for (i = 0; i < nseg; ++i) {
             if (t_s > seg_T[seg0 + i] && i + 1 < nseg) t_s = __dsub_rn(t_s, seg_T[seg0 + i]);
             else break;
         }
         tt = t_s;
-        s_first_hit = 0x7fffffff;
     }
     double my_min = INFINITY;
+    int my_first = 0x7fffffff;
     int64_t chunk_base = 0;
     for (;;) {
-        if (threadIdx.x == 0) {
-            int cnt = 0;
+        int cnt = 0, done = 0;
+        if (lane == 0) {
             while (i < nseg && cnt < PC_CLR_CHUNK) {
                 const double Ti = seg_T[seg0 + i];
                 if (!(tt < Ti)) { i++; tt = 0.0; continue; }
                 t_accu = __dadd_rn(t_accu, dt);
                 if (t_accu > horizon) { i++; tt = 0.0; continue; }
-                s_t[cnt] = tt; s_seg[cnt] = seg0 + i; cnt++;
+                s_t[w][cnt] = tt; s_seg[w][cnt] = seg0 + i; cnt++;
                 tt = __dadd_rn(tt, dt);
             }
-            s_count = cnt;
-            s_done = (i >= nseg);
+            done = (i >= nseg);
         }
-        __syncthreads();
-        const int cnt = s_count, done = s_done;      // read BEFORE thread 0 can start publishing the next chunk
-        // a warp takes 32 CONSECUTIVE samples: they are a few centimetres apart, i.e. an ideal packet
-        for (int base = (threadIdx.x >> 5) * 32; base < cnt; base += PC_CLR_THREADS) {
-            const int k = base + (threadIdx.x & 31);
+        __syncwarp();
+        cnt = __shfl_sync(PC_FULL_MASK, cnt, 0);
+        done = __shfl_sync(PC_FULL_MASK, done, 0);
+        for (int base = 0; base < cnt; base += 32) {
+            const int k = base + lane;
             const bool have = k < cnt;
             double radius = INFINITY;
             pc_best b[1];
@@ -115,10 +116,10 @@ pc_clearance_kernel(pc_tree T, pc_radius_dev R, const pc_traj_dev *__restrict__ 
             float qv[1][3] = { { 0.f, 0.f, 0.f } };
             bool search = false;
             if (have) {
-                const int32_t sg = s_seg[k];
+                const int32_t sg = s_seg[w][k];
                 const double Ti = seg_T[sg];
                 double pos[3];
-                pc_bezier_pos(coef + seg_coef_off[sg], seg_order[sg], __ddiv_rn(s_t[k], Ti), Ti, pos);
+                pc_bezier_pos(coef + seg_coef_off[sg], seg_order[sg], __ddiv_rn(s_t[w][k], Ti), Ti, pos);
                 if (T.n_points == 0 || pc_radius_early_out(pos[0], pos[1], pos[2], R)) {
                     radius = __dsub_rn(R.max_radius, R.search_margin);
                 } else {
@@ -127,27 +128,25 @@ pc_clearance_kernel(pc_tree T, pc_radius_dev R, const pc_traj_dev *__restrict__ 
                     if (search) b[0].thr = R.bound_thr;
                 }
             }
-            pc_packet_traverse<1>(T, qv, b, threadIdx.x & 31);
+            pc_packet_traverse<1>(T, qv, b, lane);
             if (have) {
                 if (search || !(radius < INFINITY)) radius = pc_radius_epilogue(b[0], R);
                 my_min = fmin(my_min, radius);
-                if (radius < 0.0) atomicMin(&s_first_hit, (int)(chunk_base + k));
+                if (radius < 0.0) my_first = min(my_first, (int)(chunk_base + k));
             }
         }
         chunk_base += cnt;
-        __syncthreads();
+        __syncwarp();                       // the chunk's schedule is consumed before lane 0 overwrites it
         if (done) break;
     }
-    // block reduction of the minimum radius
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) my_min = fmin(my_min, __shfl_xor_sync(PC_FULL_MASK, my_min, o));
-    if ((threadIdx.x & 31) == 0) s_warp_min[threadIdx.x >> 5] = my_min;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double mn = s_warp_min[0];
-        for (int w = 1; w < PC_CLR_THREADS / 32; w++) mn = fmin(mn, s_warp_min[w]);
-        if (out_min_radius) out_min_radius[tr] = (float)mn;
-        if (out_first_hit) out_first_hit[tr] = s_first_hit == 0x7fffffff ? -1 : s_first_hit;
+    for (int o = 16; o > 0; o >>= 1) {
+        my_min = fmin(my_min, __shfl_xor_sync(PC_FULL_MASK, my_min, o));
+        my_first = min(my_first, __shfl_xor_sync(PC_FULL_MASK, my_first, o));
+    }
+    if (lane == 0) {
+        if (out_min_radius) out_min_radius[tr] = (float)my_min;
+        if (out_first_hit) out_first_hit[tr] = my_first == 0x7fffffff ? -1 : my_first;
         if (out_n_samples) out_n_samples[tr] = (int32_t)chunk_base;
     }
 }

@@ -47,6 +47,7 @@ struct pc_lane {
     cudaStream_t os = nullptr;                               // stream the current batch's ordering pass runs on
     cudaEvent_t ev_deps = nullptr, ev_ordered = nullptr;
     cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr;   // profiling: batch start / ordered / searched
+    cudaEvent_t ta = nullptr, tb = nullptr;                 // profiling detail: scratch cleared / keys made (then the sort up to t1)
 };
 
 struct pc_index {
@@ -101,6 +102,7 @@ struct pc_index {
     uint32_t *grid_cell_start = nullptr; int64_t grid_cells_cap = 0;
     float4 *grid_points = nullptr; int64_t grid_points_cap = 0;
     bool onesweep = true;              // PC_ONESWEEP=0: the three-kernel-per-pass radix sort (radix_sort.cuh)
+    int key_ctas_per_sm = 0;           // occupancy of the key kernel (queried once)
     int sort_items = 16;               // keys per thread of the batch-ordering sort (PC_SORT_ITEMS = 8 | 16)
     int coop_group = 0;                     // lanes per query of the small-batch kernel: 0 = by batch size, else 32 / 16 / 8 (PC_COOP_GROUP)
     int64_t coop_g32_max = 24576, coop_g16_max = 65536;  // batch sizes up to which 32 / 16 lanes per query are used (measured:
@@ -257,6 +259,8 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
             TRY(cudaEventCreate(&ix->lane[l].t0));
             TRY(cudaEventCreate(&ix->lane[l].t1));
             TRY(cudaEventCreate(&ix->lane[l].t2));
+            TRY(cudaEventCreate(&ix->lane[l].ta));
+            TRY(cudaEventCreate(&ix->lane[l].tb));
             TRY(cudaMalloc((void **)&ix->lane[l].digit_total, RS_RADIX * sizeof(uint32_t)));
             TRY(cudaMalloc((void **)&ix->lane[l].counter, 2 * sizeof(unsigned long long)));
         }
@@ -290,6 +294,8 @@ extern "C" void pc_index_destroy(pc_index *ix)
         if (L.t0) cudaEventDestroy(L.t0);
         if (L.t1) cudaEventDestroy(L.t1);
         if (L.t2) cudaEventDestroy(L.t2);
+        if (L.ta) cudaEventDestroy(L.ta);
+        if (L.tb) cudaEventDestroy(L.tb);
     }
     if (ix->h_bbox) cudaFreeHost(ix->h_bbox);
     if (ix->tiny_q) cudaFreeHost(ix->tiny_q);
@@ -576,18 +582,29 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
         L.per_cell = per_cell;
     }
     const int drop = 30 - bits > 0 ? 30 - bits : 0;     // 24-bit sort = top 24 curve bits, 32-bit sort = all 30
-    const int64_t key_ctas = (m + 255) / 256;
-    const int grid = (int)(key_ctas < (int64_t)ix->sm_count * 8 ? key_ctas : (int64_t)ix->sm_count * 8);
+    // one wave of CTAs (as many as the key kernel's occupancy allows), each striding over the batch
+    if (ix->key_ctas_per_sm == 0) {
+        int a = 0, b = 0;
+        PC_CUDA(ix, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, pc_query_key_kernel<PC_KIND_RADIUS>, 256, 0));
+        PC_CUDA(ix, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, pc_query_key_kernel<PC_KIND_NEAREST>, 256, 0));
+        ix->key_ctas_per_sm = a < b ? a : b;
+        if (ix->key_ctas_per_sm < 1) ix->key_ctas_per_sm = 1;
+    }
+    const int64_t key_ctas = (m + 256 * PC_KEY_ITEMS - 1) / (256 * PC_KEY_ITEMS);
+    const int grid = (int)(key_ctas < (int64_t)ix->sm_count * ix->key_ctas_per_sm ? key_ctas : (int64_t)ix->sm_count * ix->key_ctas_per_sm);
     const int items = ix->sort_items;
     const bool fused_hist = ix->onesweep && m < OS_MAX_N;
     uint32_t *gh = fused_hist ? os_ghist(L.tile_hist) : nullptr;
     if (fused_hist) os_clear(L.tile_hist, m, items, bits / 8, L.os);
+    const bool prof = ix->profile && &L == &ix->lane[0];
+    if (prof) PC_CUDA(ix, cudaEventRecord(L.ta, L.os));
     if (A.kind == PC_Q_RADIUS)
         pc_query_key_kernel<PC_KIND_RADIUS><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n, gh, bits / 8);
     else
         pc_query_key_kernel<PC_KIND_NEAREST><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n, gh, bits / 8);
     ix->launches++;
     PC_CHECK_LAUNCH(ix);
+    if (prof) PC_CUDA(ix, cudaEventRecord(L.tb, L.os));
     // only the L.counter[1] compacted entries (device-side count <= m) are sorted
     int which = items == 8 ? pc_sort_pairs<uint32_t, 8>(ix, L.keys_a, L.vals_a, L.keys_b, L.vals_b, m, 0, bits, L.tile_hist, L.digit_total, L.os, L.counter + 1, fused_hist)
                            : pc_sort_pairs<uint32_t, 16>(ix, L.keys_a, L.vals_a, L.keys_b, L.vals_b, m, 0, bits, L.tile_hist, L.digit_total, L.os, L.counter + 1, fused_hist);
@@ -718,6 +735,23 @@ extern "C" int pc_profile_enable(pc_index *ix, int on)
     if (!ix) return PC_EINVAL;
     ix->profile = on != 0;
     ix->profiled = false;
+    return PC_OK;
+}
+
+// detail of the ordering pass of the last profiled, ORDERED PC_DEVICE batch: out[0] = clearing the sort scratch, out[1] = key
+// kernel (curve keys, early-outs, compaction, digit histograms), out[2] = the radix sort passes
+extern "C" int pc_profile_last_order_detail(pc_index *ix, float out[3])
+{
+    if (!ix || !out) return PC_EINVAL;
+    if (!ix->profiled) return pc_fail(ix, PC_EINVAL, "pc_profile_last_order_detail: no profiled PC_DEVICE batch yet");
+    PC_CUDA(ix, cudaSetDevice(ix->device));
+    pc_lane &L = ix->lane[0];
+    PC_CUDA(ix, cudaEventSynchronize(L.t2));
+    if (cudaEventElapsedTime(&out[0], L.t0, L.ta) != cudaSuccess || cudaEventElapsedTime(&out[1], L.ta, L.tb) != cudaSuccess ||
+        cudaEventElapsedTime(&out[2], L.tb, L.t1) != cudaSuccess) {
+        cudaGetLastError();
+        return pc_fail(ix, PC_EINVAL, "pc_profile_last_order_detail: the last batch was not ordered");
+    }
     return PC_OK;
 }
 

@@ -497,6 +497,8 @@ __device__ __forceinline__ int pc_shard_level(const uint32_t *__restrict__ bbox,
     return 2;
 }
 
+#define PC_KEY_ITEMS 8          // queries per thread and round of the key kernel: eight loads in flight, one atomic per 2048 queries
+
 template <int KIND>
 __global__ void __launch_bounds__(256)
 pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const uint32_t *__restrict__ bbox, int drop_bits,
@@ -506,44 +508,57 @@ pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
 {
     // ghist (nullable): digit histograms of the hist_passes 8-bit passes that will sort the compacted keys (radix_sort.cuh,
     // onesweep path) -- counted here, while the key is in a register, instead of by a separate pass over the keys.  The
-    // grid is a few CTAs per SM, each striding over the batch, so that a CTA flushes its histograms to global memory once.
+    // grid is one wave of CTAs, each striding over the batch in rounds of 256 x PC_KEY_ITEMS queries, so that a CTA flushes
+    // its histograms to global memory once and reserves its output range with one atomic per round.
     __shared__ uint32_t s_hist[4][RS_RADIX];
     __shared__ uint32_t s_warp[8];
     __shared__ unsigned long long s_base;
     __shared__ int s_shard_shift;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = pc_lanemask_lt();
     if (ghist) for (int j = threadIdx.x; j < hist_passes * RS_RADIX; j += 256) (&s_hist[0][0])[j] = 0;
     if (shard_n > 1 && threadIdx.x == 0) s_shard_shift = 10 - pc_shard_level(bbox, m);      // cell coordinate bits dropped per axis
     __syncthreads();
     const pc_frame f = pc_make_frame(bbox, 10);
-    for (int64_t base = (int64_t)blockIdx.x * 256; base < m; base += (int64_t)gridDim.x * 256) {
-        const int64_t i = base + threadIdx.x;
-        bool search = false;
-        uint32_t key = 0;
-        if (i < m) {
-            const float *p = q + i * qstride;
-            const float x = p[0], y = p[1], z = p[2];
-            const uint32_t cx = pc_cell_coord(x, f.lo[0], f.inv_cell, f.max_cell), cy = pc_cell_coord(y, f.lo[1], f.inv_cell, f.max_cell),
-                           cz = pc_cell_coord(z, f.lo[2], f.inv_cell, f.max_cell);
-            search = true;
-            if (shard_n > 1) {
-                const int sh = s_shard_shift;
-                uint32_t h = (cx >> sh) | ((cy >> sh) << 10) | ((cz >> sh) << 20);       // the cell, then a murmur-style finaliser
-                h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
-                search = (int)(h % (uint32_t)shard_n) == shard_rank;
-            }
-            if (search) {
-                if (KIND == PC_KIND_RADIUS && pc_radius_early_out((double)x, (double)y, (double)z, R)) {
-                    search = false;
-                    pc_write_trivial<KIND>(R, (uint32_t)i, out_idx, out_f);
-                }
-                key = pc_hilbert30_cells(cx, cy, cz) >> drop_bits;
-            }
+    const int sh = shard_n > 1 ? s_shard_shift : 0;
+    for (int64_t base = (int64_t)blockIdx.x * (256 * PC_KEY_ITEMS); base < m; base += (int64_t)gridDim.x * (256 * PC_KEY_ITEMS)) {
+        float x[PC_KEY_ITEMS], y[PC_KEY_ITEMS], z[PC_KEY_ITEMS];
+#pragma unroll
+        for (int j = 0; j < PC_KEY_ITEMS; j++) {
+            const int64_t i = base + j * 256 + threadIdx.x;
+            if (i < m) { const float *p = q + i * qstride; x[j] = p[0]; y[j] = p[1]; z[j] = p[2]; }
+            else x[j] = y[j] = z[j] = 0.f;
         }
-        // compact the queries that still need a search: only those are sorted and searched.  One atomic per 256 queries; the
-        // slot a query lands in depends on CTA scheduling, which changes the composition of packets but never a result.
-        const uint32_t mask = __ballot_sync(PC_FULL_MASK, search);
-        if (lane == 0) s_warp[warp] = __popc(mask);
+        uint32_t key[PC_KEY_ITEMS], mask[PC_KEY_ITEMS];
+        uint32_t warp_total = 0;
+#pragma unroll
+        for (int j = 0; j < PC_KEY_ITEMS; j++) {
+            const int64_t i = base + j * 256 + threadIdx.x;
+            bool search = i < m;
+            key[j] = 0;
+            if (search) {
+                const uint32_t cx = pc_cell_coord(x[j], f.lo[0], f.inv_cell, f.max_cell), cy = pc_cell_coord(y[j], f.lo[1], f.inv_cell, f.max_cell),
+                               cz = pc_cell_coord(z[j], f.lo[2], f.inv_cell, f.max_cell);
+                if (shard_n > 1) {
+                    uint32_t h = (cx >> sh) | ((cy >> sh) << 10) | ((cz >> sh) << 20);       // the cell, then a murmur-style finaliser
+                    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+                    search = (int)(h % (uint32_t)shard_n) == shard_rank;
+                }
+                if (search) {
+                    if (KIND == PC_KIND_RADIUS && pc_radius_early_out((double)x[j], (double)y[j], (double)z[j], R)) {
+                        search = false;
+                        pc_write_trivial<KIND>(R, (uint32_t)i, out_idx, out_f);
+                    } else {
+                        key[j] = pc_hilbert30_cells(cx, cy, cz) >> drop_bits;
+                    }
+                }
+            }
+            mask[j] = __ballot_sync(PC_FULL_MASK, search);
+            warp_total += __popc(mask[j]);
+        }
+        // compact the queries that still need a search: only those are sorted and searched.  The slot a query lands in depends
+        // on CTA scheduling, which changes the composition of packets but never a result.
+        if (lane == 0) s_warp[warp] = warp_total;
         __syncthreads();
         if (threadIdx.x == 0) {
             uint32_t tot = 0;
@@ -551,11 +566,16 @@ pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
             s_base = tot ? atomicAdd(n_search, (unsigned long long)tot) : 0ull;
         }
         __syncthreads();
-        if (search) {
-            const unsigned long long pos = s_base + s_warp[warp] + __popc(mask & pc_lanemask_lt());
-            keys[pos] = key;
-            vals[pos] = (uint32_t)i;
-            if (ghist) for (int p = 0; p < hist_passes; p++) atomicAdd(&s_hist[p][(key >> (8 * p)) & (RS_RADIX - 1)], 1u);
+        unsigned long long pos = s_base + s_warp[warp];
+#pragma unroll
+        for (int j = 0; j < PC_KEY_ITEMS; j++) {
+            if ((mask[j] >> lane) & 1u) {
+                const unsigned long long p = pos + __popc(mask[j] & lt);
+                keys[p] = key[j];
+                vals[p] = (uint32_t)(base + j * 256 + threadIdx.x);
+                if (ghist) for (int h = 0; h < hist_passes; h++) atomicAdd(&s_hist[h][(key[j] >> (8 * h)) & (RS_RADIX - 1)], 1u);
+            }
+            pos += __popc(mask[j]);
         }
         __syncthreads();            // s_warp / s_base are rewritten by the next round
     }

@@ -67,7 +67,7 @@ def run(queries=10_000_000):
             assert L.pc_index_build(h, C.c_void_p(t_pts.data_ptr()), len(pts), 3, 1) == 0
             L.pc_index_last_build_ms(h, C.byref(ms)); b1.append(ms.value)
         L.pc_profile_enable(h, 1)
-        res = {}
+        res, detail = {}, {}
         for kind in ("r", "n"):
             order, search = [], []
             for _ in range(6):
@@ -79,13 +79,18 @@ def run(queries=10_000_000):
                 a, b = C.c_float(), C.c_float()
                 L.pc_profile_last_batch(h, C.byref(a), C.byref(b))
                 order.append(a.value); search.append(b.value)
+                if hasattr(L, "pc_profile_last_order_detail"):
+                    d3 = (C.c_float * 3)()
+                    if L.pc_profile_last_order_detail(h, d3) == 0:
+                        detail[kind] = tuple(d3)
             res[kind] = (float(np.median(order[1:])), float(np.median(search[1:])))
         torch.cuda.synchronize()
         if ref is None:
             ref = (t_r.clone(), t_i.clone(), t_d.clone())
         same = bool((t_r == ref[0]).all().item() and (t_i == ref[1]).all().item() and (t_d == ref[2]).all().item())
         L.pc_index_destroy(h)
-        print(f"{name:28s} {np.median(b1[1:]):8.3f} {np.median(bf[1:]):9.3f} {res['r'][0]:8.3f} {res['r'][1]:9.3f} {res['n'][0]:8.3f} {res['n'][1]:9.3f} {same}", flush=True)
+        print(f"{name:28s} {np.median(b1[1:]):8.3f} {np.median(bf[1:]):9.3f} {res['r'][0]:8.3f} {res['r'][1]:9.3f} {res['n'][0]:8.3f} {res['n'][1]:9.3f} {same}"
+              + "".join(f"  {k}: clear {v[0]:.3f} keys {v[1]:.3f} sort {v[2]:.3f}" for k, v in detail.items()), flush=True)
 
 
 if __name__ == "__main__":
