@@ -68,14 +68,15 @@ pc_grid_gather_kernel(const float *__restrict__ xyz, int stride, const uint32_t 
 
 __global__ void __launch_bounds__(PC_QUERY_THREADS)
 pc_radius_grid_kernel(pc_grid G, pc_radius_dev R, const float *__restrict__ q, int64_t m, int qstride,
-                      const uint32_t *__restrict__ perm, const unsigned long long *__restrict__ m_eff,
+                      const uint32_t *__restrict__ perm, const float4 *__restrict__ ordered, const unsigned long long *__restrict__ m_eff,
                       int32_t *__restrict__ out_idx, float *__restrict__ out_f)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m || (m_eff && t >= (int64_t)*m_eff)) return;
-    const uint32_t k = perm ? perm[t] : (uint32_t)t;
-    const float *qq = q + (size_t)k * qstride;
-    const float qx = qq[0], qy = qq[1], qz = qq[2];
+    uint32_t k;
+    float qx, qy, qz;
+    if (ordered) { const float4 v = __ldg(ordered + t); qx = v.x; qy = v.y; qz = v.z; k = __float_as_uint(v.w); }
+    else { k = perm ? perm[t] : (uint32_t)t; const float *qq = q + (size_t)k * qstride; qx = qq[0]; qy = qq[1]; qz = qq[2]; }
     if (!m_eff && pc_radius_early_out((double)qx, (double)qy, (double)qz, R)) { pc_write_trivial<PC_KIND_RADIUS>(R, k, out_idx, out_f); return; }
     pc_best b; b.d2 = INFINITY; b.idx = -1; b.thr = R.bound_thr;
     const int cx = pc_grid_coord(qx, G.lo[0], G.inv_h, G.n[0]), cy = pc_grid_coord(qy, G.lo[1], G.inv_h, G.n[1]),

@@ -41,6 +41,8 @@ struct pc_lane {
     uint32_t *tile_hist = nullptr; int64_t hist_cap = 0;
     uint32_t *digit_total = nullptr;
     unsigned long long *counter = nullptr;                   // [1]: queries that still need a search after the ordering pass
+    uint32_t *bins = nullptr; int64_t bins_cap = 0;          // cell-binning ordering: 2^bits counters / cursors + their tile sums
+    float4 *ordered = nullptr; int64_t ordered_cap = 0;      // cell-binning ordering: the batch gathered into cell order
     double per_cell = 0.0;                                   // last ordered batch: estimated queries per 1/256-extent cell
     cudaEvent_t done = nullptr;
     cudaStream_t order_stream = nullptr;                     // high-priority stream for the ordering pass of pipelined batches
@@ -102,7 +104,9 @@ struct pc_index {
     uint32_t *grid_cell_start = nullptr; int64_t grid_cells_cap = 0;
     float4 *grid_points = nullptr; int64_t grid_points_cap = 0;
     bool onesweep = true;              // PC_ONESWEEP=0: the three-kernel-per-pass radix sort (radix_sort.cuh)
-    int key_ctas_per_sm = 0;           // occupancy of the key kernel (queried once)
+    int key_ctas_per_sm = 0, sortkey_ctas_per_sm = 0;   // occupancy of the bin-count / key kernels (queried once)
+    int bin_bits = 0;                  // PC_BIN_BITS: log2 of the number of cells of the binning (0 = from the batch size)
+    bool order_bins = true;            // PC_ORDER_BINS=0: always radix-sort the batch instead of binning it by cell
     int sort_items = 16;               // keys per thread of the batch-ordering sort (PC_SORT_ITEMS = 8 | 16)
     int coop_group = 0;                     // lanes per query of the small-batch kernel: 0 = by batch size, else 32 / 16 / 8 (PC_COOP_GROUP)
     int64_t coop_g32_max = 24576, coop_g16_max = 65536;  // batch sizes up to which 32 / 16 lanes per query are used (measured:
@@ -221,6 +225,8 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         if (const char *v = getenv("PC_SORT_BITS")) { ix->sort_bits_auto = false; int b_ = atoi(v); ix->sort_bits = b_ <= 0 ? 0 : (b_ <= 16 ? 16 : (b_ <= 24 ? 24 : 32)); }
         if (const char *v = getenv("PC_HOST_RAMP")) ix->host_ramp = atoi(v) != 0;
         if (const char *v = getenv("PC_ONESWEEP")) ix->onesweep = atoi(v) != 0;
+        if (const char *v = getenv("PC_ORDER_BINS")) ix->order_bins = atoi(v) != 0;
+        if (const char *v = getenv("PC_BIN_BITS")) { int b_ = atoi(v); ix->bin_bits = b_ < 12 ? 0 : (b_ > PC_BIN_MAX_BITS ? PC_BIN_MAX_BITS : b_); }
         if (const char *v = getenv("PC_GRID")) ix->use_grid = atoi(v) != 0;
         if (const char *v = getenv("PC_GRID_CELL")) { double c_ = atof(v); if (c_ > 0.0) ix->grid_cell = c_; }
         if (const char *v = getenv("PC_SORT_ITEMS")) ix->sort_items = atoi(v) == 8 ? 8 : 16;
@@ -286,7 +292,7 @@ extern "C" void pc_index_destroy(pc_index *ix)
         if (L.stream && L.own_stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
         cudaFree(L.d_q); cudaFree(L.d_i32); cudaFree(L.d_f32);
         cudaFree(L.keys_a); cudaFree(L.keys_b); cudaFree(L.vals_a); cudaFree(L.vals_b);
-        cudaFree(L.tile_hist); cudaFree(L.digit_total); cudaFree(L.counter);
+        cudaFree(L.tile_hist); cudaFree(L.digit_total); cudaFree(L.counter); cudaFree(L.bins); cudaFree(L.ordered);
         if (L.done) cudaEventDestroy(L.done);
         if (L.ev_deps) cudaEventDestroy(L.ev_deps);
         if (L.ev_ordered) cudaEventDestroy(L.ev_ordered);
@@ -548,8 +554,9 @@ struct pc_qargs {
 // Morton-order a device-resident batch on lane L: *perm = permutation (device), L.counter[1] = number of leading
 // entries that still need a search (radius batches answer the sensing-range early-outs in this pass)
 static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const float *d_q, int64_t m, int qstride,
-                           int32_t *d_idx, float *d_f, const uint32_t **perm)
+                           int32_t *d_idx, float *d_f, const uint32_t **perm, const float4 **ordered)
 {
+    *perm = nullptr; *ordered = nullptr;
     if (m > L.sort_cap) {
         int64_t c = m;
         cudaFree(L.keys_a); cudaFree(L.keys_b); cudaFree(L.vals_a); cudaFree(L.vals_b);
@@ -581,22 +588,61 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
         bits = per_cell > 16.0 ? 32 : 24;
         L.per_cell = per_cell;
     }
+    const bool prof = ix->profile && &L == &ix->lane[0];
+    if (ix->order_bins && bits == 24 && m < ((int64_t)1 << 32) - 1) {
+        // cell binning (query_kernels.cuh): counting sort by the 21-bit Hilbert cell, the queries themselves gathered into
+        // cell order.  Taken whenever the density test would have picked the 24-bit radix sort.
+        // number of cells: about half the batch size (a handful of queries per occupied cell, like the 24-bit radix order),
+        // 2^18 .. 2^24; PC_BIN_BITS overrides
+        int bin_bits = ix->bin_bits;
+        if (bin_bits == 0) { bin_bits = 17; while (bin_bits < PC_BIN_MAX_BITS && ((int64_t)1 << (bin_bits + 2)) <= m) bin_bits++; }
+        const int64_t n_bins = (int64_t)1 << bin_bits;
+        int rcb = pc_grow(ix, &L.bins, &L.bins_cap, n_bins + n_bins / PC_BIN_SCAN_TILE + 64);
+        if (rcb != PC_OK) return rcb;
+        if ((rcb = pc_grow(ix, &L.ordered, &L.ordered_cap, m)) != PC_OK) return rcb;
+        if (ix->key_ctas_per_sm == 0) {
+            int a = 0, b = 0;
+            PC_CUDA(ix, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, pc_bin_count_kernel<PC_KIND_RADIUS>, 256, 0));
+            PC_CUDA(ix, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, pc_bin_count_kernel<PC_KIND_NEAREST>, 256, 0));
+            ix->key_ctas_per_sm = a < b ? a : b;
+            if (ix->key_ctas_per_sm < 1) ix->key_ctas_per_sm = 1;
+        }
+        const int64_t rounds = (m + 256 * PC_KEY_ITEMS - 1) / (256 * PC_KEY_ITEMS);
+        const int64_t wave = (int64_t)ix->sm_count * ix->key_ctas_per_sm;
+        const int grid = (int)(rounds < wave ? rounds : wave);
+        uint32_t *tile_sum = L.bins + n_bins;
+        const int n_tiles = (int)(n_bins / PC_BIN_SCAN_TILE);
+        PC_CUDA(ix, cudaMemsetAsync(L.bins, 0, (size_t)n_bins * sizeof(uint32_t), L.os));
+        if (prof) PC_CUDA(ix, cudaEventRecord(L.ta, L.os));
+        if (A.kind == PC_Q_RADIUS)
+            pc_bin_count_kernel<PC_KIND_RADIUS><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, A.R, d_idx, d_f, L.keys_a, L.bins, bin_bits, ix->shard_rank, ix->shard_n);
+        else
+            pc_bin_count_kernel<PC_KIND_NEAREST><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, A.R, d_idx, d_f, L.keys_a, L.bins, bin_bits, ix->shard_rank, ix->shard_n);
+        if (prof) PC_CUDA(ix, cudaEventRecord(L.tb, L.os));
+        pc_bin_scan_tiles<<<n_tiles, 256, 0, L.os>>>(L.bins, tile_sum);
+        pc_bin_scan_top<<<1, 1024, 0, L.os>>>(tile_sum, n_tiles, L.counter + 1);
+        pc_bin_scan_apply<<<n_tiles, 256, 0, L.os>>>(L.bins, tile_sum);
+        pc_bin_scatter_kernel<<<grid, 256, 0, L.os>>>(d_q, m, qstride, L.keys_a, L.bins, L.ordered);
+        ix->launches += 5;
+        PC_CHECK_LAUNCH(ix);
+        *ordered = L.ordered;
+        return PC_OK;
+    }
     const int drop = 30 - bits > 0 ? 30 - bits : 0;     // 24-bit sort = top 24 curve bits, 32-bit sort = all 30
     // one wave of CTAs (as many as the key kernel's occupancy allows), each striding over the batch
-    if (ix->key_ctas_per_sm == 0) {
+    if (ix->sortkey_ctas_per_sm == 0) {
         int a = 0, b = 0;
         PC_CUDA(ix, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, pc_query_key_kernel<PC_KIND_RADIUS>, 256, 0));
         PC_CUDA(ix, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, pc_query_key_kernel<PC_KIND_NEAREST>, 256, 0));
-        ix->key_ctas_per_sm = a < b ? a : b;
-        if (ix->key_ctas_per_sm < 1) ix->key_ctas_per_sm = 1;
+        ix->sortkey_ctas_per_sm = a < b ? a : b;
+        if (ix->sortkey_ctas_per_sm < 1) ix->sortkey_ctas_per_sm = 1;
     }
     const int64_t key_ctas = (m + 256 * PC_KEY_ITEMS - 1) / (256 * PC_KEY_ITEMS);
-    const int grid = (int)(key_ctas < (int64_t)ix->sm_count * ix->key_ctas_per_sm ? key_ctas : (int64_t)ix->sm_count * ix->key_ctas_per_sm);
+    const int grid = (int)(key_ctas < (int64_t)ix->sm_count * ix->sortkey_ctas_per_sm ? key_ctas : (int64_t)ix->sm_count * ix->sortkey_ctas_per_sm);
     const int items = ix->sort_items;
     const bool fused_hist = ix->onesweep && m < OS_MAX_N;
     uint32_t *gh = fused_hist ? os_ghist(L.tile_hist) : nullptr;
     if (fused_hist) os_clear(L.tile_hist, m, items, bits / 8, L.os);
-    const bool prof = ix->profile && &L == &ix->lane[0];
     if (prof) PC_CUDA(ix, cudaEventRecord(L.ta, L.os));
     if (A.kind == PC_Q_RADIUS)
         pc_query_key_kernel<PC_KIND_RADIUS><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n, gh, bits / 8);
@@ -661,13 +707,14 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
         L.os = L.order_stream;
     }
     const uint32_t *perm = nullptr;
+    const float4 *ordered = nullptr;
     const unsigned long long *m_eff = nullptr;
     const bool prof = ix->profile && &L == &ix->lane[0];
     if (prof) PC_CUDA(ix, cudaEventRecord(L.t0, L.stream));
     // counter[1]: queries that need a search after the ordering pass
     PC_CUDA(ix, cudaMemsetAsync(L.counter, 0, 2 * sizeof(unsigned long long), L.os));
     if (pc_want_sort(ix, A.flags, m)) {
-        int rc = pc_sort_queries(ix, L, A, d_q, m, qstride, d_idx, d_f, &perm);
+        int rc = pc_sort_queries(ix, L, A, d_q, m, qstride, d_idx, d_f, &perm, &ordered);
         if (rc != PC_OK) return rc;
         m_eff = L.counter + 1;
     }
@@ -680,32 +727,33 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
     // dense batches (>= 3 queries per cell of 1/256 of the cloud's extent): 64-query packets, two queries per lane
     // (profiles/r1_sweep5*: +10 % radius, +18 % nearest at 10 M queries; -3 % at 2 M, hence the threshold)
     const bool two_per_lane = ix->query_kernel == 4 || (ix->query_kernel == 3 && ix->query_kernel_auto && L.per_cell >= 3.0);
-    if (ix->grid_ready && perm && A.kind == PC_Q_RADIUS && A.R.bounded) {
+    const bool is_ordered = perm || ordered;
+    if (ix->grid_ready && is_ordered && A.kind == PC_Q_RADIUS && A.R.bounded) {
         // experiment (PC_GRID=1): ring search over the voxel grid instead of the tree walk
         const int grid = (int)((m + PC_QUERY_THREADS - 1) / PC_QUERY_THREADS);
-        pc_radius_grid_kernel<<<grid, PC_QUERY_THREADS, 0, L.stream>>>(ix->grid, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
-    } else if (ix->query_kernel >= 3 && perm) {
+        pc_radius_grid_kernel<<<grid, PC_QUERY_THREADS, 0, L.stream>>>(ix->grid, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
+    } else if (ix->query_kernel >= 3 && is_ordered) {
         // curve-ordered batch: one warp walks the tree once for its 32 or 64 neighbouring queries
         const int per_cta = (two_per_lane ? 2 : 1) * PC_QUERY_THREADS;
         const int grid = (int)((m + per_cta - 1) / per_cta);
         if (two_per_lane) {
             if (A.kind == PC_Q_NEAREST)
-                pc_query_packet_kernel<PC_KIND_NEAREST, 2><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
+                pc_query_packet_kernel<PC_KIND_NEAREST, 2><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
             else
-                pc_query_packet_kernel<PC_KIND_RADIUS, 2><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
+                pc_query_packet_kernel<PC_KIND_RADIUS, 2><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
         } else if (A.kind == PC_Q_NEAREST)
-            pc_query_packet_kernel<PC_KIND_NEAREST, 1><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
+            pc_query_packet_kernel<PC_KIND_NEAREST, 1><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
         else
-            pc_query_packet_kernel<PC_KIND_RADIUS, 1><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
-    } else if (ix->query_kernel >= 3 && !perm && m <= ix->coop_max) {
+            pc_query_packet_kernel<PC_KIND_RADIUS, 1><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
+    } else if (ix->query_kernel >= 3 && !is_ordered && m <= ix->coop_max) {
         // small unordered batch: one warp per query (a thread-per-query search is a chain of dependent loads)
         pc_launch_coop(ix, A, T, d_q, m, qstride, d_idx, d_f, L.stream);
     } else {
         const int grid = (int)((m + PC_QUERY_THREADS - 1) / PC_QUERY_THREADS);
         if (A.kind == PC_Q_NEAREST)
-            pc_query_simple_kernel<PC_KIND_NEAREST><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
+            pc_query_simple_kernel<PC_KIND_NEAREST><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
         else
-            pc_query_simple_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, m_eff, d_idx, d_f);
+            pc_query_simple_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
     }
     ix->launches++;
     PC_CHECK_LAUNCH(ix);
@@ -784,9 +832,9 @@ static int pc_tiny_host_batch(pc_index *ix, const pc_qargs &A, const float *q, i
     if (ix->query_kernel == 1) {             // PC_QUERY_KERNEL=1: one thread per query, for comparison
         const int grid = (int)((m + PC_QUERY_THREADS - 1) / PC_QUERY_THREADS);
         if (A.kind == PC_Q_NEAREST)
-            pc_query_simple_kernel<PC_KIND_NEAREST><<<grid, PC_QUERY_THREADS, 0, ix->stream>>>(T, A.R, ix->tiny_q_dev, m, qs, nullptr, nullptr, d_i, d_f);
+            pc_query_simple_kernel<PC_KIND_NEAREST><<<grid, PC_QUERY_THREADS, 0, ix->stream>>>(T, A.R, ix->tiny_q_dev, m, qs, nullptr, nullptr, nullptr, d_i, d_f);
         else
-            pc_query_simple_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, ix->stream>>>(T, A.R, ix->tiny_q_dev, m, qs, nullptr, nullptr, d_i, d_f);
+            pc_query_simple_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, ix->stream>>>(T, A.R, ix->tiny_q_dev, m, qs, nullptr, nullptr, nullptr, d_i, d_f);
     } else {
         // one warp per query: the search of a single query is a chain of dependent loads, the warp shortens it
         pc_launch_coop(ix, A, T, ix->tiny_q_dev, m, qs, d_i, d_f, ix->stream);

@@ -219,19 +219,21 @@ __device__ __forceinline__ void pc_write_result(const pc_radius_dev &R, const pc
 
 // ---- one thread per query -------------------------------------------------------------------------------------------
 // perm (nullable): process query perm[t] in slot t (curve-ordered batches); results go to the original slot.
+// ordered (nullable, instead of perm): slot t holds the query itself, (x, y, z, original slot) -- the cell-binned batch.
 // m_eff (nullable): device-side number of leading entries of perm that need a search (the rest were answered by the
 // ordering pass).
 template <int KIND>
 __global__ void __launch_bounds__(PC_QUERY_THREADS)
 pc_query_simple_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, int64_t m, int qstride,
-                       const uint32_t *__restrict__ perm, const unsigned long long *__restrict__ m_eff,
+                       const uint32_t *__restrict__ perm, const float4 *__restrict__ ordered, const unsigned long long *__restrict__ m_eff,
                        int32_t *__restrict__ out_idx, float *__restrict__ out_f)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= m || (m_eff && t >= (int64_t)*m_eff)) return;
-    const uint32_t k = perm ? perm[t] : (uint32_t)t;
-    const float *qq = q + (size_t)k * qstride;
-    const float qx = qq[0], qy = qq[1], qz = qq[2];
+    uint32_t k;
+    float qx, qy, qz;
+    if (ordered) { const float4 v = __ldg(ordered + t); qx = v.x; qy = v.y; qz = v.z; k = __float_as_uint(v.w); }
+    else { k = perm ? perm[t] : (uint32_t)t; const float *qq = q + (size_t)k * qstride; qx = qq[0]; qy = qq[1]; qz = qq[2]; }
     bool search = T.n_points > 0;
     if (KIND == PC_KIND_RADIUS && search && !m_eff && pc_radius_early_out((double)qx, (double)qy, (double)qz, R)) search = false;
     if (!search) { pc_write_trivial<KIND>(R, k, out_idx, out_f); return; }
@@ -326,7 +328,7 @@ __device__ __forceinline__ void pc_packet_traverse(const pc_tree &T, const float
 template <int KIND, int NQ>
 __global__ void __launch_bounds__(PC_QUERY_THREADS, PC_PACKET_MIN_CTAS)
 pc_query_packet_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, int64_t m, int qstride,
-                       const uint32_t *__restrict__ perm, const unsigned long long *__restrict__ m_eff,
+                       const uint32_t *__restrict__ perm, const float4 *__restrict__ ordered, const unsigned long long *__restrict__ m_eff,
                        int32_t *__restrict__ out_idx, float *__restrict__ out_f)
 {
     const int lane = threadIdx.x & 31;
@@ -345,9 +347,14 @@ pc_query_packet_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, 
         k[j] = 0u; qv[j][0] = qv[j][1] = qv[j][2] = 0.f;
         b[j].d2 = INFINITY; b[j].idx = -1; b[j].thr = -1.0f;      // thr < 0: this slot needs nothing
         if (valid[j]) {
-            k[j] = perm ? perm[t] : (uint32_t)t;
-            const float *qq = q + (size_t)k[j] * qstride;
-            qv[j][0] = qq[0]; qv[j][1] = qq[1]; qv[j][2] = qq[2];
+            if (ordered) {
+                const float4 v = __ldg(ordered + t);           // coalesced: the batch was gathered into curve order
+                qv[j][0] = v.x; qv[j][1] = v.y; qv[j][2] = v.z; k[j] = __float_as_uint(v.w);
+            } else {
+                k[j] = perm ? perm[t] : (uint32_t)t;
+                const float *qq = q + (size_t)k[j] * qstride;
+                qv[j][0] = qq[0]; qv[j][1] = qq[1]; qv[j][2] = qq[2];
+            }
             bool search = T.n_points > 0;
             if (KIND == PC_KIND_RADIUS && search && !m_eff && pc_radius_early_out((double)qv[j][0], (double)qv[j][1], (double)qv[j][2], R)) search = false;
             if (search) b[j].thr = (KIND == PC_KIND_RADIUS) ? R.bound_thr : FLT_MAX;
@@ -584,6 +591,272 @@ pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
         for (int j = threadIdx.x; j < hist_passes * RS_RADIX; j += 256) {
             const uint32_t c = (&s_hist[0][0])[j];
             if (c) atomicAdd(&ghist[j], c);
+        }
+    }
+}
+
+// ---- ordering pass, cell-binning variant ---------------------------------------------------------------------------------
+// A batch only has to be GROUPED by small cells -- which queries share a packet matters, their order inside it does not.  So
+// instead of radix-sorting (key, slot) pairs, the batch is counting-sorted by a 21-bit cell id in one histogram pass and one
+// scatter pass, and the scatter writes the queries themselves, (x, y, z, slot) as float4, so that the search kernel reads its
+// input coalesced.  The 2^21 cells are cubes of one edge h fitted to the cloud's bounding BOX, not its bounding cube (a flat map
+// of 77 x 77 x 8 m gets 0.3 m cells -- 8 + 8 + 5 bits -- where a cubic frame of 7 bits per axis gives 0.6 m ones, which cost the
+// search 12 %): cell id = (block of 2^b x 2^b x 2^b cells, Morton order over the blocks) . (3-D Hilbert index inside the block),
+// b = the smallest per-axis bit count:
+//   pc_bin_count_kernel    cell of every query; sensing-range early-outs answered on the spot; count per cell (red.global)
+//   pc_bin_scan_*          exclusive scan of the 2^21 counts (three small kernels); the total = number of queries to search
+//   pc_bin_scatter_kernel  position = atomicAdd(cursor[cell]) -- the order inside a cell is whatever the atomics give
+// Used when a cell holds at most a few packets (the density test that picked the 24-bit radix sort); denser batches keep the
+// radix sort on the full 30-bit key, whose order inside a coarse cell matters.
+#define PC_BIN_MAX_BITS 24              // most cells a batch is binned into: 2^24 (the count follows the batch size, see pc_index.cu)
+#define PC_BIN_SKIP 0xffffffffu
+#define PC_BIN_SCAN_TILE 2048            // bins per CTA of the scan kernels (256 threads x 8)
+
+// the frame of the binning grid, derived from the index's bounding box on the device (identical on every rank)
+struct pc_bin_frame {
+    float lo[3], inv_h;
+    int bits[3];          // cells per axis = 2^bits, sum <= total_bits
+    int low;              // min(bits): the 3-D Hilbert index covers the low `low` bits of every axis
+    int n_high;           // bits of the block index = sum(bits) - 3 low
+    unsigned char src[PC_BIN_MAX_BITS];     // block-index bit o = bit (src >> 2) of axis (src & 3): the longer axes' high bits, interleaved
+};
+
+__device__ __forceinline__ pc_bin_frame pc_make_bin_frame(const uint32_t *__restrict__ bbox, int total_bits)
+{
+    pc_bin_frame F;
+    float ext[3], emax = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        F.lo[a] = pc_ordered_to_float(bbox[a]);
+        ext[a] = pc_ordered_to_float(bbox[3 + a]) - F.lo[a];
+        if (!(ext[a] >= 0.f) || !(ext[a] < INFINITY)) ext[a] = 0.f;
+        emax = fmaxf(emax, ext[a]);
+    }
+    if (!(emax > 0.f)) { F.inv_h = 0.f; F.bits[0] = F.bits[1] = F.bits[2] = F.low = 1; F.n_high = 0; return F; }
+    // smallest h (in steps of 2^(1/3)) whose per-axis power-of-two cell counts fit total_bits bits
+    float vol = 1.f;
+#pragma unroll
+    for (int a = 0; a < 3; a++) vol *= fmaxf(ext[a], emax * (1.0f / 1024.0f));
+    float h = cbrtf(vol / (float)(1u << total_bits));
+    for (int it = 0; it < 64; it++) {
+        int sum = 0;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            int b = 1;
+            while (b < 10 && (float)(1 << b) * h <= ext[a] * 1.0001f) b++;
+            F.bits[a] = b; sum += b;
+        }
+        if (sum <= total_bits && (float)(1 << F.bits[0]) * h > ext[0] && (float)(1 << F.bits[1]) * h > ext[1] && (float)(1 << F.bits[2]) * h > ext[2]) break;
+        h *= 1.2599211f;
+    }
+    F.inv_h = 1.0f / h;
+    F.low = min(F.bits[0], min(F.bits[1], F.bits[2]));
+    F.n_high = 0;
+    for (int bit = 0; bit < 10; bit++)
+        for (int a = 0; a < 3; a++)
+            if (F.bits[a] - F.low > bit && F.n_high < PC_BIN_MAX_BITS) F.src[F.n_high++] = (unsigned char)(a | ((F.low + bit) << 2));
+    return F;
+}
+
+__device__ __forceinline__ uint32_t pc_hilbert_cells_var(uint32_t x, uint32_t y, uint32_t z, int bits);
+
+__device__ __forceinline__ uint32_t pc_bin_of(float x, float y, float z, const pc_bin_frame &F)
+{
+    uint32_t c[3];
+    const float v[3] = { x, y, z };
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        float t = (v[a] - F.lo[a]) * F.inv_h;
+        t = fminf(fmaxf(t, 0.0f), (float)((1 << F.bits[a]) - 1));      // NaN -> 0; queries outside the cloud's box -> border cells
+        c[a] = (uint32_t)t;
+    }
+    const uint32_t mask = (1u << F.low) - 1u;
+    const uint32_t inner = pc_hilbert_cells_var(c[0] & mask, c[1] & mask, c[2] & mask, F.low);
+    // block index: the remaining high bits of the longer axes, interleaved (a Morton order over the blocks)
+    uint32_t blk = 0;
+    for (int o = 0; o < F.n_high; o++) blk |= ((c[F.src[o] & 3] >> (F.src[o] >> 2)) & 1u) << o;
+    return (blk << (3 * F.low)) | inner;
+}
+
+// Skilling's transform for a runtime number of bits per axis (1..10)
+__device__ __forceinline__ uint32_t pc_hilbert_cells_var(uint32_t x, uint32_t y, uint32_t z, int bits)
+{
+    uint32_t X[3] = { x, y, z };
+    const uint32_t M = 1u << (bits - 1);
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {
+        const uint32_t P = Q - 1;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            if (X[i] & Q) X[0] ^= P;
+            else { const uint32_t t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+        }
+    }
+    X[1] ^= X[0];
+    X[2] ^= X[1];
+    uint32_t t = 0;
+    for (uint32_t Q = M; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
+    X[0] ^= t; X[1] ^= t; X[2] ^= t;
+    return (pc_spread10(X[0]) << 2) | (pc_spread10(X[1]) << 1) | pc_spread10(X[2]);
+}
+
+// Skilling's transform for BITS bits per axis (compile-time)
+template <int BITS>
+__device__ __forceinline__ uint32_t pc_hilbert_cells_n(uint32_t x, uint32_t y, uint32_t z)
+{
+    uint32_t X[3] = { x, y, z };
+    const uint32_t M = 1u << (BITS - 1);
+#pragma unroll
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {
+        const uint32_t P = Q - 1;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            if (X[i] & Q) X[0] ^= P;
+            else { const uint32_t t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+        }
+    }
+    X[1] ^= X[0];
+    X[2] ^= X[1];
+    uint32_t t = 0;
+#pragma unroll
+    for (uint32_t Q = M; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
+    X[0] ^= t; X[1] ^= t; X[2] ^= t;
+    return (pc_spread10(X[0]) << 2) | (pc_spread10(X[1]) << 1) | pc_spread10(X[2]);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+pc_bin_count_kernel(const float *__restrict__ q, int64_t m, int qstride, const uint32_t *__restrict__ bbox,
+                    pc_radius_dev R, int32_t *__restrict__ out_idx, float *__restrict__ out_f,
+                    uint32_t *__restrict__ cellkey, uint32_t *__restrict__ bins, int bin_bits, int shard_rank, int shard_n)
+{
+    __shared__ int s_shard_shift;
+    __shared__ pc_bin_frame s_frame;
+    if (threadIdx.x == 0) {
+        s_frame = pc_make_bin_frame(bbox, bin_bits);
+        if (shard_n > 1) s_shard_shift = 10 - pc_shard_level(bbox, m);
+    }
+    __syncthreads();
+    const pc_bin_frame &F = s_frame;          // read from shared memory (the bit table is indexed dynamically)
+    const pc_frame f = pc_make_frame(bbox, 10);
+    const int sh = shard_n > 1 ? s_shard_shift : 0;
+    for (int64_t base = (int64_t)blockIdx.x * (256 * PC_KEY_ITEMS); base < m; base += (int64_t)gridDim.x * (256 * PC_KEY_ITEMS)) {
+        float x[PC_KEY_ITEMS], y[PC_KEY_ITEMS], z[PC_KEY_ITEMS];
+#pragma unroll
+        for (int j = 0; j < PC_KEY_ITEMS; j++) {
+            const int64_t i = base + j * 256 + threadIdx.x;
+            if (i < m) { const float *p = q + i * qstride; x[j] = p[0]; y[j] = p[1]; z[j] = p[2]; }
+            else x[j] = y[j] = z[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < PC_KEY_ITEMS; j++) {
+            const int64_t i = base + j * 256 + threadIdx.x;
+            if (i >= m) continue;
+            bool search = true;
+            if (shard_n > 1) {
+                const uint32_t cx = pc_cell_coord(x[j], f.lo[0], f.inv_cell, f.max_cell), cy = pc_cell_coord(y[j], f.lo[1], f.inv_cell, f.max_cell),
+                               cz = pc_cell_coord(z[j], f.lo[2], f.inv_cell, f.max_cell);
+                uint32_t h = (cx >> sh) | ((cy >> sh) << 10) | ((cz >> sh) << 20);       // the cell, then a murmur-style finaliser
+                h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+                search = (int)(h % (uint32_t)shard_n) == shard_rank;
+            }
+            if (search && KIND == PC_KIND_RADIUS && pc_radius_early_out((double)x[j], (double)y[j], (double)z[j], R)) {
+                search = false;
+                pc_write_trivial<KIND>(R, (uint32_t)i, out_idx, out_f);
+            }
+            uint32_t key = PC_BIN_SKIP;
+            if (search) {
+                key = pc_bin_of(x[j], y[j], z[j], F);
+                atomicAdd(bins + key, 1u);
+            }
+            cellkey[i] = key;
+        }
+    }
+}
+
+// exclusive scan of n_bins counts in place: tile sums -> scan of the tile sums by one CTA (total -> *n_search) -> apply
+__global__ void __launch_bounds__(256)
+pc_bin_scan_tiles(const uint32_t *__restrict__ bins, uint32_t *__restrict__ tile_sum)
+{
+    __shared__ uint32_t s_w[8];
+    const uint4 *p = reinterpret_cast<const uint4 *>(bins + (size_t)blockIdx.x * PC_BIN_SCAN_TILE) + 2 * threadIdx.x;
+    const uint4 a = p[0], b = p[1];
+    uint32_t v = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(PC_FULL_MASK, v, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; w++) t += s_w[w]; tile_sum[blockIdx.x] = t; }
+}
+
+__global__ void __launch_bounds__(1024)
+pc_bin_scan_top(uint32_t *__restrict__ tile_sum, int n_tiles, unsigned long long *__restrict__ n_search)
+{
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const uint32_t v = i < n_tiles ? tile_sum[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(PC_FULL_MASK, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (int w = 0; w < warp; w++) woff += s_w[w];
+        const uint32_t carry = s_carry;
+        if (i < n_tiles) tile_sum[i] = carry + woff + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + woff + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_search = (unsigned long long)s_carry;
+}
+
+__global__ void __launch_bounds__(256)
+pc_bin_scan_apply(uint32_t *__restrict__ bins, const uint32_t *__restrict__ tile_sum)
+{
+    __shared__ uint32_t s_w[8];
+    uint4 *p = reinterpret_cast<uint4 *>(bins + (size_t)blockIdx.x * PC_BIN_SCAN_TILE) + 2 * threadIdx.x;
+    uint4 a = p[0], b = p[1];
+    const uint32_t mine = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(PC_FULL_MASK, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t run = tile_sum[blockIdx.x] + incl - mine;
+    for (int w = 0; w < warp; w++) run += s_w[w];
+    uint32_t t;
+    t = a.x; a.x = run; run += t;  t = a.y; a.y = run; run += t;  t = a.z; a.z = run; run += t;  t = a.w; a.w = run; run += t;
+    t = b.x; b.x = run; run += t;  t = b.y; b.y = run; run += t;  t = b.z; b.z = run; run += t;  t = b.w; b.w = run; run += t;
+    p[0] = a; p[1] = b;
+}
+
+__global__ void __launch_bounds__(256)
+pc_bin_scatter_kernel(const float *__restrict__ q, int64_t m, int qstride, const uint32_t *__restrict__ cellkey,
+                      uint32_t *__restrict__ cursor, float4 *__restrict__ ordered)
+{
+    for (int64_t base = (int64_t)blockIdx.x * (256 * PC_KEY_ITEMS); base < m; base += (int64_t)gridDim.x * (256 * PC_KEY_ITEMS)) {
+        float x[PC_KEY_ITEMS], y[PC_KEY_ITEMS], z[PC_KEY_ITEMS];
+        uint32_t key[PC_KEY_ITEMS];
+#pragma unroll
+        for (int j = 0; j < PC_KEY_ITEMS; j++) {
+            const int64_t i = base + j * 256 + threadIdx.x;
+            key[j] = PC_BIN_SKIP;
+            if (i < m) {
+                key[j] = cellkey[i];
+                const float *p = q + i * qstride; x[j] = p[0]; y[j] = p[1]; z[j] = p[2];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PC_KEY_ITEMS; j++) {
+            if (key[j] == PC_BIN_SKIP) continue;
+            const uint32_t pos = atomicAdd(cursor + key[j], 1u);
+            ordered[pos] = make_float4(x[j], y[j], z[j], __uint_as_float((uint32_t)(base + j * 256 + threadIdx.x)));
         }
     }
 }
