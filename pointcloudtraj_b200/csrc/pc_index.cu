@@ -106,6 +106,7 @@ struct pc_index {
     bool onesweep = true;              // PC_ONESWEEP=0: the three-kernel-per-pass radix sort (radix_sort.cuh)
     int key_ctas_per_sm = 0, sortkey_ctas_per_sm = 0;   // occupancy of the bin-count / key kernels (queried once)
     int bin_bits = 0;                  // PC_BIN_BITS: log2 of the number of cells of the binning (0 = from the batch size)
+    bool order_bins_all = false;       // PC_ORDER_BINS=2: bin unbounded (nearest / full-NN) batches too
     bool order_bins = true;            // PC_ORDER_BINS=0: always radix-sort the batch instead of binning it by cell
     int sort_items = 16;               // keys per thread of the batch-ordering sort (PC_SORT_ITEMS = 8 | 16)
     int coop_group = 0;                     // lanes per query of the small-batch kernel: 0 = by batch size, else 32 / 16 / 8 (PC_COOP_GROUP)
@@ -221,11 +222,11 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         TRY(cudaGetDeviceProperties(&prop, device));
         if (prop.major < 10) { rc = pc_fail(nullptr, PC_ECUDA, "pc_index_create: device is sm_%d%d, this library is built for sm_100a only", prop.major, prop.minor); break; }
         ix->sm_count = prop.multiProcessorCount;
-        if (const char *v = getenv("PC_QUERY_KERNEL")) { ix->query_kernel_auto = false; int b_ = atoi(v); ix->query_kernel = (b_ == 1 || b_ == 4) ? b_ : 3; }
+        if (const char *v = getenv("PC_QUERY_KERNEL")) { ix->query_kernel_auto = false; int b_ = atoi(v); ix->query_kernel = (b_ == 1 || b_ == 4 || b_ == 5) ? b_ : 3; }
         if (const char *v = getenv("PC_SORT_BITS")) { ix->sort_bits_auto = false; int b_ = atoi(v); ix->sort_bits = b_ <= 0 ? 0 : (b_ <= 16 ? 16 : (b_ <= 24 ? 24 : 32)); }
         if (const char *v = getenv("PC_HOST_RAMP")) ix->host_ramp = atoi(v) != 0;
         if (const char *v = getenv("PC_ONESWEEP")) ix->onesweep = atoi(v) != 0;
-        if (const char *v = getenv("PC_ORDER_BINS")) ix->order_bins = atoi(v) != 0;
+        if (const char *v = getenv("PC_ORDER_BINS")) { ix->order_bins = atoi(v) != 0; ix->order_bins_all = atoi(v) == 2; }
         if (const char *v = getenv("PC_BIN_BITS")) { int b_ = atoi(v); ix->bin_bits = b_ < 12 ? 0 : (b_ > PC_BIN_MAX_BITS ? PC_BIN_MAX_BITS : b_); }
         if (const char *v = getenv("PC_GRID")) ix->use_grid = atoi(v) != 0;
         if (const char *v = getenv("PC_GRID_CELL")) { double c_ = atof(v); if (c_ > 0.0) ix->grid_cell = c_; }
@@ -589,7 +590,9 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
         L.per_cell = per_cell;
     }
     const bool prof = ix->profile && &L == &ix->lane[0];
-    if (ix->order_bins && bits == 24 && m < ((int64_t)1 << 32) - 1) {
+    // (bounded radius batches only: unbounded nearest batches measured 5 % slower end to end on the binned order -- their
+    // search is 11 % slower on it, profiles/r2_order_bins_sweep.txt -- and keep the radix sort)
+    if (ix->order_bins && bits == 24 && m < ((int64_t)1 << 32) - 1 && (ix->order_bins_all || (A.kind == PC_Q_RADIUS && A.R.bounded))) {
         // cell binning (query_kernels.cuh): counting sort by the 21-bit Hilbert cell, the queries themselves gathered into
         // cell order.  Taken whenever the density test would have picked the 24-bit radix sort.
         // number of cells: about half the batch size (a handful of queries per occupied cell, like the 24-bit radix order),
@@ -734,9 +737,14 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
         pc_radius_grid_kernel<<<grid, PC_QUERY_THREADS, 0, L.stream>>>(ix->grid, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
     } else if (ix->query_kernel >= 3 && is_ordered) {
         // curve-ordered batch: one warp walks the tree once for its 32 or 64 neighbouring queries
-        const int per_cta = (two_per_lane ? 2 : 1) * PC_QUERY_THREADS;
+        const int per_cta = (ix->query_kernel == 5 ? 4 : (two_per_lane ? 2 : 1)) * PC_QUERY_THREADS;
         const int grid = (int)((m + per_cta - 1) / per_cta);
-        if (two_per_lane) {
+        if (ix->query_kernel == 5) {           // experiment: 128-query packets, four queries per lane
+            if (A.kind == PC_Q_NEAREST)
+                pc_query_packet_kernel<PC_KIND_NEAREST, 4><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
+            else
+                pc_query_packet_kernel<PC_KIND_RADIUS, 4><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
+        } else if (two_per_lane) {
             if (A.kind == PC_Q_NEAREST)
                 pc_query_packet_kernel<PC_KIND_NEAREST, 2><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
             else

@@ -326,7 +326,7 @@ __device__ __forceinline__ void pc_packet_traverse(const pc_tree &T, const float
 }
 
 template <int KIND, int NQ>
-__global__ void __launch_bounds__(PC_QUERY_THREADS, PC_PACKET_MIN_CTAS)
+__global__ void __launch_bounds__(PC_QUERY_THREADS, NQ <= 2 ? PC_PACKET_MIN_CTAS : PC_PACKET_MIN_CTAS / 2)
 pc_query_packet_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, int64_t m, int qstride,
                        const uint32_t *__restrict__ perm, const float4 *__restrict__ ordered, const unsigned long long *__restrict__ m_eff,
                        int32_t *__restrict__ out_idx, float *__restrict__ out_f)
@@ -659,6 +659,7 @@ __device__ __forceinline__ pc_bin_frame pc_make_bin_frame(const uint32_t *__rest
 }
 
 __device__ __forceinline__ uint32_t pc_hilbert_cells_var(uint32_t x, uint32_t y, uint32_t z, int bits);
+template <int BITS> __device__ __forceinline__ uint32_t pc_hilbert_cells_n(uint32_t x, uint32_t y, uint32_t z);
 
 __device__ __forceinline__ uint32_t pc_bin_of(float x, float y, float z, const pc_bin_frame &F)
 {
@@ -671,7 +672,14 @@ __device__ __forceinline__ uint32_t pc_bin_of(float x, float y, float z, const p
         c[a] = (uint32_t)t;
     }
     const uint32_t mask = (1u << F.low) - 1u;
-    const uint32_t inner = pc_hilbert_cells_var(c[0] & mask, c[1] & mask, c[2] & mask, F.low);
+    uint32_t inner;                                       // unrolled transforms for the usual block sizes (warp-uniform switch)
+    switch (F.low) {
+    case 4: inner = pc_hilbert_cells_n<4>(c[0] & mask, c[1] & mask, c[2] & mask); break;
+    case 5: inner = pc_hilbert_cells_n<5>(c[0] & mask, c[1] & mask, c[2] & mask); break;
+    case 6: inner = pc_hilbert_cells_n<6>(c[0] & mask, c[1] & mask, c[2] & mask); break;
+    case 7: inner = pc_hilbert_cells_n<7>(c[0] & mask, c[1] & mask, c[2] & mask); break;
+    default: inner = pc_hilbert_cells_var(c[0] & mask, c[1] & mask, c[2] & mask, F.low); break;
+    }
     // block index: the remaining high bits of the longer axes, interleaved (a Morton order over the blocks)
     uint32_t blk = 0;
     for (int o = 0; o < F.n_high; o++) blk |= ((c[F.src[o] & 3] >> (F.src[o] >> 2)) & 1u) << o;

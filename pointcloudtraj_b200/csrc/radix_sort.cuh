@@ -354,35 +354,18 @@ os_pass(const KeyT *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) if (w < warp) woff += warp_sum[w];
         local_base[tid] = woff + incl - run;
-        // Decoupled look-back, 8 predecessors per round trip: warp w reads the 256 status words of tile (base - w), all of a
-        // thread's loads in flight at once, and parks them in shared memory (the staging arrays are still free); thread d
-        // then walks the 8 words of digit d from the nearest predecessor backwards, adding counts until it meets an inclusive
-        // prefix.  A thread-serial walk (one predecessor per L2 round trip) made the first wave of ~600 resident tiles the
-        // bottleneck of the whole pass (profiles/r2_sort_lookback.txt).
+        // decoupled look-back: thread d walks the predecessors' words of digit d backwards, adding counts until it meets an
+        // inclusive prefix.  (A variant that read 8 predecessors per round trip -- one per warp, parked in shared memory -- was
+        // slower, 0.234 vs 0.206 ms for three passes over 5.6 M pairs: profiles/r2_variants_ab.txt.)
         uint32_t excl = 0;
-        if (tile > 0) {                                   // uniform per CTA
-            uint32_t *s_look = s_val;                     // RS_WARPS x RS_RADIX words <= RS_THREADS * ITEMS
-            bool done = false;
-            for (int64_t base = tile - 1;; base -= RS_WARPS) {
-                const int64_t p = base - warp;
-                uint32_t v[RS_RADIX / 32];
-#pragma unroll
-                for (int j = 0; j < RS_RADIX / 32; j++) v[j] = p >= 0 ? status[p * RS_RADIX + lane + 32 * j] : OS_FLAG_INCL;
-#pragma unroll
-                for (int j = 0; j < RS_RADIX / 32; j++) {
-                    while ((v[j] & (OS_FLAG_LOCAL | OS_FLAG_INCL)) == 0) v[j] = status[p * RS_RADIX + lane + 32 * j];   // running, not published yet
-                    s_look[warp * RS_RADIX + lane + 32 * j] = v[j];
-                }
-                __syncthreads();
-                if (!done) {
-#pragma unroll
-                    for (int w = 0; w < RS_WARPS; w++) {
-                        const uint32_t u = s_look[w * RS_RADIX + tid];
-                        excl += u & OS_VALUE_MASK;
-                        if (u & OS_FLAG_INCL) { done = true; break; }
-                    }
-                }
-                if (__syncthreads_and(done)) break;       // also fences s_look before the next round overwrites it
+        if (tile > 0) {
+            int64_t look = tile - 1;
+            for (;;) {
+                const uint32_t v = status[look * RS_RADIX + tid];
+                if ((v & (OS_FLAG_LOCAL | OS_FLAG_INCL)) == 0) continue;      // predecessor is running but has not published yet
+                excl += v & OS_VALUE_MASK;
+                if (v & OS_FLAG_INCL) break;
+                look--;                                                     // tile 0 always publishes an inclusive prefix
             }
             *mine = (excl + run) | OS_FLAG_INCL;
         }
