@@ -25,8 +25,10 @@
 #define PC_HOST_CHUNK (3 << 20)         // queries per pipelined chunk (scripts/e2e_sweep.py: 3 Mi with a 1/4, 1/2 ramp is the
                                         // optimum for 10 M batches; smaller chunks are sparser subsets -> less coherent packets)
 #define PC_TINY_BATCH 4096              // PC_HOST calls up to this size: one kernel reading / writing mapped pinned host buffers
-#define PC_SORT_MIN_BATCH (1 << 17)     // PC_QUERY_AUTO orders batches at least this large (scripts/small_batch_ab.py: below
-                                        // ~130k queries one warp per query on the unordered batch has the lower latency)
+#define PC_SORT_MIN_RADIUS 640000       // PC_QUERY_AUTO orders radius / nearest batches at least this large: below, one thread per
+#define PC_SORT_MIN_NEAREST 360000      // query on the UNORDERED batch is faster on the prefix-split tree (profiles/r2_mid_batch_ab.txt)
+#define PC_COOP_MAX_BATCH 24576         // unordered batches up to this size: a group of lanes per query (profiles/r2_small_batch_ab.txt)
+#define PC_SORT_MIN_BATCH (1 << 17)     // smallest chunk of a pipelined PC_HOST call
 
 static thread_local char g_create_error[256] = "";
 
@@ -110,10 +112,9 @@ struct pc_index {
     bool order_bins = true;            // PC_ORDER_BINS=0: always radix-sort the batch instead of binning it by cell
     int sort_items = 16;               // keys per thread of the batch-ordering sort (PC_SORT_ITEMS = 8 | 16)
     int coop_group = 0;                     // lanes per query of the small-batch kernel: 0 = by batch size, else 32 / 16 / 8 (PC_COOP_GROUP)
-    int64_t coop_g32_max = 24576, coop_g16_max = 65536;  // batch sizes up to which 32 / 16 lanes per query are used (measured:
-                                                         // narrower groups gain 5-12 % above these sizes, lose below)
-    int64_t coop_max = PC_SORT_MIN_BATCH;   // unordered batches up to this size run one warp per query (PC_COOP_MAX_BATCH)
-    int64_t sort_min = PC_SORT_MIN_BATCH;   // PC_QUERY_AUTO orders batches at least this large (PC_SORT_MIN_BATCH)
+    int64_t coop_g32_max = 6144, coop_g16_max = 12288;   // batch sizes up to which 32 / 16 lanes per query are used (8 above)
+    int64_t coop_max = PC_COOP_MAX_BATCH;   // unordered batches up to this size run a group of lanes per query (PC_COOP_MAX_BATCH)
+    int64_t sort_min_radius = PC_SORT_MIN_RADIUS, sort_min_nearest = PC_SORT_MIN_NEAREST;   // PC_SORT_MIN_BATCH sets both
     int64_t tiny_batch = PC_TINY_BATCH;   // PC_HOST calls up to this many queries take the mapped-memory path (PC_TINY_BATCH_QUERIES, 0 = off)
     bool host_ramp = true;                // PC_HOST calls: smaller first chunks (PC_HOST_RAMP=0 switches it off)
     int64_t host_chunk = PC_HOST_CHUNK;   // PC_HOST calls: queries per pipelined chunk (PC_HOST_CHUNK_QUERIES)
@@ -234,7 +235,7 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         if (const char *v = getenv("PC_HOST_CHUNK_QUERIES")) { long long b_ = atoll(v); if (b_ >= 1024) ix->host_chunk = b_; }
         if (const char *v = getenv("PC_COOP_GROUP")) { int b_ = atoi(v); ix->coop_group = (b_ == 32 || b_ == 16 || b_ == 8) ? b_ : 0; }
         if (const char *v = getenv("PC_COOP_MAX_BATCH")) { long long b_ = atoll(v); ix->coop_max = b_ < 0 ? 0 : b_; }
-        if (const char *v = getenv("PC_SORT_MIN_BATCH")) { long long b_ = atoll(v); ix->sort_min = b_ < 1 ? 1 : b_; }
+        if (const char *v = getenv("PC_SORT_MIN_BATCH")) { long long b_ = atoll(v); ix->sort_min_radius = ix->sort_min_nearest = b_ < 1 ? 1 : b_; }
         if (const char *v = getenv("PC_TINY_BATCH_QUERIES")) { long long b_ = atoll(v); ix->tiny_batch = b_ < 0 ? 0 : (b_ > PC_TINY_BATCH ? PC_TINY_BATCH : b_); }
         if (cuda_stream) { ix->stream = (cudaStream_t)cuda_stream; ix->own_stream = false; }
         else { TRY(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking)); ix->own_stream = true; }
@@ -662,13 +663,13 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
     return PC_OK;
 }
 
-static bool pc_want_sort(const pc_index *ix, int flags, int64_t m)
+static bool pc_want_sort(const pc_index *ix, int flags, int64_t m, bool unbounded)
 {
     if (ix->n == 0 || ix->sort_bits == 0) return false;
     if (ix->shard_n > 1) return true;          // the share is selected by the ordering pass
     if (flags & PC_QUERY_SORTED) return true;
     if (flags & PC_QUERY_UNSORTED) return false;
-    return m >= ix->sort_min;
+    return m >= (unbounded ? ix->sort_min_nearest : ix->sort_min_radius);
 }
 
 // small unordered batch: G lanes per query.  A whole warp per query has the lowest latency while the batch fits the GPU's
@@ -704,7 +705,7 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
     // are scheduled ahead of the queued CTAs of OTHER lanes' search kernels (issue-bound) and overlap with them.  Everything
     // already queued on the lane (input copy, the lane's previous batch, which still reads the sort buffers) comes first.
     L.os = L.stream;
-    if (split_streams && pc_want_sort(ix, A.flags, m)) {
+    if (split_streams && pc_want_sort(ix, A.flags, m, A.kind == PC_Q_NEAREST || !A.R.bounded)) {
         PC_CUDA(ix, cudaEventRecord(L.ev_deps, L.stream));
         PC_CUDA(ix, cudaStreamWaitEvent(L.order_stream, L.ev_deps, 0));
         L.os = L.order_stream;
@@ -716,7 +717,7 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
     if (prof) PC_CUDA(ix, cudaEventRecord(L.t0, L.stream));
     // counter[1]: queries that need a search after the ordering pass
     PC_CUDA(ix, cudaMemsetAsync(L.counter, 0, 2 * sizeof(unsigned long long), L.os));
-    if (pc_want_sort(ix, A.flags, m)) {
+    if (pc_want_sort(ix, A.flags, m, A.kind == PC_Q_NEAREST || !A.R.bounded)) {
         int rc = pc_sort_queries(ix, L, A, d_q, m, qstride, d_idx, d_f, &perm, &ordered);
         if (rc != PC_OK) return rc;
         m_eff = L.counter + 1;
@@ -863,7 +864,7 @@ static int pc_query_dispatch(pc_index *ix, const pc_qargs &A, const float *q, in
     if (m == 0) return PC_OK;
     const int qs = (int)q_stride;
     if (space == PC_DEVICE) return pc_run_batch(ix, ix->lane[0], A, q, m, qs, out_idx, out_f);
-    if (space == PC_HOST && m <= ix->tiny_batch && !pc_want_sort(ix, A.flags, m)) return pc_tiny_host_batch(ix, A, q, m, qs, out_idx, out_f);
+    if (space == PC_HOST && m <= ix->tiny_batch && !pc_want_sort(ix, A.flags, m, A.kind == PC_Q_NEAREST || !A.R.bounded)) return pc_tiny_host_batch(ix, A, q, m, qs, out_idx, out_f);
 
     // order the side lanes after the last (possibly still running) index build / broadcast on the handle's stream
     for (int l = 1; l < PC_PIPE_LANES; l++) PC_CUDA(ix, cudaStreamWaitEvent(ix->lane[l].stream, ix->ev_ready, 0));

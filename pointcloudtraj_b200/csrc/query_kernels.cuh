@@ -348,7 +348,7 @@ pc_query_packet_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, 
         b[j].d2 = INFINITY; b[j].idx = -1; b[j].thr = -1.0f;      // thr < 0: this slot needs nothing
         if (valid[j]) {
             if (ordered) {
-                const float4 v = __ldg(ordered + t);           // coalesced: the batch was gathered into curve order
+                const float4 v = __ldcs(ordered + t);          // coalesced: the batch was gathered into cell order; read once
                 qv[j][0] = v.x; qv[j][1] = v.y; qv[j][2] = v.z; k[j] = __float_as_uint(v.w);
             } else {
                 k[j] = perm ? perm[t] : (uint32_t)t;
@@ -601,7 +601,7 @@ pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
 // scatter pass, and the scatter writes the queries themselves, (x, y, z, slot) as float4, so that the search kernel reads its
 // input coalesced.  The 2^21 cells are cubes of one edge h fitted to the cloud's bounding BOX, not its bounding cube (a flat map
 // of 77 x 77 x 8 m gets 0.3 m cells -- 8 + 8 + 5 bits -- where a cubic frame of 7 bits per axis gives 0.6 m ones, which cost the
-// search 12 %): cell id = (block of 2^b x 2^b x 2^b cells, Morton order over the blocks) . (3-D Hilbert index inside the block),
+// search 12 %): cell id = (block of 2^b x 2^b x 2^b cells, row-major over the blocks) . (3-D Hilbert index inside the block),
 // b = the smallest per-axis bit count:
 //   pc_bin_count_kernel    cell of every query; sensing-range early-outs answered on the spot; count per cell (red.global)
 //   pc_bin_scan_*          exclusive scan of the 2^21 counts (three small kernels); the total = number of queries to search
@@ -617,8 +617,8 @@ struct pc_bin_frame {
     float lo[3], inv_h;
     int bits[3];          // cells per axis = 2^bits, sum <= total_bits
     int low;              // min(bits): the 3-D Hilbert index covers the low `low` bits of every axis
-    int n_high;           // bits of the block index = sum(bits) - 3 low
-    unsigned char src[PC_BIN_MAX_BITS];     // block-index bit o = bit (src >> 2) of axis (src & 3): the longer axes' high bits, interleaved
+    int sh_y, sh_z;       // block index = hx | hy << sh_y | hz << sh_z, h = the axis' bits above `low` (row-major over the blocks:
+                          // with <= a few hundred blocks of 2^low cells per axis their order hardly matters)
 };
 
 __device__ __forceinline__ pc_bin_frame pc_make_bin_frame(const uint32_t *__restrict__ bbox, int total_bits)
@@ -632,7 +632,7 @@ __device__ __forceinline__ pc_bin_frame pc_make_bin_frame(const uint32_t *__rest
         if (!(ext[a] >= 0.f) || !(ext[a] < INFINITY)) ext[a] = 0.f;
         emax = fmaxf(emax, ext[a]);
     }
-    if (!(emax > 0.f)) { F.inv_h = 0.f; F.bits[0] = F.bits[1] = F.bits[2] = F.low = 1; F.n_high = 0; return F; }
+    if (!(emax > 0.f)) { F.inv_h = 0.f; F.bits[0] = F.bits[1] = F.bits[2] = F.low = 1; F.sh_y = F.sh_z = 0; return F; }
     // smallest h (in steps of 2^(1/3)) whose per-axis power-of-two cell counts fit total_bits bits
     float vol = 1.f;
 #pragma unroll
@@ -651,10 +651,8 @@ __device__ __forceinline__ pc_bin_frame pc_make_bin_frame(const uint32_t *__rest
     }
     F.inv_h = 1.0f / h;
     F.low = min(F.bits[0], min(F.bits[1], F.bits[2]));
-    F.n_high = 0;
-    for (int bit = 0; bit < 10; bit++)
-        for (int a = 0; a < 3; a++)
-            if (F.bits[a] - F.low > bit && F.n_high < PC_BIN_MAX_BITS) F.src[F.n_high++] = (unsigned char)(a | ((F.low + bit) << 2));
+    F.sh_y = F.bits[0] - F.low;
+    F.sh_z = F.sh_y + F.bits[1] - F.low;
     return F;
 }
 
@@ -680,9 +678,7 @@ __device__ __forceinline__ uint32_t pc_bin_of(float x, float y, float z, const p
     case 7: inner = pc_hilbert_cells_n<7>(c[0] & mask, c[1] & mask, c[2] & mask); break;
     default: inner = pc_hilbert_cells_var(c[0] & mask, c[1] & mask, c[2] & mask, F.low); break;
     }
-    // block index: the remaining high bits of the longer axes, interleaved (a Morton order over the blocks)
-    uint32_t blk = 0;
-    for (int o = 0; o < F.n_high; o++) blk |= ((c[F.src[o] & 3] >> (F.src[o] >> 2)) & 1u) << o;
+    const uint32_t blk = (c[0] >> F.low) | ((c[1] >> F.low) << F.sh_y) | ((c[2] >> F.low) << F.sh_z);
     return (blk << (3 * F.low)) | inner;
 }
 
@@ -744,7 +740,7 @@ pc_bin_count_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
         if (shard_n > 1) s_shard_shift = 10 - pc_shard_level(bbox, m);
     }
     __syncthreads();
-    const pc_bin_frame &F = s_frame;          // read from shared memory (the bit table is indexed dynamically)
+    const pc_bin_frame F = s_frame;
     const pc_frame f = pc_make_frame(bbox, 10);
     const int sh = shard_n > 1 ? s_shard_shift : 0;
     for (int64_t base = (int64_t)blockIdx.x * (256 * PC_KEY_ITEMS); base < m; base += (int64_t)gridDim.x * (256 * PC_KEY_ITEMS)) {
@@ -752,7 +748,7 @@ pc_bin_count_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
 #pragma unroll
         for (int j = 0; j < PC_KEY_ITEMS; j++) {
             const int64_t i = base + j * 256 + threadIdx.x;
-            if (i < m) { const float *p = q + i * qstride; x[j] = p[0]; y[j] = p[1]; z[j] = p[2]; }
+            if (i < m) { const float *p = q + i * qstride; x[j] = __ldcs(p); y[j] = __ldcs(p + 1); z[j] = __ldcs(p + 2); }   // read once: evict first
             else x[j] = y[j] = z[j] = 0.f;
         }
 #pragma unroll
@@ -856,8 +852,8 @@ pc_bin_scatter_kernel(const float *__restrict__ q, int64_t m, int qstride, const
             const int64_t i = base + j * 256 + threadIdx.x;
             key[j] = PC_BIN_SKIP;
             if (i < m) {
-                key[j] = cellkey[i];
-                const float *p = q + i * qstride; x[j] = p[0]; y[j] = p[1]; z[j] = p[2];
+                key[j] = __ldcs(cellkey + i);
+                const float *p = q + i * qstride; x[j] = __ldcs(p); y[j] = __ldcs(p + 1); z[j] = __ldcs(p + 2);
             }
         }
 #pragma unroll
