@@ -263,3 +263,49 @@ pc_tree_fit_kernel(float4 *rec, const float4 *__restrict__ points, const int32_t
         add = 1;
     }
 }
+
+// ---- tree, step 3: seeds for the lane-group walks ------------------------------------------------------------------------------
+// The kernels that put a whole group of lanes on ONE query (pc_query_coop_kernel, pc_range_coop_kernel) would spend their first
+// five steps with 1, 2, 4, 8, 16 busy lanes if they started at the root.  One warp expands the top of the tree breadth-first
+// until the next level would not fit 32 lanes and leaves the frontier here: up to 32 inner nodes, plus the (rare) leaves met
+// on the way as (reference, count) pairs.  Layout (uint32 words): [0] inner count, [1] leaf count, [2..34) inner nodes,
+// [34..98) leaf pairs.  Lives right behind the points, inside the span pc_index_broadcast ships.
+#define PC_SEED_WORDS 100
+#define PC_SEED_INNER 2
+#define PC_SEED_LEAF 34
+
+__global__ void __launch_bounds__(32)
+pc_tree_seed_kernel(const float4 *__restrict__ rec, uint32_t root, uint32_t root_count, uint32_t *__restrict__ seeds)
+{
+    __shared__ uint32_t cur[32], nxt[64], leaf[64];
+    const int lane = threadIdx.x;
+    int n = 0, n_leaf = 0;
+    if (root & PC_REF_LEAF) { if (lane == 0) { leaf[0] = root; leaf[1] = root_count; } n_leaf = 1; }
+    else { if (lane == 0) cur[0] = root; n = 1; }
+    __syncwarp();
+    while (n > 0 && 2 * n <= 32 && n_leaf + 2 * n <= 32) {
+        uint32_t r[2] = { 0, 0 }, c[2] = { 0, 0 };
+        bool inner[2] = { false, false }, isleaf[2] = { false, false };
+        if (lane < n) {
+            const float *w = reinterpret_cast<const float *>(rec + 4ull * cur[lane]);
+            r[0] = __float_as_uint(w[3]); c[0] = __float_as_uint(w[7]); r[1] = __float_as_uint(w[11]); c[1] = __float_as_uint(w[15]);
+            for (int k = 0; k < 2; k++) { isleaf[k] = (r[k] & PC_REF_LEAF) != 0; inner[k] = !isleaf[k]; }
+        }
+        int n_new = 0;
+        const uint32_t lt = (1u << lane) - 1u;
+        for (int k = 0; k < 2; k++) {
+            const uint32_t mi = __ballot_sync(PC_FULL_MASK, inner[k]), ml = __ballot_sync(PC_FULL_MASK, isleaf[k]);
+            if (inner[k]) nxt[n_new + __popc(mi & lt)] = r[k];
+            if (isleaf[k]) { const int p = n_leaf + __popc(ml & lt); leaf[2 * p] = r[k]; leaf[2 * p + 1] = c[k]; }
+            n_new += __popc(mi);
+            n_leaf += __popc(ml);
+        }
+        __syncwarp();
+        if (lane < n_new) cur[lane] = nxt[lane];
+        n = n_new;
+        __syncwarp();
+    }
+    if (lane == 0) { seeds[0] = (uint32_t)n; seeds[1] = (uint32_t)n_leaf; }
+    if (lane < n) seeds[PC_SEED_INNER + lane] = cur[lane];
+    if (lane < n_leaf) { seeds[PC_SEED_LEAF + 2 * lane] = leaf[2 * lane]; seeds[PC_SEED_LEAF + 2 * lane + 1] = leaf[2 * lane + 1]; }
+}

@@ -139,8 +139,8 @@ extern "C" int pc_index_broadcast(pc_index *ix, pc_comm *c, int root)
         ix->bbox_from_bcast = h.n > 0;
     }
     if (h.n > 0) {
-        // records [0, 4 n_nodes) and the points (+ PC_LEAF pad copies) behind them are one contiguous span of the tree array
-        const size_t bytes = (size_t)(4 * h.n_nodes + h.n + PC_LEAF) * sizeof(float4);
+        // records [0, 4 n_nodes), the points (+ PC_LEAF pad copies) and the seeds behind them are one contiguous span of the tree array
+        const size_t bytes = (size_t)(4 * h.n_nodes + h.n + PC_LEAF) * sizeof(float4) + PC_SEED_WORDS * sizeof(uint32_t);   // + the seeds
         if ((int64_t)(bytes / sizeof(float4)) > ix->tree_cap) return pc_fail(ix, PC_ENOMEM, "pc_index_broadcast: arena too small");
         PC_NCCL(ix, g_nccl.Broadcast(ix->tree, ix->tree, bytes, 0 /* ncclInt8 */, root, c->nccl, st));
     }

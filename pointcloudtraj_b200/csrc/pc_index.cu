@@ -195,7 +195,7 @@ static int pc_reserve_cloud(pc_index *ix, int64_t n)
     PC_CUDA(ix, cudaMalloc(&ix->keys_b, (size_t)cap * ix->key_bytes));
     PC_CUDA(ix, cudaMalloc((void **)&ix->vals_a, (size_t)cap * sizeof(uint32_t)));
     PC_CUDA(ix, cudaMalloc((void **)&ix->vals_b, (size_t)cap * sizeof(uint32_t)));
-    ix->tree_cap = 4 * cap + cap + 2 * PC_LEAF;            // one 64-byte record and one point per point, + pad points
+    ix->tree_cap = 4 * cap + cap + 2 * PC_LEAF + PC_SEED_WORDS / 4 + 1;     // one 64-byte record and one point per point, pad points, seeds
     PC_CUDA(ix, cudaMalloc((void **)&ix->tree, (size_t)ix->tree_cap * sizeof(float4)));
     ix->hist_cap = pc_sort_scratch_words(cap, 8, ix->key_bytes == 8 ? 8 : 4);
     PC_CUDA(ix, cudaMalloc((void **)&ix->tile_hist, (size_t)ix->hist_cap * sizeof(uint32_t)));
@@ -453,6 +453,12 @@ extern "C" int pc_index_build(pc_index *ix, const float *xyz, int64_t n, int64_t
             ix->launches++;
             PC_CHECK_LAUNCH(ix);
         }
+        // the seeds of the lane-group walks sit right behind the points (the records' child references are final after the
+        // nodes kernel; the boxes are not needed)
+        pc_tree_seed_kernel<<<1, 32, 0, st>>>(ix->tree, n_nodes > 0 ? 0u : PC_REF_LEAF, n_nodes > 0 ? 0u : (uint32_t)n,
+                                               reinterpret_cast<uint32_t *>(ix->points + n + PC_LEAF));
+        ix->launches++;
+        PC_CHECK_LAUNCH(ix);
     }
     PC_CUDA(ix, cudaMemcpyAsync(ix->h_bbox, ix->d_bbox, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     PC_CUDA(ix, cudaEventRecord(ix->ev_b1, st));
@@ -541,6 +547,7 @@ static pc_tree pc_tree_of(const pc_index *ix)
 {
     pc_tree T;
     T.rec = ix->tree; T.points = ix->points; T.n_points = ix->n; T.root = ix->root; T.root_count = ix->root_count;
+    T.seeds = reinterpret_cast<const uint32_t *>(ix->points + ix->n + PC_LEAF);
     return T;
 }
 

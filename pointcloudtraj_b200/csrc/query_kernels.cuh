@@ -36,6 +36,7 @@ struct pc_tree {
     int64_t n_points;
     uint32_t root;                       // child reference of the whole cloud: inner node 0, or the leaf PC_REF_LEAF | 0
     uint32_t root_count;                 // number of points when the root is a leaf
+    const uint32_t *__restrict__ seeds;  // top of the tree expanded to <= 32 inner nodes (+ leaves met on the way): pc_tree_seed_kernel
 };
 
 // one box (min, max: 32 bytes, 32-byte aligned) with ONE 256-bit read-only load (sm_100: LDG.E.256)
@@ -403,13 +404,12 @@ pc_query_coop_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, in
     pc_best b[1];
     b[0].d2 = INFINITY; b[0].idx = -1; b[0].thr = (KIND == PC_KIND_RADIUS) ? R.bound_thr : FLT_MAX;
     uint2 *F = s_front[w * GROUPS + grp];
-    int size = 0;
-    if (T.root & PC_REF_LEAF) {
-        if (gl == 0) pc_scan_leaf<1>(T.points + (T.root & ~PC_REF_LEAF), qv, b);      // the whole cloud is one leaf
-    } else {
-        if (gl == 0) F[0] = make_uint2(T.root, 0u);
-        size = 1;
-    }
+    // start from the seeds: the top of the tree already expanded to <= 32 inner nodes (box distance unknown: 0), the few
+    // leaves met on the way scanned by the first lanes
+    const int n_seed = (int)T.seeds[0], n_seed_leaf = (int)T.seeds[1];
+    for (int j = gl; j < n_seed_leaf; j += G) pc_scan_leaf<1>(T.points + (T.seeds[PC_SEED_LEAF + 2 * j] & ~PC_REF_LEAF), qv, b);
+    for (int j = gl; j < n_seed; j += G) F[j] = make_uint2(T.seeds[PC_SEED_INNER + j], 0u);
+    int size = n_seed;
     __syncwarp(gmask);
     const uint32_t lt = (1u << gl) - 1u;
     while (size > 0) {
@@ -480,7 +480,7 @@ pc_query_coop_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, in
 // rank's share is then as dense in space as the whole batch (dense packets) and spread over the whole map (equal cost per
 // rank).  The level is computed HERE, from the index's bounding box and the batch size only -- both identical on every
 // rank that holds a replica -- so all ranks agree on the owner of every query whatever the state of their host-side caches:
-// the finest cells (<= 128 per axis) that still hold >= 128 queries (two packets) each -- finer cells balance the ranks
+// the finest cells (<= 1024 per axis) that still hold >= 128 queries (two packets) each -- finer cells balance the ranks
 // better, coarser ones keep more packets inside one cell.
 // Measured on C5 with 8 GPUs: array slices 37 ms; contiguous stretches of the curve 41 ms and round-robin 32^3 cells 43 ms
 // (both unbalanced: 18..42 ms per rank -- on a flat map the low bits of the cell index encode the z layer); hashed cells:
@@ -494,7 +494,7 @@ __device__ __forceinline__ int pc_shard_level(const uint32_t *__restrict__ bbox,
         emax = fmaxf(emax, ext[a]);
     }
     if (!(emax > 0.f) || !(emax < INFINITY)) return 2;
-    for (int lv = 7; lv > 2; lv--) {
+    for (int lv = 10; lv > 2; lv--) {
         const double c = (double)emax / (double)(1 << lv);
         double v = 1.0;
 #pragma unroll

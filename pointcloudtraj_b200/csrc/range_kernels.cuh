@@ -79,22 +79,37 @@ pc_range_coop_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstr
     const uint32_t lt = (1u << lane) - 1u;
     int64_t total = 0;
     int size = 0;
-    if (T.root & PC_REF_LEAF) {
-        // the whole cloud is one leaf: one point per lane
-        bool hit = false;
-        int32_t id = 0;
-        if (lane < (int)T.root_count) {
-            const float4 p = __ldg(T.points + lane);
-            const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
-            if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr) hit = pc_exact_d2(p.x, p.y, p.z, qxd, qyd, qzd) <= r2;
-            id = __float_as_int(p.w);
+    {
+        // start from the seeds (pc_tree_seed_kernel): the leaves met while the top of the tree was expanded -- one per lane, only
+        // their own `count` points -- and up to 32 inner nodes for the frontier
+        const int n_seed = (int)T.seeds[0], n_seed_leaf = (int)T.seeds[1];
+        bool hit[PC_LEAF];
+        int32_t id[PC_LEAF];
+#pragma unroll
+        for (int i = 0; i < PC_LEAF; i++) { hit[i] = false; id[i] = 0; }
+        if (lane < n_seed_leaf) {
+            const uint32_t ref = T.seeds[PC_SEED_LEAF + 2 * lane], cnt = T.seeds[PC_SEED_LEAF + 2 * lane + 1];
+            const float4 *pts = T.points + (ref & ~PC_REF_LEAF);
+#pragma unroll
+            for (int i = 0; i < PC_LEAF; i++) {
+                if ((uint32_t)i < cnt) {
+                    const float4 p = __ldg(pts + i);
+                    const float dx = p.x - qx, dy = p.y - qy, dz = p.z - qz;
+                    if (fmaf(dz, dz, fmaf(dy, dy, dx * dx)) <= thr) hit[i] = pc_exact_d2(p.x, p.y, p.z, qxd, qyd, qzd) <= r2;
+                    id[i] = __float_as_int(p.w);
+                }
+            }
         }
-        const uint32_t mask = __ballot_sync(PC_FULL_MASK, hit);
-        if (FILL && hit) out_idx[begin + __popc(mask & lt)] = id;
-        total = __popc(mask);
-    } else {
-        if (lane == 0) F[0] = T.root;
-        size = 1;
+        if (n_seed_leaf > 0) {
+#pragma unroll
+            for (int i = 0; i < PC_LEAF; i++) {
+                const uint32_t mask = __ballot_sync(PC_FULL_MASK, hit[i]);
+                if (FILL && hit[i]) out_idx[begin + total + __popc(mask & lt)] = id[i];
+                total += __popc(mask);
+            }
+        }
+        if (lane < n_seed) F[lane] = T.seeds[PC_SEED_INNER + lane];
+        size = n_seed;
     }
     __syncwarp();
     while (size > 0) {

@@ -245,7 +245,7 @@ def c5(n_pts, n_q, shard):
         print(json.dumps({"config": "c5_scaling", "n_gpus": world, "points": n_pts, "queries_total": n_q, "scaling": "strong",
                           "sharding": shard if world > 1 else "none", "queries_answered_over_ranks": answered,
                           "index_build_ms": build_ms, "index_broadcast_ms": bcast_ms,
-                          "index_bytes": int(ix.view().leaf_base * 64 + ix.view().n_leaves * 64),
+                          "index_bytes": int(ix.view().n_nodes * 64 + (ix.view().n_points + 4) * 16),
                           "nearest_ms_max_over_ranks": float(t.item()), "nearest_ms_per_rank": [round(v, 3) for v in per_rank], "nearest_qps": n_q / float(t.item()) * 1e3,
                           "parity_spot_check": ok}))
     ix.close()
