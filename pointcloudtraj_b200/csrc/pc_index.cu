@@ -22,8 +22,9 @@
 
 #define PC_VERSION_STRING "pcindex 0.2 (sm_100a)"
 #define PC_PIPE_LANES 3                 // concurrent H2D / kernel / D2H chunks for PC_HOST calls
-#define PC_HOST_CHUNK (3 << 20)         // queries per pipelined chunk (scripts/e2e_sweep.py: 3 Mi with a 1/4, 1/2 ramp is the
-                                        // optimum for 10 M batches; smaller chunks are sparser subsets -> less coherent packets)
+#define PC_HOST_CHUNK (1 << 20)         // queries per pipelined chunk (scripts/e2e_sweep.py, profiles/r2_e2e_chunk_sweep.txt: 1 Mi
+                                        // without a ramp of smaller first chunks is the optimum for 10 M batches on the
+                                        // round-2 kernels; round 1: 3 Mi with a ramp)
 #define PC_TINY_BATCH 4096              // PC_HOST calls up to this size: one kernel reading / writing mapped pinned host buffers
 #define PC_SORT_MIN_RADIUS 640000       // PC_QUERY_AUTO orders radius / nearest batches at least this large: below, one thread per
 #define PC_SORT_MIN_NEAREST 360000      // query on the UNORDERED batch is faster on the prefix-split tree (profiles/r2_mid_batch_ab.txt)
@@ -116,7 +117,7 @@ struct pc_index {
     int64_t coop_max = PC_COOP_MAX_BATCH;   // unordered batches up to this size run a group of lanes per query (PC_COOP_MAX_BATCH)
     int64_t sort_min_radius = PC_SORT_MIN_RADIUS, sort_min_nearest = PC_SORT_MIN_NEAREST;   // PC_SORT_MIN_BATCH sets both
     int64_t tiny_batch = PC_TINY_BATCH;   // PC_HOST calls up to this many queries take the mapped-memory path (PC_TINY_BATCH_QUERIES, 0 = off)
-    bool host_ramp = true;                // PC_HOST calls: smaller first chunks (PC_HOST_RAMP=0 switches it off)
+    bool host_ramp = false;               // PC_HOST calls: smaller first chunks (PC_HOST_RAMP=1 switches it on)
     int64_t host_chunk = PC_HOST_CHUNK;   // PC_HOST calls: queries per pipelined chunk (PC_HOST_CHUNK_QUERIES)
     char err[256] = "";
 };

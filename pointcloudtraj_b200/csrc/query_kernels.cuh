@@ -55,6 +55,39 @@ __device__ __forceinline__ float pc_box_d2(const float4 lo, const float4 hi, flo
     return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
 }
 
+// ---- packed fp32x2 arithmetic (Blackwell: FADD2 / FFMA2) ------------------------------------------------------------------
+// The 64-query packets give every lane TWO queries; their box and point distances are computed two at a time with the packed
+// add.f32x2 / fma.f32x2 instructions of sm_100 (SASS FADD2 / FFMA2 -- a box bound or point coordinate enters as a scalar
+// operand that the instruction broadcasts to both halves, so no packing moves are needed).  Each half is an ordinary IEEE
+// fp32 operation: the results are bit-identical with the scalar code, at 15 instead of 24 instructions per (box, 2 queries).
+__device__ __forceinline__ float2 pc_add2(float2 a, float2 b)
+{
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+__device__ __forceinline__ float2 pc_fma2(float2 a, float2 b, float2 c)
+{
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return r;
+}
+
+// squared distance of a box to two queries; nq* = (-qa, -qb) per axis.  Same operations as pc_box_d2, two at a time.
+__device__ __forceinline__ float2 pc_box_d2x2(const float4 lo, const float4 hi, float2 nqx, float2 nqy, float2 nqz)
+{
+    const float2 m1 = make_float2(-1.f, -1.f), zero = make_float2(0.f, 0.f);
+    float2 t1 = pc_add2(make_float2(lo.x, lo.x), nqx), t2 = pc_fma2(nqx, m1, make_float2(-hi.x, -hi.x));      // lo - q, q - hi
+    const float2 dx = make_float2(fmaxf(fmaxf(t1.x, t2.x), 0.0f), fmaxf(fmaxf(t1.y, t2.y), 0.0f));
+    t1 = pc_add2(make_float2(lo.y, lo.y), nqy); t2 = pc_fma2(nqy, m1, make_float2(-hi.y, -hi.y));
+    const float2 dy = make_float2(fmaxf(fmaxf(t1.x, t2.x), 0.0f), fmaxf(fmaxf(t1.y, t2.y), 0.0f));
+    t1 = pc_add2(make_float2(lo.z, lo.z), nqz); t2 = pc_fma2(nqz, m1, make_float2(-hi.z, -hi.z));
+    const float2 dz = make_float2(fmaxf(fmaxf(t1.x, t2.x), 0.0f), fmaxf(fmaxf(t1.y, t2.y), 0.0f));
+    return pc_fma2(dz, dz, pc_fma2(dy, dy, pc_fma2(dx, dx, zero)));
+}
+
 // the reference's fp64 expression: s = 0; s += (px-qx)^2; s += (py-qy)^2; s += (pz-qz)^2  (kdtree.c:379-382)
 __device__ __forceinline__ double pc_exact_d2(float px, float py, float pz, double qx, double qy, double qz)
 {
@@ -113,6 +146,32 @@ __device__ __forceinline__ void pc_scan_leaf(const float4 *__restrict__ pts, con
 #pragma unroll
             for (int i = 0; i < PC_LEAF; i++) pc_consider(p[i], d[j][i], q[j][0], q[j][1], q[j][2], b[j]);
         }
+    }
+}
+
+// the same leaf scan for the two queries of a lane, distances two at a time (nq* = (-qa, -qb) per axis)
+__device__ __forceinline__ void pc_scan_leaf_x2(const float4 *__restrict__ pts, float2 nqx, float2 nqy, float2 nqz, pc_best (&b)[2])
+{
+    float4 p[PC_LEAF];
+    float2 d[PC_LEAF];
+    const float2 zero = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < PC_LEAF; i++) p[i] = __ldg(pts + i);
+    float mina = FLT_MAX, minb = FLT_MAX;
+#pragma unroll
+    for (int i = 0; i < PC_LEAF; i++) {
+        const float2 ex = pc_add2(make_float2(p[i].x, p[i].x), nqx), ey = pc_add2(make_float2(p[i].y, p[i].y), nqy),
+                     ez = pc_add2(make_float2(p[i].z, p[i].z), nqz);
+        d[i] = pc_fma2(ez, ez, pc_fma2(ey, ey, pc_fma2(ex, ex, zero)));
+        mina = fminf(mina, d[i].x); minb = fminf(minb, d[i].y);
+    }
+    if (mina <= b[0].thr) {
+#pragma unroll
+        for (int i = 0; i < PC_LEAF; i++) pc_consider(p[i], d[i].x, -nqx.x, -nqy.x, -nqz.x, b[0]);
+    }
+    if (minb <= b[1].thr) {
+#pragma unroll
+        for (int i = 0; i < PC_LEAF; i++) pc_consider(p[i], d[i].y, -nqx.y, -nqy.y, -nqz.y, b[1]);
     }
 }
 
@@ -264,6 +323,12 @@ __device__ __forceinline__ void pc_packet_traverse(const pc_tree &T, const float
     for (int j = 0; j < NQ; j++) any = any || b[j].thr >= 0.f;
     if (__ballot_sync(PC_FULL_MASK, any) == 0) return;
     if (T.root & PC_REF_LEAF) { pc_scan_leaf<NQ>(T.points + (T.root & ~PC_REF_LEAF), q, b); return; }
+    // NQ == 2: the lane's two queries packed per axis, negated (pc_box_d2x2, pc_scan_leaf_x2)
+    const float2 nqx = make_float2(-q[0][0], -q[NQ - 1][0]), nqy = make_float2(-q[0][1], -q[NQ - 1][1]), nqz = make_float2(-q[0][2], -q[NQ - 1][2]);
+    auto scan = [&](const float4 *pts) {
+        if constexpr (NQ == 2) pc_scan_leaf_x2(pts, nqx, nqy, nqz, b);
+        else pc_scan_leaf<NQ>(pts, q, b);
+    };
     uint32_t e0 = 0, e1 = 0, e2 = 0;        // warp stack of PC_STACK = 96 entries: entry i lives in lane i & 31, register i >> 5
     int sp = 0;
     uint32_t ref = T.root;
@@ -284,10 +349,18 @@ __device__ __forceinline__ void pc_packet_traverse(const pc_tree &T, const float
 #endif
         float d0[NQ], d1[NQ];
         bool want0 = false, want1 = false;
+        if constexpr (NQ == 2) {
+            const float2 a0 = pc_box_d2x2(lo0, hi0, nqx, nqy, nqz), a1 = pc_box_d2x2(lo1, hi1, nqx, nqy, nqz);
+            d0[0] = a0.x; d0[1] = a0.y; d1[0] = a1.x; d1[1] = a1.y;
+        } else {
+#pragma unroll
+            for (int j = 0; j < NQ; j++) {
+                d0[j] = pc_box_d2(lo0, hi0, q[j][0], q[j][1], q[j][2]);
+                d1[j] = pc_box_d2(lo1, hi1, q[j][0], q[j][1], q[j][2]);
+            }
+        }
 #pragma unroll
         for (int j = 0; j < NQ; j++) {
-            d0[j] = pc_box_d2(lo0, hi0, q[j][0], q[j][1], q[j][2]);
-            d1[j] = pc_box_d2(lo1, hi1, q[j][0], q[j][1], q[j][2]);
             want0 = want0 || d0[j] <= b[j].thr;
             want1 = want1 || d1[j] <= b[j].thr;
         }
@@ -305,14 +378,14 @@ __device__ __forceinline__ void pc_packet_traverse(const pc_tree &T, const float
             }
             const uint32_t r0 = __float_as_uint(lo0.w), r1 = __float_as_uint(lo1.w);
             const uint32_t rn = first0 ? r0 : r1, rf = first0 ? r1 : r0;
-            if (rn & PC_REF_LEAF) pc_scan_leaf<NQ>(T.points + (rn & ~PC_REF_LEAF), q, b);
+            if (rn & PC_REF_LEAF) scan(T.points + (rn & ~PC_REF_LEAF));
             else next = rn;
             if (both) {
                 if (rf & PC_REF_LEAF) {
                     bool again = false;          // the near leaf may have tightened the bounds
 #pragma unroll
                     for (int j = 0; j < NQ; j++) again = again || (first0 ? d1[j] : d0[j]) <= b[j].thr;
-                    if (__ballot_sync(PC_FULL_MASK, again)) pc_scan_leaf<NQ>(T.points + (rf & ~PC_REF_LEAF), q, b);
+                    if (__ballot_sync(PC_FULL_MASK, again)) scan(T.points + (rf & ~PC_REF_LEAF));
                 } else if (next != PC_NO_NODE) {
                     if (lane == (sp & 31)) { if (sp < 32) e0 = rf; else if (sp < 64) e1 = rf; else e2 = rf; }
                     sp++;
@@ -856,11 +929,15 @@ pc_bin_scatter_kernel(const float *__restrict__ q, int64_t m, int qstride, const
                 const float *p = q + i * qstride; x[j] = __ldcs(p); y[j] = __ldcs(p + 1); z[j] = __ldcs(p + 2);
             }
         }
+        // all of a thread's cursor atomics first, then the stores: eight round trips in flight instead of eight in a row
+        uint32_t pos[PC_KEY_ITEMS];
 #pragma unroll
         for (int j = 0; j < PC_KEY_ITEMS; j++) {
-            if (key[j] == PC_BIN_SKIP) continue;
-            const uint32_t pos = atomicAdd(cursor + key[j], 1u);
-            ordered[pos] = make_float4(x[j], y[j], z[j], __uint_as_float((uint32_t)(base + j * 256 + threadIdx.x)));
+            pos[j] = 0;
+            if (key[j] != PC_BIN_SKIP) pos[j] = atomicAdd(cursor + key[j], 1u);
         }
+#pragma unroll
+        for (int j = 0; j < PC_KEY_ITEMS; j++)
+            if (key[j] != PC_BIN_SKIP) ordered[pos[j]] = make_float4(x[j], y[j], z[j], __uint_as_float((uint32_t)(base + j * 256 + threadIdx.x)));
     }
 }
