@@ -98,8 +98,9 @@ typedef struct pc_index_view {
     uint32_t root;         /* child reference of the whole cloud: inner node 0, or 0x80000000 | 0 (a leaf)      */
     uint32_t root_count;   /* points of the root when it is a leaf                                            */
     const void *points;    /* float4[n_points + 4]: x, y, z, original index (int bits), curve order; = records + 4 n_nodes */
-    const void *records;   /* float4[4 * n_nodes]: node i -> [min0 | max0 | min1 | max1] of its two children, .w words:
-                              min.w = child reference (bit 31: leaf, low bits: first point), max.w = leaf point count   */
+    const void *records;   /* float4[4 * n_nodes]: node i -> 16 words, the boxes of its two children interleaved per axis:
+                              [min0.x min1.x min0.y min1.y min0.z min1.z ref0 ref1 | max0.x max1.x max0.y max1.y max0.z max1.z cnt0 cnt1]
+                              ref = child reference (bit 31: leaf, low bits: first point), cnt = leaf point count       */
     float bbox_lo[3], bbox_hi[3];
 } pc_index_view;
 

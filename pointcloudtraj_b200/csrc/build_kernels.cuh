@@ -2,10 +2,14 @@
 //
 // Index layout in HBM: ONE float4 array (`tree`) per index,
 //   records tree[0 .. 4 (n-1))   : inner node i of the binary radix tree over the curve-sorted keys (T. Karras, HPG 2012) is the
-//                                  64-byte record tree[4i .. 4i+3] = [min0 | max0 | min1 | max1], the tight boxes of its two
-//                                  children; the .w words hold the children: min.w = child reference, max.w = number of points
-//                                  when the child is a leaf.  Every node is split where the highest differing bit of its first
-//                                  and last key flips, so node boundaries coincide with the cells of the curve.
+//                                  64-byte record tree[4i .. 4i+3], the tight boxes of its two children with the two children
+//                                  INTERLEAVED per axis, as 16 words:
+//                                    [min0.x min1.x min0.y min1.y min0.z min1.z ref0 ref1 | max0.x max1.x max0.y max1.y max0.z max1.z cnt0 cnt1]
+//                                  (ref = child reference, cnt = number of points when the child is a leaf), so that a
+//                                  256-bit load puts (child 0, child 1) of one bound into adjacent registers and one packed
+//                                  fp32x2 instruction handles both children (query_kernels.cuh).  Every node is split where
+//                                  the highest differing bit of its first and last key flips, so node boundaries coincide
+//                                  with the cells of the curve.
 //   points  tree[4 (n-1) .. +n+PC_LEAF) : (x, y, z, original index as int bits) in curve order, padded with PC_LEAF copies of
 //                                  the last point (a leaf scan reads PC_LEAF consecutive points from any start).
 // A child whose range holds <= PC_LEAF points is a LEAF: its reference is PC_REF_LEAF | (index of its first point).  Inner
@@ -123,6 +127,11 @@ pc_keygen_kernel(const float *__restrict__ xyz, int64_t n, int stride, const uin
 // sorted keys: range, split, child references (the .w words of its record) and the parent links of its inner children.
 // The arrival counters of the fit kernel are cleared here.
 #define PC_NODE_UNUSED 0xffffffffu
+// word offsets inside a record (see the layout above); child slot c = 0 / 1
+#define PC_REC_LO(axis, c) (2 * (axis) + (c))
+#define PC_REC_HI(axis, c) (8 + 2 * (axis) + (c))
+#define PC_REC_REF(c) (6 + (c))
+#define PC_REC_CNT(c) (14 + (c))
 #ifndef PC_FIT_ACQREL
 #define PC_FIT_ACQREL 1             // arrival counter: one acq_rel atomic instead of fence + atomic + fence (-8 % build time)
 #endif
@@ -146,10 +155,11 @@ pc_tree_nodes_kernel(const float *__restrict__ xyz, int stride, const uint32_t *
     int64_t f, l, s;
     pc_lbvh_node(keys, n, i, &f, &l, &s);
     float *w = reinterpret_cast<float *>(rec + 4 * i);
-    if (l - f + 1 <= PC_LEAF) { w[3] = __uint_as_float(PC_NODE_UNUSED); return; }   // collapsed into a leaf of its parent
+    if (l - f + 1 <= PC_LEAF) { w[PC_REC_REF(0)] = __uint_as_float(PC_NODE_UNUSED); return; }   // collapsed into a leaf of its parent
     uint32_t r0, c0, r1, c1;
     pc_lbvh_children(f, l, s, &r0, &c0, &r1, &c1);
-    w[3] = __uint_as_float(r0); w[7] = __uint_as_float(c0); w[11] = __uint_as_float(r1); w[15] = __uint_as_float(c1);
+    w[PC_REC_REF(0)] = __uint_as_float(r0); w[PC_REC_CNT(0)] = __uint_as_float(c0);
+    w[PC_REC_REF(1)] = __uint_as_float(r1); w[PC_REC_CNT(1)] = __uint_as_float(c1);
     if (!(r0 & PC_REF_LEAF)) parent[r0] = (int32_t)i;
     if (!(r1 & PC_REF_LEAF)) parent[r1] = (int32_t)i;
 }
@@ -185,11 +195,11 @@ pc_tree_fit_kernel(float4 *rec, const float4 *__restrict__ points, const int32_t
     const bool exists = i < n - 1;
     volatile float *w = reinterpret_cast<volatile float *>(rec + 4 * (exists ? i : 0));
     uint32_t r0 = PC_NODE_UNUSED, c0 = 0, r1 = 0, c1 = 0;
-    if (exists) r0 = __float_as_uint(w[3]);
+    if (exists) r0 = __float_as_uint(w[PC_REC_REF(0)]);
     const bool used = exists && r0 != PC_NODE_UNUSED;
     bool filled0 = false, filled1 = false;
     if (used) {
-        c0 = __float_as_uint(w[7]); r1 = __float_as_uint(w[11]); c1 = __float_as_uint(w[15]);
+        c0 = __float_as_uint(w[PC_REC_CNT(0)]); r1 = __float_as_uint(w[PC_REC_REF(1)]); c1 = __float_as_uint(w[PC_REC_CNT(1)]);
         if (r0 & PC_REF_LEAF) { pc_leaf_box(points, r0 & ~PC_REF_LEAF, c0, &s_box[t][0][0], &s_box[t][0][3]); filled0 = true; }
         if (r1 & PC_REF_LEAF) { pc_leaf_box(points, r1 & ~PC_REF_LEAF, c1, &s_box[t][1][0], &s_box[t][1][3]); filled1 = true; }
     }
@@ -225,8 +235,13 @@ pc_tree_fit_kernel(float4 *rec, const float4 *__restrict__ points, const int32_t
     }
     if (!used) return;
     // the slots known so far go to the node's record (the others belong to children in other CTAs)
-    if (filled0) { w[0] = s_box[t][0][0]; w[1] = s_box[t][0][1]; w[2] = s_box[t][0][2]; w[4] = s_box[t][0][3]; w[5] = s_box[t][0][4]; w[6] = s_box[t][0][5]; }
-    if (filled1) { w[8] = s_box[t][1][0]; w[9] = s_box[t][1][1]; w[10] = s_box[t][1][2]; w[12] = s_box[t][1][3]; w[13] = s_box[t][1][4]; w[14] = s_box[t][1][5]; }
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        if (c ? filled1 : filled0) {
+#pragma unroll
+            for (int a = 0; a < 3; a++) { w[PC_REC_LO(a, c)] = s_box[t][c][a]; w[PC_REC_HI(a, c)] = s_box[t][c][3 + a]; }
+        }
+    }
     // ---- phase B: arrivals across CTAs ---------------------------------------------------------------------------------------
     // Every used node announces the slots it filled to its own counter; a node that is complete and whose parent did NOT take
     // its box in phase A (the parent sits in another CTA) pushes the box upwards.
@@ -253,12 +268,13 @@ pc_tree_fit_kernel(float4 *rec, const float4 *__restrict__ points, const int32_t
         const int32_t par = parent[node];
         if (par < 0) break;                                    // the root is complete
         volatile float *c = reinterpret_cast<volatile float *>(rec + 4 * node);
-        const float mlx = fminf(c[0], c[8]), mly = fminf(c[1], c[9]), mlz = fminf(c[2], c[10]);
-        const float mhx = fmaxf(c[4], c[12]), mhy = fmaxf(c[5], c[13]), mhz = fmaxf(c[6], c[14]);
         volatile float *p = reinterpret_cast<volatile float *>(rec + 4 * (int64_t)par);
-        const int slot = __float_as_uint(p[3]) == (uint32_t)node ? 0 : 8;     // left child = first reference of the parent
-        p[slot + 0] = mlx; p[slot + 1] = mly; p[slot + 2] = mlz;
-        p[slot + 4] = mhx; p[slot + 5] = mhy; p[slot + 6] = mhz;
+        const int slot = __float_as_uint(p[PC_REC_REF(0)]) == (uint32_t)node ? 0 : 1;     // left child = first reference of the parent
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            p[PC_REC_LO(a, slot)] = fminf(c[PC_REC_LO(a, 0)], c[PC_REC_LO(a, 1)]);
+            p[PC_REC_HI(a, slot)] = fmaxf(c[PC_REC_HI(a, 0)], c[PC_REC_HI(a, 1)]);
+        }
         node = par;
         add = 1;
     }
@@ -288,7 +304,8 @@ pc_tree_seed_kernel(const float4 *__restrict__ rec, uint32_t root, uint32_t root
         bool inner[2] = { false, false }, isleaf[2] = { false, false };
         if (lane < n) {
             const float *w = reinterpret_cast<const float *>(rec + 4ull * cur[lane]);
-            r[0] = __float_as_uint(w[3]); c[0] = __float_as_uint(w[7]); r[1] = __float_as_uint(w[11]); c[1] = __float_as_uint(w[15]);
+            r[0] = __float_as_uint(w[PC_REC_REF(0)]); c[0] = __float_as_uint(w[PC_REC_CNT(0)]);
+            r[1] = __float_as_uint(w[PC_REC_REF(1)]); c[1] = __float_as_uint(w[PC_REC_CNT(1)]);
             for (int k = 0; k < 2; k++) { isleaf[k] = (r[k] & PC_REF_LEAF) != 0; inner[k] = !isleaf[k]; }
         }
         int n_new = 0;

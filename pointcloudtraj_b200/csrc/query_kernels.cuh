@@ -39,27 +39,12 @@ struct pc_tree {
     const uint32_t *__restrict__ seeds;  // top of the tree expanded to <= 32 inner nodes (+ leaves met on the way): pc_tree_seed_kernel
 };
 
-// one box (min, max: 32 bytes, 32-byte aligned) with ONE 256-bit read-only load (sm_100: LDG.E.256)
-__device__ __forceinline__ void pc_load_box(const float4 *__restrict__ box, float4 &lo, float4 &hi)
-{
-    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
-        : "l"(box));
-}
-
-__device__ __forceinline__ float pc_box_d2(const float4 lo, const float4 hi, float qx, float qy, float qz)
-{
-    float dx = fmaxf(fmaxf(lo.x - qx, qx - hi.x), 0.0f);
-    float dy = fmaxf(fmaxf(lo.y - qy, qy - hi.y), 0.0f);
-    float dz = fmaxf(fmaxf(lo.z - qz, qz - hi.z), 0.0f);
-    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-}
-
 // ---- packed fp32x2 arithmetic (Blackwell: FADD2 / FFMA2) ------------------------------------------------------------------
-// The 64-query packets give every lane TWO queries; their box and point distances are computed two at a time with the packed
-// add.f32x2 / fma.f32x2 instructions of sm_100 (SASS FADD2 / FFMA2 -- a box bound or point coordinate enters as a scalar
-// operand that the instruction broadcasts to both halves, so no packing moves are needed).  Each half is an ordinary IEEE
-// fp32 operation: the results are bit-identical with the scalar code, at 15 instead of 24 instructions per (box, 2 queries).
+// sm_100 adds packed add.f32x2 / fma.f32x2 (SASS FADD2 / FFMA2): two independent IEEE fp32 operations per instruction on a
+// register pair, and an operand may be a scalar that the instruction broadcasts to both halves.  The records interleave the
+// two children per axis (build_kernels.cuh), so the distance of one query to BOTH child boxes takes 15 instructions instead
+// of 24 -- in every walk, whatever the number of queries per lane -- and the 64-query packets also scan a leaf for their two
+// queries at once.  Each half is an ordinary fp32 operation: the results are bit-identical with scalar code.
 __device__ __forceinline__ float2 pc_add2(float2 a, float2 b)
 {
     float2 r;
@@ -75,15 +60,31 @@ __device__ __forceinline__ float2 pc_fma2(float2 a, float2 b, float2 c)
     return r;
 }
 
-// squared distance of a box to two queries; nq* = (-qa, -qb) per axis.  Same operations as pc_box_d2, two at a time.
-__device__ __forceinline__ float2 pc_box_d2x2(const float4 lo, const float4 hi, float2 nqx, float2 nqy, float2 nqz)
+// one record: two 256-bit read-only loads (sm_100: LDG.E.256).  L = [min0.x min1.x min0.y min1.y min0.z min1.z ref0 ref1],
+// H = [max0.x max1.x max0.y max1.y max0.z max1.z cnt0 cnt1]
+struct pc_rec { float L[8], H[8]; };
+__device__ __forceinline__ pc_rec pc_load_rec(const float4 *__restrict__ rec)
+{
+    pc_rec r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.L[0]), "=f"(r.L[1]), "=f"(r.L[2]), "=f"(r.L[3]), "=f"(r.L[4]), "=f"(r.L[5]), "=f"(r.L[6]), "=f"(r.L[7]) : "l"(rec));
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.H[0]), "=f"(r.H[1]), "=f"(r.H[2]), "=f"(r.H[3]), "=f"(r.H[4]), "=f"(r.H[5]), "=f"(r.H[6]), "=f"(r.H[7]) : "l"(rec + 2));
+    return r;
+}
+__device__ __forceinline__ uint32_t pc_rec_ref(const pc_rec &r, int c) { return __float_as_uint(r.L[6 + c]); }
+__device__ __forceinline__ uint32_t pc_rec_cnt(const pc_rec &r, int c) { return __float_as_uint(r.H[6 + c]); }
+
+// squared distances of one query to the two child boxes of a record: (.x = child 0, .y = child 1).  Per axis
+// max(min - q, q - max, 0), then dz^2 + (dy^2 + dx^2) with fused multiply-adds, as the scalar formula did.
+__device__ __forceinline__ float2 pc_rec_d2(const pc_rec &r, float qx, float qy, float qz)
 {
     const float2 m1 = make_float2(-1.f, -1.f), zero = make_float2(0.f, 0.f);
-    float2 t1 = pc_add2(make_float2(lo.x, lo.x), nqx), t2 = pc_fma2(nqx, m1, make_float2(-hi.x, -hi.x));      // lo - q, q - hi
+    float2 t1 = pc_add2(make_float2(r.L[0], r.L[1]), make_float2(-qx, -qx)), t2 = pc_fma2(make_float2(r.H[0], r.H[1]), m1, make_float2(qx, qx));
     const float2 dx = make_float2(fmaxf(fmaxf(t1.x, t2.x), 0.0f), fmaxf(fmaxf(t1.y, t2.y), 0.0f));
-    t1 = pc_add2(make_float2(lo.y, lo.y), nqy); t2 = pc_fma2(nqy, m1, make_float2(-hi.y, -hi.y));
+    t1 = pc_add2(make_float2(r.L[2], r.L[3]), make_float2(-qy, -qy)); t2 = pc_fma2(make_float2(r.H[2], r.H[3]), m1, make_float2(qy, qy));
     const float2 dy = make_float2(fmaxf(fmaxf(t1.x, t2.x), 0.0f), fmaxf(fmaxf(t1.y, t2.y), 0.0f));
-    t1 = pc_add2(make_float2(lo.z, lo.z), nqz); t2 = pc_fma2(nqz, m1, make_float2(-hi.z, -hi.z));
+    t1 = pc_add2(make_float2(r.L[4], r.L[5]), make_float2(-qz, -qz)); t2 = pc_fma2(make_float2(r.H[4], r.H[5]), m1, make_float2(qz, qz));
     const float2 dz = make_float2(fmaxf(fmaxf(t1.x, t2.x), 0.0f), fmaxf(fmaxf(t1.y, t2.y), 0.0f));
     return pc_fma2(dz, dz, pc_fma2(dy, dy, pc_fma2(dx, dx, zero)));
 }
@@ -186,13 +187,10 @@ __device__ __forceinline__ void pc_nearest_traverse(const pc_tree &T, float qx, 
     int sp = 0;
     uint32_t ref = T.root;
     for (;;) {
-        const float4 *pair = T.rec + 4ull * ref;
-        float4 lo0, hi0, lo1, hi1;
-        pc_load_box(pair, lo0, hi0);
-        pc_load_box(pair + 2, lo1, hi1);
-        const float d0 = pc_box_d2(lo0, hi0, qx, qy, qz);
-        const float d1 = pc_box_d2(lo1, hi1, qx, qy, qz);
-        const uint32_t r0 = __float_as_uint(lo0.w), r1 = __float_as_uint(lo1.w);
+        const pc_rec rec = pc_load_rec(T.rec + 4ull * ref);
+        const float2 dd = pc_rec_d2(rec, qx, qy, qz);
+        const float d0 = dd.x, d1 = dd.y;
+        const uint32_t r0 = pc_rec_ref(rec, 0), r1 = pc_rec_ref(rec, 1);
         const bool first0 = d0 <= d1;
         const uint32_t rn = first0 ? r0 : r1, rf = first0 ? r1 : r0;
         const float dn = fminf(d0, d1), df = fmaxf(d0, d1);
@@ -323,7 +321,7 @@ __device__ __forceinline__ void pc_packet_traverse(const pc_tree &T, const float
     for (int j = 0; j < NQ; j++) any = any || b[j].thr >= 0.f;
     if (__ballot_sync(PC_FULL_MASK, any) == 0) return;
     if (T.root & PC_REF_LEAF) { pc_scan_leaf<NQ>(T.points + (T.root & ~PC_REF_LEAF), q, b); return; }
-    // NQ == 2: the lane's two queries packed per axis, negated (pc_box_d2x2, pc_scan_leaf_x2)
+    // NQ == 2: the lane's two queries packed per axis, negated, for the leaf scans (pc_scan_leaf_x2)
     const float2 nqx = make_float2(-q[0][0], -q[NQ - 1][0]), nqy = make_float2(-q[0][1], -q[NQ - 1][1]), nqz = make_float2(-q[0][2], -q[NQ - 1][2]);
     auto scan = [&](const float4 *pts) {
         if constexpr (NQ == 2) pc_scan_leaf_x2(pts, nqx, nqy, nqz, b);
@@ -333,14 +331,11 @@ __device__ __forceinline__ void pc_packet_traverse(const pc_tree &T, const float
     int sp = 0;
     uint32_t ref = T.root;
     for (;;) {
-        const float4 *pair = T.rec + 4ull * ref;
-        float4 lo0, hi0, lo1, hi1;
-        pc_load_box(pair, lo0, hi0);
-        pc_load_box(pair + 2, lo1, hi1);
+        const pc_rec rec = pc_load_rec(T.rec + 4ull * ref);
 #if PC_PACKET_PREFETCH
         {   // the next visit is one of the two children (or a stack entry): start their records' trip from L2 now, while the
             // box tests and votes below run (a leaf reference fetches a line of the points instead, also the next access)
-            const uint32_t c0 = __float_as_uint(lo0.w), c1 = __float_as_uint(lo1.w);
+            const uint32_t c0 = pc_rec_ref(rec, 0), c1 = pc_rec_ref(rec, 1);
             const float4 *a0 = (c0 & PC_REF_LEAF) ? T.points + (c0 & ~PC_REF_LEAF) : T.rec + 4ull * c0;
             const float4 *a1 = (c1 & PC_REF_LEAF) ? T.points + (c1 & ~PC_REF_LEAF) : T.rec + 4ull * c1;
             asm volatile("prefetch.global.L1 [%0];" ::"l"(a0));
@@ -349,15 +344,10 @@ __device__ __forceinline__ void pc_packet_traverse(const pc_tree &T, const float
 #endif
         float d0[NQ], d1[NQ];
         bool want0 = false, want1 = false;
-        if constexpr (NQ == 2) {
-            const float2 a0 = pc_box_d2x2(lo0, hi0, nqx, nqy, nqz), a1 = pc_box_d2x2(lo1, hi1, nqx, nqy, nqz);
-            d0[0] = a0.x; d0[1] = a0.y; d1[0] = a1.x; d1[1] = a1.y;
-        } else {
 #pragma unroll
-            for (int j = 0; j < NQ; j++) {
-                d0[j] = pc_box_d2(lo0, hi0, q[j][0], q[j][1], q[j][2]);
-                d1[j] = pc_box_d2(lo1, hi1, q[j][0], q[j][1], q[j][2]);
-            }
+        for (int j = 0; j < NQ; j++) {
+            const float2 dd = pc_rec_d2(rec, q[j][0], q[j][1], q[j][2]);       // both children at once
+            d0[j] = dd.x; d1[j] = dd.y;
         }
 #pragma unroll
         for (int j = 0; j < NQ; j++) {
@@ -376,7 +366,7 @@ __device__ __forceinline__ void pc_packet_traverse(const pc_tree &T, const float
                 const uint32_t pa = __ballot_sync(PC_FULL_MASK, d0[0] <= d1[0]) & ia;
                 first0 = 2 * __popc(pa) >= __popc(ia);
             }
-            const uint32_t r0 = __float_as_uint(lo0.w), r1 = __float_as_uint(lo1.w);
+            const uint32_t r0 = pc_rec_ref(rec, 0), r1 = pc_rec_ref(rec, 1);
             const uint32_t rn = first0 ? r0 : r1, rf = first0 ? r1 : r0;
             if (rn & PC_REF_LEAF) scan(T.points + (rn & ~PC_REF_LEAF));
             else next = rn;
@@ -498,12 +488,10 @@ pc_query_coop_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, in
         float dn = INFINITY, df = INFINITY;      // inner children to push (INFINITY: none)
         uint32_t cn = 0, cf = 0;
         if (active) {
-            const float4 *pair = T.rec + 4ull * e.x;
-            float4 lo0, hi0, lo1, hi1;
-            pc_load_box(pair, lo0, hi0);
-            pc_load_box(pair + 2, lo1, hi1);
-            const float d0 = pc_box_d2(lo0, hi0, qx, qy, qz), d1 = pc_box_d2(lo1, hi1, qx, qy, qz);
-            const uint32_t r0 = __float_as_uint(lo0.w), r1 = __float_as_uint(lo1.w);
+            const pc_rec rec = pc_load_rec(T.rec + 4ull * e.x);
+            const float2 dd = pc_rec_d2(rec, qx, qy, qz);
+            const float d0 = dd.x, d1 = dd.y;
+            const uint32_t r0 = pc_rec_ref(rec, 0), r1 = pc_rec_ref(rec, 1);
             const bool first0 = d0 <= d1;
             const uint32_t rn = first0 ? r0 : r1, rf = first0 ? r1 : r0;
             const float dnn = fminf(d0, d1), dff = fmaxf(d0, d1);

@@ -124,14 +124,11 @@ pc_range_coop_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstr
         bool push0 = false, push1 = false, leaf0 = false, leaf1 = false;
         uint32_t r0 = 0, r1 = 0, c0 = 0, c1 = 0;
         if (active) {
-            const float4 *pair = T.rec + 4ull * node;
-            float4 lo0, hi0, lo1, hi1;
-            pc_load_box(pair, lo0, hi0);
-            pc_load_box(pair + 2, lo1, hi1);
-            const bool in0 = pc_box_d2(lo0, hi0, qx, qy, qz) <= thr;
-            const bool in1 = pc_box_d2(lo1, hi1, qx, qy, qz) <= thr;
-            r0 = __float_as_uint(lo0.w); r1 = __float_as_uint(lo1.w);
-            c0 = __float_as_uint(hi0.w); c1 = __float_as_uint(hi1.w);
+            const pc_rec rec = pc_load_rec(T.rec + 4ull * node);
+            const float2 dd = pc_rec_d2(rec, qx, qy, qz);
+            const bool in0 = dd.x <= thr, in1 = dd.y <= thr;
+            r0 = pc_rec_ref(rec, 0); r1 = pc_rec_ref(rec, 1);
+            c0 = pc_rec_cnt(rec, 0); c1 = pc_rec_cnt(rec, 1);
             leaf0 = in0 && (r0 & PC_REF_LEAF); leaf1 = in1 && (r1 & PC_REF_LEAF);
             push0 = in0 && !(r0 & PC_REF_LEAF); push1 = in1 && !(r1 & PC_REF_LEAF);
         }
