@@ -107,6 +107,7 @@ struct pc_index {
     uint32_t *grid_cell_start = nullptr; int64_t grid_cells_cap = 0;
     float4 *grid_points = nullptr; int64_t grid_points_cap = 0;
     bool onesweep = true;              // PC_ONESWEEP=0: the three-kernel-per-pass radix sort (radix_sort.cuh)
+    uint16_t *hilbert_lut = nullptr;   // 16^3 + 32^3 Hilbert indices for the cell binning (pc_hilbert_lut_kernel)
     int key_ctas_per_sm = 0, sortkey_ctas_per_sm = 0;   // occupancy of the bin-count / key kernels (queried once)
     int bin_bits = 0;                  // PC_BIN_BITS: log2 of the number of cells of the binning (0 = from the batch size)
     bool order_bins_all = false;       // PC_ORDER_BINS=2: bin unbounded (nearest / full-NN) batches too
@@ -247,6 +248,11 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         TRY(cudaMalloc((void **)&ix->d_bbox, 8 * sizeof(uint32_t)));
         TRY(cudaHostAlloc((void **)&ix->h_bbox, 8 * sizeof(uint32_t), cudaHostAllocDefault));
         TRY(cudaMalloc((void **)&ix->digit_total, RS_RADIX * sizeof(uint32_t)));
+        // the Hilbert lookup tables of the cell binning: filled here, once, so that every stream of the handle may read them
+        TRY(cudaMalloc((void **)&ix->hilbert_lut, (size_t)(PC_LUT4_WORDS + PC_LUT5_WORDS) * sizeof(uint16_t)));
+        pc_hilbert_lut_kernel<<<PC_LUT5_WORDS / 256, 256, 0, ix->stream>>>(ix->hilbert_lut, ix->hilbert_lut + PC_LUT4_WORDS);
+        TRY(cudaGetLastError());
+        TRY(cudaStreamSynchronize(ix->stream));
         TRY(cudaHostAlloc((void **)&ix->tiny_q, PC_TINY_BATCH * 4 * sizeof(float), cudaHostAllocMapped));
         TRY(cudaHostAlloc((void **)&ix->tiny_f, PC_TINY_BATCH * sizeof(float), cudaHostAllocMapped));
         TRY(cudaHostAlloc((void **)&ix->tiny_i, PC_TINY_BATCH * sizeof(int32_t), cudaHostAllocMapped));
@@ -312,7 +318,7 @@ extern "C" void pc_index_destroy(pc_index *ix)
     if (ix->tiny_i) cudaFreeHost(ix->tiny_i);
     cudaFree(ix->d_xyz); cudaFree(ix->d_bbox); cudaFree(ix->keys_a); cudaFree(ix->keys_b);
     cudaFree(ix->vals_a); cudaFree(ix->vals_b); cudaFree(ix->tile_hist); cudaFree(ix->digit_total);
-    cudaFree(ix->tree); cudaFree(ix->scratch); cudaFree(ix->grid_cell_start); cudaFree(ix->grid_points);
+    cudaFree(ix->tree); cudaFree(ix->scratch); cudaFree(ix->grid_cell_start); cudaFree(ix->grid_points); cudaFree(ix->hilbert_lut);
     if (ix->ev_b0) cudaEventDestroy(ix->ev_b0);
     if (ix->ev_b1) cudaEventDestroy(ix->ev_b1);
     if (ix->ev_ready) cudaEventDestroy(ix->ev_ready);
@@ -627,9 +633,9 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
         PC_CUDA(ix, cudaMemsetAsync(L.bins, 0, (size_t)n_bins * sizeof(uint32_t), L.os));
         if (prof) PC_CUDA(ix, cudaEventRecord(L.ta, L.os));
         if (A.kind == PC_Q_RADIUS)
-            pc_bin_count_kernel<PC_KIND_RADIUS><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, A.R, d_idx, d_f, L.keys_a, L.bins, bin_bits, ix->shard_rank, ix->shard_n);
+            pc_bin_count_kernel<PC_KIND_RADIUS><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, A.R, d_idx, d_f, L.keys_a, L.bins, bin_bits, ix->shard_rank, ix->shard_n, ix->hilbert_lut);
         else
-            pc_bin_count_kernel<PC_KIND_NEAREST><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, A.R, d_idx, d_f, L.keys_a, L.bins, bin_bits, ix->shard_rank, ix->shard_n);
+            pc_bin_count_kernel<PC_KIND_NEAREST><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, A.R, d_idx, d_f, L.keys_a, L.bins, bin_bits, ix->shard_rank, ix->shard_n, ix->hilbert_lut);
         if (prof) PC_CUDA(ix, cudaEventRecord(L.tb, L.os));
         pc_bin_scan_tiles<<<n_tiles, 256, 0, L.os>>>(L.bins, tile_sum);
         pc_bin_scan_top<<<1, 1024, 0, L.os>>>(tile_sum, n_tiles, L.counter + 1);

@@ -720,7 +720,14 @@ __device__ __forceinline__ pc_bin_frame pc_make_bin_frame(const uint32_t *__rest
 __device__ __forceinline__ uint32_t pc_hilbert_cells_var(uint32_t x, uint32_t y, uint32_t z, int bits);
 template <int BITS> __device__ __forceinline__ uint32_t pc_hilbert_cells_n(uint32_t x, uint32_t y, uint32_t z);
 
-__device__ __forceinline__ uint32_t pc_bin_of(float x, float y, float z, const pc_bin_frame &F)
+// 3-D Hilbert indices of the 16^3 and 32^3 blocks as lookup tables (2 + 64 KB, L1-resident): the transform itself is ~100
+// instructions per query, most of what the count kernel executes.  Filled once per device by pc_hilbert_lut_kernel.
+#define PC_LUT4_WORDS 4096
+#define PC_LUT5_WORDS 32768
+__global__ void __launch_bounds__(256)
+pc_hilbert_lut_kernel(uint16_t *__restrict__ lut4, uint16_t *__restrict__ lut5);
+
+__device__ __forceinline__ uint32_t pc_bin_of(float x, float y, float z, const pc_bin_frame &F, const uint16_t *__restrict__ lut)
 {
     uint32_t c[3];
     const float v[3] = { x, y, z };
@@ -733,8 +740,8 @@ __device__ __forceinline__ uint32_t pc_bin_of(float x, float y, float z, const p
     const uint32_t mask = (1u << F.low) - 1u;
     uint32_t inner;                                       // unrolled transforms for the usual block sizes (warp-uniform switch)
     switch (F.low) {
-    case 4: inner = pc_hilbert_cells_n<4>(c[0] & mask, c[1] & mask, c[2] & mask); break;
-    case 5: inner = pc_hilbert_cells_n<5>(c[0] & mask, c[1] & mask, c[2] & mask); break;
+    case 4: inner = __ldg(lut + (((c[2] & mask) << 8) | ((c[1] & mask) << 4) | (c[0] & mask))); break;
+    case 5: inner = __ldg(lut + PC_LUT4_WORDS + (((c[2] & mask) << 10) | ((c[1] & mask) << 5) | (c[0] & mask))); break;
     case 6: inner = pc_hilbert_cells_n<6>(c[0] & mask, c[1] & mask, c[2] & mask); break;
     case 7: inner = pc_hilbert_cells_n<7>(c[0] & mask, c[1] & mask, c[2] & mask); break;
     default: inner = pc_hilbert_cells_var(c[0] & mask, c[1] & mask, c[2] & mask, F.low); break;
@@ -788,11 +795,20 @@ __device__ __forceinline__ uint32_t pc_hilbert_cells_n(uint32_t x, uint32_t y, u
     return (pc_spread10(X[0]) << 2) | (pc_spread10(X[1]) << 1) | pc_spread10(X[2]);
 }
 
+__global__ void __launch_bounds__(256)
+pc_hilbert_lut_kernel(uint16_t *__restrict__ lut4, uint16_t *__restrict__ lut5)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < PC_LUT4_WORDS) lut4[i] = (uint16_t)pc_hilbert_cells_n<4>(i & 15u, (i >> 4) & 15u, (i >> 8) & 15u);
+    if (i < PC_LUT5_WORDS) lut5[i] = (uint16_t)pc_hilbert_cells_n<5>(i & 31u, (i >> 5) & 31u, (i >> 10) & 31u);
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(256)
 pc_bin_count_kernel(const float *__restrict__ q, int64_t m, int qstride, const uint32_t *__restrict__ bbox,
                     pc_radius_dev R, int32_t *__restrict__ out_idx, float *__restrict__ out_f,
-                    uint32_t *__restrict__ cellkey, uint32_t *__restrict__ bins, int bin_bits, int shard_rank, int shard_n)
+                    uint32_t *__restrict__ cellkey, uint32_t *__restrict__ bins, int bin_bits, int shard_rank, int shard_n,
+                    const uint16_t *__restrict__ lut)
 {
     __shared__ int s_shard_shift;
     __shared__ pc_bin_frame s_frame;
@@ -830,7 +846,7 @@ pc_bin_count_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
             }
             uint32_t key = PC_BIN_SKIP;
             if (search) {
-                key = pc_bin_of(x[j], y[j], z[j], F);
+                key = pc_bin_of(x[j], y[j], z[j], F, lut);
                 atomicAdd(bins + key, 1u);
             }
             cellkey[i] = key;
