@@ -22,8 +22,9 @@
 #define PC_THR_SLACK 1.00000095367431640625f   // 1 + 2^-20
 #define PC_NO_NODE 0xffffffffu
 #ifndef PC_PACKET_MIN_CTAS
-#define PC_PACKET_MIN_CTAS 8        // resident CTAs per SM the packet kernels are compiled for (<= 64 registers: -2 % search
-                                    // time against 7 CTAs at 72 registers, profiles/r2_variants_ab.txt)
+#define PC_PACKET_MIN_CTAS 10       // resident CTAs per SM the packet kernels are compiled for (<= 48 registers).  With the packed
+                                    // arithmetic the kernel waits on record loads more than on issue slots: 10 CTAs 0.81 ms,
+                                    // 9: 0.82, 8: 0.85, 6: 0.87, 12 (40 registers, spills): 0.97 (profiles/r2_variants_ab.txt)
 #endif
 #ifndef PC_PACKET_PREFETCH
 #define PC_PACKET_PREFETCH 0        // 1: when a record arrives, pull the records of its two children towards L1 (measured:
@@ -344,10 +345,16 @@ __device__ __forceinline__ void pc_packet_traverse(const pc_tree &T, const float
 #endif
         float d0[NQ], d1[NQ];
         bool want0 = false, want1 = false;
+        if constexpr (NQ == 2) {
+            // from the packed negated copies, so that the queries are held once (registers: the kernel runs 10 CTAs per SM)
+            const float2 da = pc_rec_d2(rec, -nqx.x, -nqy.x, -nqz.x), db = pc_rec_d2(rec, -nqx.y, -nqy.y, -nqz.y);
+            d0[0] = da.x; d1[0] = da.y; d0[1] = db.x; d1[1] = db.y;
+        } else {
 #pragma unroll
-        for (int j = 0; j < NQ; j++) {
-            const float2 dd = pc_rec_d2(rec, q[j][0], q[j][1], q[j][2]);       // both children at once
-            d0[j] = dd.x; d1[j] = dd.y;
+            for (int j = 0; j < NQ; j++) {
+                const float2 dd = pc_rec_d2(rec, q[j][0], q[j][1], q[j][2]);       // both children at once
+                d0[j] = dd.x; d1[j] = dd.y;
+            }
         }
 #pragma unroll
         for (int j = 0; j < NQ; j++) {
