@@ -168,6 +168,49 @@ int  pc_clearance_batch(pc_index *ix, const pc_traj *traj, int64_t n_traj,
                         double dt, double horizon, const pc_radius_params *params,
                         int32_t *out_first_hit, float *out_min_radius, int32_t *out_n_samples);
 
+/* ---- the RRT* sample stream and one speculative expansion batch, generated on the device ----------- */
+/* genSample's state (corridor_finder.cpp:333-358, the branches taken while no path is known: inform_status == false).
+ * engine_state is the state of std::default_random_engine (= minstd_rand0; the reference seeds it with 0, :12, which the
+ * standard maps to state 1): the next draw is 16807 * engine_state mod (2^31 - 1).  lo/hi are the bounds of rand_x, rand_y,
+ * rand_z, in_lo/in_hi those of rand_x_in, rand_y_in, rand_z_in (setPt, :52-91). */
+typedef struct pc_sampler {
+    uint32_t engine_state, reserved;
+    double goal_ratio, inlier_ratio;
+    double end_pt[3];
+    double lo[3], hi[3];
+    double in_lo[3], in_hi[3];
+} pc_sampler;
+/* The next k samples of that stream, bit-identical with k calls of genSample() on libstdc++ (two draws per uniform double,
+ * one or four uniforms per sample; the variable stride is resolved on the device, see sampler_kernels.cuh).  out_xyz: k x 3
+ * doubles in `space` (PC_HOST or PC_DEVICE); *out_engine_state (host, nullable): the state to continue from (seed a host
+ * engine with it).  The informed-ellipsoid branch (:361-378, libm calls) is not offered: generate those samples on the host. */
+int  pc_sample_batch(pc_index *ix, const pc_sampler *sampler, int64_t k, int space, double *out_xyz, uint32_t *out_engine_state);
+
+/* The frozen node set a speculative batch is steered against: centres (n x 3 doubles, Node::coord), radii (Node::radius) and
+ * valid flags, in node-list order; host memory. */
+typedef struct pc_node_set {
+    int64_t n;
+    const double *coord;
+    const float *radius;
+    const uint8_t *valid;
+} pc_node_set;
+typedef struct pc_candidate {      /* one new node the expansion loop would go on with */
+    double center[3];              /* genNewNode's centre (corridor_finder.cpp:385-402) */
+    float radius;                  /* radiusSearch(centre) */
+    int32_t nearest;               /* the vertex it was steered from (index into the node set) */
+} pc_candidate;
+/* One batch of the expansion loop (SafeRegionExpansion, corridor_finder.cpp:720-731) without per-sample host traffic: the
+ * next k samples of `sampler` are generated on the device, each is steered from its nearest vertex of `set` (findNearstVertex
+ * on the float32 centres, exact fp64 distances; `nodes` is a second handle that holds the index of the node set and is
+ * rebuilt here), radiusSearch answers the centres against `cloud`'s index, and only the candidates the loop would keep
+ * (nearest vertex valid, centre z >= z_l, radius >= safety_margin, :726-731) come back, in sample order.  out: host memory,
+ * cap entries; *out_count is always the number of candidates (PC_ECAP if it exceeds cap).  Both handles must live on the
+ * same device.  Identical, candidate for candidate, with k x genSample + pc_nearest_batch + steering on the host +
+ * pc_radius_batch (tests/test_sampler_gpu.py). */
+int  pc_expand_batch(pc_index *cloud, pc_index *nodes, const pc_node_set *set, const pc_sampler *sampler,
+                     const pc_radius_params *params, double z_l, double safety_margin, int64_t k,
+                     pc_candidate *out, int64_t cap, int64_t *out_count, uint32_t *out_engine_state);
+
 /* ---- pinned host memory for PC_HOST calls ------------------------------------------------------ */
 void *pc_host_alloc(int64_t bytes);
 void  pc_host_free(void *p);

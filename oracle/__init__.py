@@ -93,6 +93,9 @@ def lib():
                                                C.c_double, C.c_double, C.c_double, C.c_int64, _f32p, _f64p,
                                                _i64p, _f64p]
         L.po_check_safe_trajectory.restype = C.c_int64
+        L.po_gen_samples.argtypes = [C.c_void_p, C.c_int64, _f64p]
+        L.po_steer.argtypes = [_f64p, _f64p, C.c_float, _f64p]
+        L.po_steer_batch.argtypes = [_f64p, C.c_int64, _f64p, _f32p, _i32p, _f64p]
         _lib = L
     return _lib
 
@@ -134,6 +137,44 @@ class RadiusParams(C.Structure):
         p.search_margin, p.max_radius, p.sample_range = search_margin, max_radius, sample_range
         p.start[0], p.start[1], p.start[2] = [float(v) for v in start]
         return p
+
+
+class Sampler(C.Structure):
+    """Mirror of po_sampler / pc_sampler: genSample's state (corridor_finder.cpp:333-358) -- the minstd_rand0 engine state and the
+    bounds setPt gives the uniform distributions (:52-91)."""
+    _fields_ = [("engine_state", C.c_uint32), ("reserved", C.c_uint32), ("goal_ratio", C.c_double), ("inlier_ratio", C.c_double),
+                ("end_pt", C.c_double * 3), ("lo", C.c_double * 3), ("hi", C.c_double * 3), ("in_lo", C.c_double * 3), ("in_hi", C.c_double * 3)]
+
+    @classmethod
+    def make(cls, start, end, box, sample_range, safety_margin, inlier_ratio, goal_ratio, engine_state=1):
+        """The state after setParam(safety_margin, ., ., sample_range) + setPt(start, end, *box, ...); engine_state 1 is what
+        default_random_engine(0) starts from."""
+        s = cls()
+        s.engine_state, s.goal_ratio, s.inlier_ratio = int(engine_state), float(goal_ratio), float(inlier_ratio)
+        xl, xh, yl, yh, zl, zh = [float(v) for v in box]
+        for a in range(3):
+            s.end_pt[a] = float(end[a])
+        s.lo[0], s.hi[0], s.lo[1], s.hi[1], s.lo[2], s.hi[2] = xl, xh, yl, yh, zl + safety_margin, zh
+        s.in_lo[0], s.in_hi[0] = start[0] - sample_range, start[0] + sample_range
+        s.in_lo[1], s.in_hi[1] = start[1] - sample_range, start[1] + sample_range
+        s.in_lo[2], s.in_hi[2] = zl + safety_margin, zh
+        return s
+
+
+def gen_samples(sampler: Sampler, k):
+    """The next k samples of the stream (float64 (k, 3)); sampler.engine_state is advanced."""
+    out = np.empty((int(k), 3))
+    lib().po_gen_samples(C.byref(sampler), int(k), _ptr(out, _f64p))
+    return out
+
+
+def steer(samples, node_coord, node_radius, nearest):
+    """genNewNode's centres for samples[j] steered from node nearest[j] (float64 (k, 3))."""
+    samples = np.ascontiguousarray(samples, np.float64); node_coord = np.ascontiguousarray(node_coord, np.float64)
+    node_radius = np.ascontiguousarray(node_radius, np.float32); nearest = np.ascontiguousarray(nearest, np.int32)
+    out = np.empty_like(samples)
+    lib().po_steer_batch(_ptr(samples, _f64p), len(samples), _ptr(node_coord, _f64p), _ptr(node_radius, _f32p), _ptr(nearest, _i32p), _ptr(out, _f64p))
+    return out
 
 
 class _KdBase:
@@ -331,6 +372,7 @@ def planner_lib():
         L.rp_get_path.argtypes = [_f64p, _f64p, C.c_int]
         L.rp_get_tree.argtypes = [_f64p, C.c_int]
         L.rp_stats.argtypes = [C.POINTER(C.c_longlong)]
+        L.rp_gen_samples.argtypes = [C.c_longlong, _f64p]
         L.rp_radius_search.argtypes = [_f64p]
         L.rp_radius_search.restype = d
         L.rp_radius_batch.argtypes = [_f64p, C.c_longlong, _f64p]
@@ -392,6 +434,12 @@ class PlannerReference:
         s = (C.c_longlong * 6)()
         self._L.rp_stats(s)
         return dict(nodes=s[0], path_exists=bool(s[1]), cloud_queries=s[2], rebuilds=s[3], warnings=s[4], global_navi=bool(s[5]))
+
+    def gen_samples(self, k):
+        """k calls of the unmodified genSample on the planner's own engine: float64 (k, 3)."""
+        out = np.empty((int(k), 3))
+        self._L.rp_gen_samples(int(k), _ptr(out, _f64p))
+        return out
 
     def radius_search(self, p):
         p = np.ascontiguousarray(p, np.float64)

@@ -11,6 +11,10 @@
  *   po_binomial              follows Planner/src/bezier_base.cpp:35-48,256-266 (int factorial quotient)
  *   po_bezier_pos            follows Planner/src/sim_planning_demo.cpp:715-727 (getPosFromBezier)
  *   po_check_safe_trajectory follows Planner/src/sim_planning_demo.cpp:729-781 (checkSafeTrajectory)
+ *   po_gen_samples           follows Planner/src/corridor_finder.cpp:333-358  (genSample while inform_status is false) on
+ *                            std::default_random_engine (minstd_rand0, eng(0) at :12) and libstdc++'s
+ *                            uniform_real_distribution<double> (generate_canonical, bits/random.tcc: two draws per double)
+ *   po_steer                 follows Planner/src/corridor_finder.cpp:385-402  (the centre genNewNode queries)
  *
  * The cloud query inside radiusSearch is PCL/FLANN float32 in the reference (un-vendored third
  * party, PCL 1.10 EXACT, Planner/CMakeLists.txt:18; no reference test pins its outputs).  Per
@@ -143,4 +147,68 @@ int64_t po_check_safe_trajectory(const kdo_tree *t, const po_radius_params *P,
     if (n_samples) *n_samples = k;
     if (min_radius) *min_radius = rmin;
     return first_hit;
+}
+
+/* ---- the sample stream ------------------------------------------------------------------------------------------------- */
+/* same field order as pc_sampler in include/pc_index.h */
+typedef struct {
+    uint32_t engine_state, reserved;
+    double goal_ratio, inlier_ratio;
+    double end_pt[3];
+    double lo[3], hi[3];
+    double in_lo[3], in_hi[3];
+} po_sampler;
+
+/* minstd_rand0: x' = 16807 x mod 2147483647 */
+static inline uint32_t po_lcg(uint32_t *st) { *st = (uint32_t)(((uint64_t)*st * 16807u) % 2147483647u); return *st; }
+
+/* std::generate_canonical<double, 53>(minstd_rand0): range r = max - min + 1 = 2147483646, m = 2 draws,
+ * sum = (x1 - 1) * 1 + (x2 - 1) * r, ret = sum / (double)(r * r) (the long double product rounded to double) */
+static double po_canonical(uint32_t *st)
+{
+    const long double r = 2147483646.0L;
+    double sum = 0.0, tmp = 1.0;
+    for (int k = 2; k != 0; --k) {
+        sum += (double)(po_lcg(st) - 1u) * tmp;
+        tmp = (double)(tmp * r);
+    }
+    double ret = sum / tmp;
+    if (ret >= 1.0) ret = nextafter(1.0, 0.0);
+    return ret;
+}
+
+static inline double po_uniform(uint32_t *st, double a, double b) { return po_canonical(st) * (b - a) + a; }
+
+/* k samples; S->engine_state is advanced */
+void po_gen_samples(po_sampler *S, int64_t k, double *out3)
+{
+    uint32_t st = S->engine_state;
+    for (int64_t i = 0; i < k; i++) {
+        double *pt = out3 + 3 * i;
+        const double bias = po_uniform(&st, 0.0, 1.0);
+        if (bias <= S->goal_ratio) { pt[0] = S->end_pt[0]; pt[1] = S->end_pt[1]; pt[2] = S->end_pt[2]; continue; }
+        if (bias > S->goal_ratio && bias <= (S->goal_ratio + S->inlier_ratio)) {
+            for (int a = 0; a < 3; a++) pt[a] = po_uniform(&st, S->in_lo[a], S->in_hi[a]);
+        } else {
+            for (int a = 0; a < 3; a++) pt[a] = po_uniform(&st, S->lo[a], S->hi[a]);
+        }
+    }
+    S->engine_state = st;
+}
+
+/* genNewNode's centre: the sample pulled onto the surface of the nearest node's sphere */
+void po_steer(const double sample[3], const double node[3], float node_radius, double center[3])
+{
+    const double dis = sqrt(sq(node[0] - sample[0]) + sq(node[1] - sample[1]) + sq(node[2] - sample[2]));
+    if (dis > node_radius) {
+        const double steer_dis = node_radius / dis;
+        for (int a = 0; a < 3; a++) center[a] = node[a] + (sample[a] - node[a]) * steer_dis;
+    } else {
+        for (int a = 0; a < 3; a++) center[a] = sample[a];
+    }
+}
+
+void po_steer_batch(const double *samples, int64_t k, const double *node_coord, const float *node_radius, const int32_t *nearest, double *centers)
+{
+    for (int64_t j = 0; j < k; j++) po_steer(samples + 3 * j, node_coord + 3 * (int64_t)nearest[j], node_radius[nearest[j]], centers + 3 * j);
 }

@@ -144,6 +144,11 @@ void rp_stats(long long out[6])
     out[5] = g_planner->getGlobalNaviStatus() ? 1 : 0;
 }
 
+// k calls of the UNMODIFIED genSample (corridor_finder.cpp:333-383) on the planner's own engine (eng(0), :12)
+void rp_gen_samples(long long k, double *out3)
+{
+    for (long long i = 0; i < k; i++) { const Vector3d v = g_planner->genSample(); out3[3 * i] = v(0); out3[3 * i + 1] = v(1); out3[3 * i + 2] = v(2); }
+}
 double rp_radius_search(const double *p) { Vector3d v(p[0], p[1], p[2]); return g_planner->radiusSearch(v); }
 void rp_radius_batch(const double *p, long long n, double *out) { for (long long i = 0; i < n; i++) out[i] = rp_radius_search(p + 3 * i); }
 int rp_check_traj_pt_col(const double *p) { Vector3d v(p[0], p[1], p[2]); return g_planner->checkTrajPtCol(v) ? 1 : 0; }

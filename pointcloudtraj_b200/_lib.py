@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "pc_host_alloc", "pc_host_free",
     "pc_comm_unique_id", "pc_comm_init", "pc_comm_destroy", "pc_index_broadcast", "pc_shard_range",
     "pc_launch_count", "pc_profile_enable", "pc_profile_last_batch", "pc_batch_shard", "pc_index_set_radius_arith",
-    "pc_profile_last_order_detail",
+    "pc_profile_last_order_detail", "pc_sample_batch", "pc_expand_batch",
 ]
 
 
@@ -44,6 +44,35 @@ class PcRadiusParams(C.Structure):
         p.search_margin, p.max_radius, p.sample_range = float(search_margin), float(max_radius), float(sample_range)
         p.start[0], p.start[1], p.start[2] = [float(v) for v in start]
         return p
+
+
+class PcSampler(C.Structure):
+    """pc_sampler: genSample's state while no path is known (corridor_finder.cpp:333-358) -- the minstd_rand0 engine state and
+    the bounds setPt (:52-91) gives the uniform distributions."""
+    _fields_ = [("engine_state", C.c_uint32), ("reserved", C.c_uint32), ("goal_ratio", C.c_double), ("inlier_ratio", C.c_double),
+                ("end_pt", C.c_double * 3), ("lo", C.c_double * 3), ("hi", C.c_double * 3), ("in_lo", C.c_double * 3), ("in_hi", C.c_double * 3)]
+
+    @classmethod
+    def make(cls, start, end, box, sample_range, safety_margin, inlier_ratio, goal_ratio, engine_state=1):
+        """The state after setParam(safety_margin, ., ., sample_range) + setPt(start, end, *box, ...); default_random_engine(0)
+        starts from state 1."""
+        s = cls()
+        s.engine_state, s.goal_ratio, s.inlier_ratio = int(engine_state), float(goal_ratio), float(inlier_ratio)
+        xl, xh, yl, yh, zl, zh = [float(v) for v in box]
+        for a in range(3):
+            s.end_pt[a] = float(end[a])
+        s.lo[0], s.hi[0], s.lo[1], s.hi[1], s.lo[2], s.hi[2] = xl, xh, yl, yh, zl + safety_margin, zh
+        s.in_lo[0], s.in_hi[0] = start[0] - sample_range, start[0] + sample_range
+        s.in_lo[1], s.in_hi[1] = start[1] - sample_range, start[1] + sample_range
+        s.in_lo[2], s.in_hi[2] = zl + safety_margin, zh
+        return s
+
+
+class PcNodeSet(C.Structure):
+    _fields_ = [("n", C.c_int64), ("coord", C.c_void_p), ("radius", C.c_void_p), ("valid", C.c_void_p)]
+
+
+PC_CANDIDATE_DTYPE = [("center", "<f8", (3,)), ("radius", "<f4"), ("nearest", "<i4")]      # pc_candidate, 32 bytes
 
 
 class PcTraj(C.Structure):
@@ -112,5 +141,8 @@ def load():
     L.pc_profile_enable.argtypes = [vp, i32]
     L.pc_profile_last_batch.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.pc_profile_last_order_detail.argtypes = [vp, C.POINTER(C.c_float)]
+    L.pc_sample_batch.argtypes = [vp, C.POINTER(PcSampler), i64, i32, vp, C.POINTER(C.c_uint32)]
+    L.pc_expand_batch.argtypes = [vp, vp, C.POINTER(PcNodeSet), C.POINTER(PcSampler), C.POINTER(PcRadiusParams), C.c_double, C.c_double,
+                                  i64, vp, i64, C.POINTER(i64), C.POINTER(C.c_uint32)]
     _lib = L
     return L

@@ -19,6 +19,7 @@
 #include "range_kernels.cuh"
 #include "clearance_kernels.cuh"
 #include "grid_kernels.cuh"
+#include "sampler_kernels.cuh"
 
 #define PC_VERSION_STRING "pcindex 0.2 (sm_100a)"
 #define PC_PIPE_LANES 3                 // concurrent H2D / kernel / D2H chunks for PC_HOST calls
@@ -1011,6 +1012,7 @@ extern "C" int pc_radius_batch(pc_index *ix, const float *q_xyz, int64_t m, int6
 
 #include "range_host.inl"
 #include "clearance_host.inl"
+#include "sampler_host.inl"
 #include "comm_host.inl"
 #include "kd_compat.inl"
 

@@ -210,6 +210,35 @@ class PointCloudIndex:
         self._check(self._L.pc_sphere_gather(self._h, c, float(radius), L.PC_HOST, C.c_void_p(out.ctypes.data), cnt.value, C.byref(cnt)))
         return out[: cnt.value]
 
+    def sample_batch(self, sampler: L.PcSampler, k, advance=True):
+        """The next k samples of the planner's stream, generated on the device (float64 (k, 3)); the sampler's engine state is
+        advanced past them (pc_sample_batch)."""
+        out = np.empty((int(k), 3), dtype=np.float64)
+        st = C.c_uint32(0)
+        self._check(self._L.pc_sample_batch(self._h, C.byref(sampler), int(k), L.PC_HOST, C.c_void_p(out.ctypes.data), C.byref(st)))
+        if advance:
+            sampler.engine_state = st.value
+        return out
+
+    def expand_batch(self, nodes: "PointCloudIndex", node_coord, node_radius, node_valid, sampler: L.PcSampler, params: L.PcRadiusParams,
+                     z_l, safety_margin, k, cap=None, advance=True):
+        """One speculative batch of the expansion loop on the device (pc_expand_batch): k samples steered against the frozen
+        node set, radiusSearch for the centres against THIS index; returns the candidates the loop would keep as a structured
+        array (center float64 x3, radius float32, nearest int32), in sample order."""
+        nc = np.ascontiguousarray(node_coord, dtype=np.float64)
+        nr = np.ascontiguousarray(node_radius, dtype=np.float32)
+        nv = np.ascontiguousarray(node_valid, dtype=np.uint8)
+        ns = L.PcNodeSet(nc.shape[0], nc.ctypes.data, nr.ctypes.data, nv.ctypes.data)
+        cap = int(k) if cap is None else int(cap)
+        out = np.empty(max(cap, 1), dtype=np.dtype(L.PC_CANDIDATE_DTYPE))
+        assert out.dtype.itemsize == 32
+        cnt, st = C.c_int64(0), C.c_uint32(0)
+        self._check(self._L.pc_expand_batch(self._h, nodes._h, C.byref(ns), C.byref(sampler), C.byref(params), float(z_l), float(safety_margin),
+                                            int(k), C.c_void_p(out.ctypes.data), cap, C.byref(cnt), C.byref(st)))
+        if advance:
+            sampler.engine_state = st.value
+        return out[: cnt.value]
+
     def clearance(self, traj_first_seg, seg_order, seg_T, seg_coef_off, coef, params: L.PcRadiusParams,
                   t_now=None, dt=0.02, horizon=2.0):
         """checkSafeTrajectory for a batch of piecewise Bezier trajectories (host arrays, CSR layout of

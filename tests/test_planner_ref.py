@@ -134,3 +134,20 @@ def test_oracle_bezier_and_clearance_walk_vs_compiled_reference():
             assert n == k and (rpts == mine["pts"][:k]).all()
             n_hit += hit
     assert n_hit > 5
+
+
+@pytest.mark.parametrize("goal,inlier", [(0.15, 0.3), (0.0, 0.5), (0.6, 0.2), (1.0, 0.0)])
+def test_oracle_sample_stream_vs_compiled_reference(goal, inlier):
+    """po_gen_samples (minstd_rand0 + libstdc++'s generate_canonical restated in C) against k calls of the unmodified genSample
+    (corridor_finder.cpp:333-383) on the planner's own engine: bit-identical samples, and the stream continues from the
+    returned engine state."""
+    start, end, box = (0.0, 0.0, 2.0), (40.0, 10.0, 2.0), (-50.0, 50.0, -50.0, 50.0, 0.0, 5.0)
+    ref = oracle.PlannerReference(0.6, 0.25, 1.5, 30.0)
+    ref.set_pt(start, end, box, 30.0, 1000, inlier, goal)
+    want = ref.gen_samples(300_000)
+    s = oracle.Sampler.make(start, end, box, 30.0, 0.6, inlier, goal)
+    got = oracle.gen_samples(s, 100_000)
+    got2 = oracle.gen_samples(s, 200_000)
+    assert (got == want[:100_000]).all() and (got2 == want[100_000:]).all()
+    share = (want == np.array(end)).all(1).mean()
+    assert abs(share - goal) < 0.01

@@ -1,0 +1,97 @@
+"""GPU parity tests for pc_sample_batch (genSample on the device) and pc_expand_batch (one speculative batch of the
+expansion loop with no per-sample host traffic)."""
+import numpy as np
+import pytest
+
+import oracle
+from pointcloudtraj_b200 import PC_QUERY_AUTO, PcError, PcRadiusParams, PcSampler, PointCloudIndex, synth
+
+pytestmark = pytest.mark.gpu
+
+START, END = (0.0, 0.0, 2.0), (40.0, 10.0, 2.0)
+BOX = (-50.0, 50.0, -50.0, 50.0, 0.0, 5.0)
+PRM = dict(safety_margin=0.6, search_margin=0.25, max_radius=1.5, sample_range=30.0)
+
+
+def _samplers(inlier, goal, state=1):
+    a = (START, END, BOX, PRM["sample_range"], PRM["safety_margin"], inlier, goal)
+    return PcSampler.make(*a, engine_state=state), oracle.Sampler.make(*a, engine_state=state)
+
+
+@pytest.fixture(scope="module")
+def ix():
+    h = PointCloudIndex(max_points=1 << 18, device=0)
+    yield h
+    h.close()
+
+
+@pytest.mark.parametrize("goal,inlier,k", [(0.15, 0.3, 1_000_003), (0.0, 0.5, 70_001), (1.0, 0.0, 50_000), (0.55, 0.45, 300_000),
+                                           (0.15, 0.3, 1), (0.15, 0.3, 7), (0.9, 0.05, 8192 * 3)])
+def test_sample_stream_vs_oracle(ix, goal, inlier, k):
+    """Bit-identical samples and engine state, whatever the share of one-uniform (goal) samples in the stream."""
+    ps, os_ = _samplers(inlier, goal)
+    got = ix.sample_batch(ps, k)
+    want = oracle.gen_samples(os_, k)
+    assert (got == want).all()
+    assert ps.engine_state == os_.engine_state
+    # the stream continues where the batch stopped: a second batch from the returned state
+    got2 = ix.sample_batch(ps, 1000)
+    want2 = oracle.gen_samples(os_, 1000)
+    assert (got2 == want2).all() and ps.engine_state == os_.engine_state
+
+
+@pytest.mark.skipif(not oracle.have_planner_reference(), reason="oracle/_ref/libplanner_ref.so not built")
+def test_sample_stream_vs_compiled_reference(ix):
+    """Against k calls of the UNMODIFIED genSample (corridor_finder.cpp:333-383) on the planner's own engine (eng(0))."""
+    ref = oracle.PlannerReference(**PRM)
+    ref.set_pt(START, END, BOX, 30.0, 1000, 0.3, 0.15)
+    want = ref.gen_samples(400_000)
+    ps, _ = _samplers(0.3, 0.15)
+    got = ix.sample_batch(ps, 400_000)
+    assert (got == want).all()
+
+
+def test_sample_bad_arguments(ix):
+    ps, _ = _samplers(0.3, 0.15, state=0)
+    with pytest.raises(PcError):
+        ix.sample_batch(ps, 10)
+    ps, _ = _samplers(0.3, 0.15)
+    assert ix.sample_batch(ps, 0).shape == (0, 3) and ps.engine_state == 1
+
+
+def _host_pipeline(ix, nodes, node_coord, node_radius, node_valid, osamp, P, z_l, safety_margin, k):
+    """The same batch through the buffer API: host samples, pc_nearest_batch on the node index, steering on the host,
+    pc_radius_batch, the loop's filter (corridor_finder.cpp:720-731)."""
+    s = oracle.gen_samples(osamp, k)
+    nodes.build(node_coord.astype(np.float32))
+    nn, _ = nodes.nearest(s.astype(np.float32), flags=PC_QUERY_AUTO)
+    ok = (nn >= 0) & (node_valid[np.maximum(nn, 0)] != 0)
+    c = oracle.steer(s, node_coord, node_radius, np.maximum(nn, 0))
+    r = ix.radius(c.astype(np.float32), P)
+    keep = ok & ~((c[:, 2] < z_l) | (r.astype(np.float64) < safety_margin))
+    return c[keep], r[keep], nn[keep]
+
+
+@pytest.mark.parametrize("n_nodes,k", [(1, 5000), (37, 4096), (3000, 200_000), (20_000, 1_000_000)])
+def test_expand_batch_vs_buffer_api(ix, n_nodes, k):
+    pts, half = synth.forest_cloud(200_000, seed=6, variant="J", return_half=True)
+    ix.build(pts)
+    rng = np.random.default_rng(n_nodes)
+    # a plausible frozen tree: nodes scattered around the start, float32 radii, a few invalid ones
+    node_coord = np.column_stack([rng.uniform(-25, 25, n_nodes), rng.uniform(-25, 25, n_nodes), rng.uniform(0.7, 4.0, n_nodes)])
+    node_coord[0] = START
+    node_radius = rng.uniform(0.6, 1.25, n_nodes).astype(np.float32)
+    node_valid = (rng.uniform(size=n_nodes) > 0.02).astype(np.uint8)
+    node_valid[0] = 1
+    P = PcRadiusParams.make(PRM["search_margin"], PRM["max_radius"], PRM["sample_range"], START)
+    ps, os_ = _samplers(0.3, 0.15, state=12345)
+    with PointCloudIndex(max_points=1 << 16, device=0) as nodes, PointCloudIndex(max_points=1 << 16, device=0) as nodes_h:
+        cand = ix.expand_batch(nodes, node_coord, node_radius, node_valid, ps, P, BOX[4], PRM["safety_margin"], k)
+        c, r, nn = _host_pipeline(ix, nodes_h, node_coord, node_radius, node_valid, os_, P, BOX[4], PRM["safety_margin"], k)
+        assert len(cand) == len(c) and 0 < len(c) < k
+        assert (cand["center"] == c).all() and (cand["radius"] == r).all() and (cand["nearest"] == nn).all()
+        assert ps.engine_state == os_.engine_state
+        # capacity overflow: the count is still reported
+        with pytest.raises(PcError) as e:
+            ix.expand_batch(nodes, node_coord, node_radius, node_valid, ps, P, BOX[4], PRM["safety_margin"], k, cap=3, advance=False)
+        assert e.value.code == -4
