@@ -423,6 +423,70 @@ def run_b200(args):
     host_roof_gbs = world * 16 * M * e2e_steps / host_roof_s / 1e9
     del d_q2, d_r2
 
+    # device-generated path (pc_expand_batch): a step's M samples are drawn on the device from the planner's engine state
+    # (minstd_rand0 + libstdc++'s uniform_real_distribution, bit-identical with genSample), steered from their nearest vertex of a
+    # frozen node set, answered by radiusSearch, and only the candidates the expansion loop keeps come back -- no 12 B/query
+    # H2D.  Timed by the host clock around the C-ABI call (host buffers in, host buffers out), like e2e.
+    from pointcloudtraj_b200 import PcSampler
+    rngn = np.random.default_rng(77 + rank)
+    n_nodes = 4096
+    node_coord = np.column_stack([rngn.uniform(-25, 25, n_nodes), rngn.uniform(-25, 25, n_nodes), rngn.uniform(0.7, 4.0, n_nodes)])
+    node_coord[0] = start
+    node_radius = rngn.uniform(0.6, 1.25, n_nodes).astype(np.float32)
+    node_valid = np.ones(n_nodes, np.uint8)
+    smp = PcSampler.make(start, (0.8 * half, 0.5 * half, 2.0), (-half, half, -half, half, 0.0, 4.0), PARAMS["sample_range"], 0.6, 0.3, 0.1,
+                         engine_state=1 + rank)
+    dg = None
+    with PointCloudIndex(max_points=1 << 16, device=local, stream=stream) as nodes_ix:
+        from pointcloudtraj_b200 import _lib as pclib
+        nset = pclib.PcNodeSet(n_nodes, node_coord.ctypes.data, node_radius.ctypes.data, node_valid.ctypes.data)
+        cand_pin = torch.empty(32 * M, dtype=torch.uint8).pin_memory()         # pc_candidate records, pinned like the e2e buffers
+        cand_np = cand_pin.numpy()
+        cnt_c, st_c = C.c_int64(0), C.c_uint32(0)
+
+        def step_expand(k):
+            rc = lib.pc_expand_batch(ix._h, nodes_ix._h, C.byref(nset), C.byref(smp), C.byref(P), 0.0, 0.6, k, C.c_void_p(cand_np.ctypes.data), M,
+                                     C.byref(cnt_c), C.byref(st_c))
+            if rc != 0:
+                raise RuntimeError(lib.pc_last_error(ix._h).decode())
+            smp.engine_state = st_c.value
+            return cnt_c.value
+        # same answers as the buffer API on a planner-sized batch: device samples -> pc_nearest_batch -> host steering -> pc_radius_batch
+        chk = PcSampler.make(start, (0.8 * half, 0.5 * half, 2.0), (-half, half, -half, half, 0.0, 4.0), PARAMS["sample_range"], 0.6, 0.3, 0.1, engine_state=4242)
+        kc = 200_000
+        s_host = ix.sample_batch(chk, kc, advance=False)
+        cand = ix.expand_batch(nodes_ix, node_coord, node_radius, node_valid, chk, P, 0.0, 0.6, kc, advance=False)
+        with PointCloudIndex(max_points=1 << 16, device=local) as nodes_chk:
+            nodes_chk.build(node_coord.astype(np.float32))
+            nn, _ = nodes_chk.nearest(s_host.astype(np.float32))
+        cn = node_coord[nn]
+        d = cn - s_host
+        dis = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2])
+        rad = node_radius[nn].astype(np.float64)
+        far = dis > rad
+        ctr = np.where(far[:, None], cn + (s_host - cn) * (rad / np.where(far, dis, 1.0))[:, None], s_host)
+        rr = ix.radius(ctr.astype(np.float32), P)
+        keep = ~((ctr[:, 2] < 0.0) | (rr.astype(np.float64) < 0.6))
+        dg_same = bool(len(cand) == int(keep.sum()) and (cand["center"] == ctr[keep]).all() and (cand["radius"] == rr[keep]).all())
+        for _ in range(2):
+            step_expand(M)
+        barrier()
+        dg_steps = max(3, min(args.steps, 8))
+        t0 = time.perf_counter()
+        n_cand = 0
+        for _ in range(dg_steps):
+            n_cand += step_expand(M)
+        dg_s = max_over_ranks(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        for _ in range(50):
+            step_expand(4096)
+        small_us = (time.perf_counter() - t0) / 50 * 1e6
+        dg = {"value": world * M * dg_steps / dg_s, "unit": "samples/s", "samples_per_call": M, "node_set": n_nodes,
+              "candidates_per_call": n_cand // dg_steps, "h2d_bytes_per_call": n_nodes * 29, "d2h_bytes_per_call": 32 * (n_cand // dg_steps) + 12,
+              "matches_buffer_api": dg_same, "planner_batch_4096_us": small_us,
+              "how": "pc_expand_batch: samples generated on the device from the engine state, nearest vertex + steering + radiusSearch + "
+                     "the loop's early rejections on the device; host clock around the call, result in host memory"}
+
     # strong scaling (N > 1): ONE batch of N x M queries against the time rank 0 needs for the whole batch alone, split two ways:
     #  (a) contiguous slices (pc_shard_range): every rank reads and answers only its N-th of the array -- a random, N times
     #      sparser sample of the batch, so packets are less coherent, but nothing is replicated;
@@ -544,7 +608,7 @@ def run_b200(args):
                 "all_queries_searched": {"value": all_searched_qps, "unit": UNIT, "note": "per GPU, same batch with sample_range = -1 (no early-outs), one stream"},
                 "index_build_ms_1M": float(np.median(build_ms[1:])), "index_broadcast_ms": bcast_ms,
                 "host_cpu_binding": (f"{len(numa_cpus)} CPUs next to the GPU (NVML affinity)" if numa_cpus else None),
-                "replicas_match_root": replica_ok, "strong": strong}
+                "replicas_match_root": replica_ok, "strong": strong, "device_generated": dg}
         if not args.no_cpu_baseline and world == 1:
             cb, r_cpu = cpu_baseline(pts, q_host, start, args.cpu_sample)
             cb["gpu_matches_cpu_sample"] = bool((r_cpu.astype(np.float32) == t_r[: len(r_cpu)].cpu().numpy()).all())

@@ -13,6 +13,7 @@
 //   firstCollision  Planner/src/status_inspector.cpp:33-46   ground-truth collision check of executed positions
 //   observe         Planner/src/camera_sensor.cpp:133-145    LiDAR-mode observation (all points within max_dist)
 //   NodeSnapshotIndex   corridor_finder.cpp:428-437, 462-464 batched findNearstVertex / treeRewire neighbourhoods against a frozen node set
+//   DeviceExpansion     corridor_finder.cpp:720-731, 333-358  one speculative batch of the expansion loop generated and answered on the device
 //   exportCorridor      sim_planning_demo.cpp:571-592        (Path, Radius) -> PolynomialTrajectoryExtra.path_* / radii
 //
 // No Eigen/PCL/ROS dependency: points are plain double[3] / float arrays (pcl::PointXYZ is x,y,z,pad float32 =
@@ -219,9 +220,42 @@ public:
         return nearest(samples, k, out_nearest, out_d2);
     }
     const char *lastError() const { return pc_last_error(ix_); }
+    pc_index *handle() { return ix_; }
 
 private:
     pc_index *ix_ = nullptr;
+};
+
+// One speculative batch of the expansion loop without per-sample host traffic (pc_expand_batch): the samples are generated on
+// the device from the planner's engine state, steered against the frozen node set, answered against the cloud, and only the
+// candidates the loop keeps come back.  `nodes` holds the index of the node set (rebuilt per batch).
+class DeviceExpansion {
+public:
+    DeviceExpansion(SafeRegionCloud &cloud, NodeSnapshotIndex &nodes) : cloud_(cloud), nodes_(nodes) {}
+
+    // returns PC_OK or an error code; centers (count x 3), radii (count), nearest (count, nullable) in sample order
+    int run(const pc_sampler &sampler, const pc_node_set &set, double z_l, int64_t k, std::vector<double> &centers, std::vector<double> &radii,
+            uint32_t *engine_state_after, std::vector<int32_t> *nearest = nullptr)
+    {
+        if ((int64_t)buf_.size() < k) buf_.resize((size_t)k);
+        int64_t count = 0;
+        const int rc = pc_expand_batch(cloud_.handle(), nodes_.handle(), &set, &sampler, &cloud_.params(), z_l, cloud_.safety_margin, k,
+                                       buf_.data(), (int64_t)buf_.size(), &count, engine_state_after);
+        if (rc != PC_OK) return rc;
+        centers.resize((size_t)count * 3); radii.resize((size_t)count);
+        if (nearest) nearest->resize((size_t)count);
+        for (int64_t i = 0; i < count; i++) {
+            for (int a = 0; a < 3; a++) centers[(size_t)i * 3 + a] = buf_[(size_t)i].center[a];
+            radii[(size_t)i] = (double)buf_[(size_t)i].radius;
+            if (nearest) (*nearest)[(size_t)i] = buf_[(size_t)i].nearest;
+        }
+        return PC_OK;
+    }
+
+private:
+    SafeRegionCloud &cloud_;
+    NodeSnapshotIndex &nodes_;
+    std::vector<pc_candidate> buf_;
 };
 
 }  // namespace pc

@@ -25,6 +25,11 @@
 //                                 (a candidate's centre was chosen against the snapshot; its radius is exact for that
 //                                 centre, so every sphere of the resulting corridor is still obstacle-free)
 //
+//   + setDeviceBatch(fn)          the snapshot phase of every batch (K x genSample, nearest vertex, steering, radius, the loop's
+//                                 early rejections) in ONE provider call that is handed the engine state instead of samples
+//                                 (pc_expand_batch generates the stream on the device); used while no path is known -- the
+//                                 informed-ellipsoid samples (libm calls) stay on the host.  Same corridor, bit for bit.
+//
 // Deviations from the reference, on purpose: (1) iteration budget instead of ros::Time; (2) the informed-sampling
 // ellipsoid is updated when an end node is found, as SafeRegionRefine does (:796) -- in SafeRegionExpansion that call is
 // commented out (:742) while inform_status is still set, which samples from uninitialised elli_l / elli_s; (3) the node
@@ -46,6 +51,7 @@
 #include <limits>
 #include <memory>
 #include <random>
+#include <sstream>
 #include <vector>
 
 namespace pc {
@@ -238,31 +244,56 @@ public:
         std::vector<int64_t> range_off;
         std::vector<int32_t> range_idx;
         std::vector<RrtNode *> snapshot, batch_nodes, found;
+        std::vector<double> node_coord;
+        std::vector<float> node_radius;
+        std::vector<uint8_t> node_valid;
         int it = 0;
         while (it < max_iterations && it < max_samples) {
             const int k_now = std::min(K, std::min(max_iterations, max_samples) - it);
             int n = 0;
-            for (int j = 0; j < k_now; j++) genSample(&samples[(size_t)j * 3]);
-            if (snapshot_nearest_ || snapshot_range_) {
+            const bool on_device = device_batch_ && !inform_status;      // the informed-ellipsoid samples are drawn here
+            if (centers.size() < (size_t)K * 3) centers.resize((size_t)K * 3);
+            if (radii.size() < (size_t)K) radii.resize((size_t)K);
+            if (!on_device) for (int j = 0; j < k_now; j++) genSample(&samples[(size_t)j * 3]);
+            if (snapshot_nearest_ || snapshot_range_ || on_device) {
                 // the K nearest-vertex queries of a batch go against the SAME frozen node set, so they are one
                 // batched exact-NN call on the node centres (float positions, like kd_nearestf)
                 snapshot = node_list_;
                 node_pos.resize(snapshot.size() * 3);
                 for (size_t i = 0; i < snapshot.size(); i++) for (int a = 0; a < 3; a++) node_pos[3 * i + a] = (float)snapshot[i]->coord[a];
             }
-            if (snapshot_nearest_) {
+            if (on_device) {
+                node_coord.resize(snapshot.size() * 3); node_radius.resize(snapshot.size()); node_valid.resize(snapshot.size());
+                for (size_t i = 0; i < snapshot.size(); i++) {
+                    for (int a = 0; a < 3; a++) node_coord[3 * i + a] = snapshot[i]->coord[a];
+                    node_radius[i] = snapshot[i]->radius; node_valid[i] = snapshot[i]->valid ? 1 : 0;
+                }
+                DeviceBatchRequest req;
+                req.engine_state = engineState(); req.goal_ratio = goal_ratio; req.inlier_ratio = inlier_ratio;
+                const U *g[3] = { &rand_x, &rand_y, &rand_z }, *l[3] = { &rand_x_in, &rand_y_in, &rand_z_in };
+                for (int a = 0; a < 3; a++) {
+                    req.end_pt[a] = end_pt[a];
+                    req.lo[a] = g[a]->a(); req.hi[a] = g[a]->b(); req.in_lo[a] = l[a]->a(); req.in_hi[a] = l[a]->b();
+                }
+                req.z_l = z_l; req.safety_margin = safety_margin; req.k = k_now; req.n_nodes = (int)snapshot.size();
+                req.node_coord = node_coord.data(); req.node_radius = node_radius.data(); req.node_valid = node_valid.data();
+                eng_.seed(device_batch_(req, centers, radii));
+                n = (int)radii.size();
+                cloud_queries += k_now;
+                radius_calls++; device_batches++;
+            } else if (snapshot_nearest_) {
                 for (size_t i = 0; i < (size_t)k_now * 3; i++) sample_pos[i] = (float)samples[i];
                 snapshot_nearest_(node_pos.data(), (int)snapshot.size(), sample_pos.data(), k_now, nearest_idx.data());
                 node_tree_calls++;
             }
-            for (int j = 0; j < k_now; j++) {
+            for (int j = 0; j < k_now && !on_device; j++) {
                 const double *s = &samples[(size_t)j * 3];
                 RrtNode *nearest = snapshot_nearest_ ? (nearest_idx[(size_t)j] >= 0 ? node_list_[(size_t)nearest_idx[(size_t)j]] : nullptr) : findNearestVertex(s);
                 if (!nearest || !nearest->valid) continue;
                 steer(s, nearest, &centers[(size_t)n * 3]);
                 n++;
             }
-            if (n > 0) {
+            if (n > 0 && !on_device) {
                 radius_(centers.data(), n, radii.data());
                 cloud_queries += n;
                 radius_calls++;
@@ -461,6 +492,23 @@ public:
                                                std::vector<int64_t> &offsets, std::vector<int32_t> &idx)>;
     void setSnapshotRange(SnapshotRangeFn fn) { snapshot_range_ = std::move(fn); }
     const NodeKdTree &nodeTree() const { return node_tree_; }
+    // optional: the whole snapshot phase of a batch behind one call.  The provider gets genSample's state (engine state and
+    // distribution bounds: corridor_finder.cpp:333-358 with setPt :52-91) and the frozen node set, draws the next k samples of
+    // that stream itself, and returns the centres / radii of the candidates the loop would keep (nearest vertex valid, centre
+    // z >= z_l, radius >= safety_margin) in sample order, plus the engine state behind the k-th sample.
+    struct DeviceBatchRequest {
+        uint32_t engine_state;
+        double goal_ratio, inlier_ratio, end_pt[3], lo[3], hi[3], in_lo[3], in_hi[3], z_l, safety_margin;
+        int k, n_nodes;
+        const double *node_coord;      // n_nodes x 3
+        const float *node_radius;
+        const uint8_t *node_valid;
+    };
+    using DeviceBatchFn = std::function<uint32_t(const DeviceBatchRequest &req, std::vector<double> &centers, std::vector<double> &radii)>;
+    void setDeviceBatch(DeviceBatchFn fn) { device_batch_ = std::move(fn); }
+    int64_t device_batches = 0;
+    // state of the engine: the next draw is 16807 * state mod 2^31-1 (operator<< of linear_congruential_engine writes it)
+    uint32_t engineState() const { std::ostringstream os; os << eng_; return (uint32_t)std::stoul(os.str()); }
 
     double safety_margin = 0, search_margin = 0, max_radius = 0, sample_range = 0;
 
@@ -757,6 +805,7 @@ private:
     RadiusBatchFn radius_;
     SnapshotNearestFn snapshot_nearest_;
     SnapshotRangeFn snapshot_range_;
+    DeviceBatchFn device_batch_;
     const std::vector<RrtNode *> *found_override_ = nullptr;
     bool defer_remove_ = false;
     std::default_random_engine eng_;

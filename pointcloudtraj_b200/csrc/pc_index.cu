@@ -82,8 +82,11 @@ struct pc_index {
 
     pc_lane lane[PC_PIPE_LANES];
 
-    // generic device scratch for range / clearance
+    // generic device scratch for range / clearance / expansion batches
     void *scratch = nullptr; int64_t scratch_cap = 0;
+    // pc_expand_batch: running candidate totals per chunk (pinned) and the events the host waits on before copying a chunk back
+    unsigned long long *h_totals = nullptr;
+    cudaEvent_t ev_chunk[2] = { nullptr, nullptr };
 
     // tiny PC_HOST batches (the planner's one-query-at-a-time calls): pinned, device-mapped host buffers the kernel reads the
     // queries from and writes the results to directly -- one launch + one stream sync instead of two staged copies
@@ -314,6 +317,8 @@ extern "C" void pc_index_destroy(pc_index *ix)
         if (L.tb) cudaEventDestroy(L.tb);
     }
     if (ix->h_bbox) cudaFreeHost(ix->h_bbox);
+    if (ix->h_totals) cudaFreeHost(ix->h_totals);
+    for (int i = 0; i < 2; i++) if (ix->ev_chunk[i]) cudaEventDestroy(ix->ev_chunk[i]);
     if (ix->tiny_q) cudaFreeHost(ix->tiny_q);
     if (ix->tiny_f) cudaFreeHost(ix->tiny_f);
     if (ix->tiny_i) cudaFreeHost(ix->tiny_i);

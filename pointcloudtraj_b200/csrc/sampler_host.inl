@@ -17,6 +17,9 @@ static int pc_make_sampler_dev(pc_index *ix, const pc_sampler *s, pc_sampler_dev
     return PC_OK;
 }
 
+#define PC_EXPAND_CHUNK ((int64_t)1 << 21)      // samples per pipelined chunk of a large expansion batch
+#define PC_EXPAND_MAX_CHUNKS 512
+
 // device buffers of one sample stream of k samples
 struct pc_sample_bufs { uint32_t *masks; pc_jump *tile_map; uint2 *tile_entry; uint32_t *state; int64_t n_tiles; };
 
@@ -107,12 +110,14 @@ extern "C" int pc_expand_batch(pc_index *cloud, pc_index *nodes, const pc_node_s
     const int64_t b_valid = pc_align_up(n, 256), b_pos = pc_align_up(n * (int64_t)sizeof(float4), 256);
     const int64_t b_xyz = pc_align_up(3 * k * (int64_t)sizeof(double), 256), b_q = pc_align_up(k * (int64_t)sizeof(float4), 256);
     const int64_t b_nn = pc_align_up(k * (int64_t)sizeof(int32_t), 256), b_r = pc_align_up(k * (int64_t)sizeof(float), 256), b_ok = pc_align_up(k, 256);
-    const int64_t n_ctile = (k + PC_CAND_TILE - 1) / PC_CAND_TILE;
+    if ((k + PC_EXPAND_CHUNK - 1) / PC_EXPAND_CHUNK > PC_EXPAND_MAX_CHUNKS) return pc_fail(ix, PC_EINVAL, "pc_expand_batch: batch too large");
+    const int64_t n_ctile = (PC_EXPAND_CHUNK + PC_EXPAND_CHUNK / 2 + PC_CAND_TILE - 1) / PC_CAND_TILE;
     const int64_t b_ctile = pc_align_up(n_ctile * (int64_t)sizeof(uint32_t), 256);
+    const int64_t b_total = pc_align_up((PC_EXPAND_MAX_CHUNKS + 1) * (int64_t)sizeof(unsigned long long), 256);
     const int64_t want_out = cap < k ? cap : k;
     const int64_t b_out = pc_align_up(want_out * (int64_t)sizeof(pc_candidate_dev), 256);
     void *base = nullptr;
-    if ((rc = pc_scratch(ix, b_coord + b_rad + b_valid + b_pos + pc_sample_scratch_bytes(k) + b_xyz + b_q + b_nn + b_r + b_ok + b_ctile + 256 + b_out, &base)) != PC_OK) return rc;
+    if ((rc = pc_scratch(ix, b_coord + b_rad + b_valid + b_pos + pc_sample_scratch_bytes(k) + b_xyz + b_q + b_nn + b_r + b_ok + b_ctile + b_total + b_out, &base)) != PC_OK) return rc;
     char *p = (char *)base;
     double *d_coord = (double *)p; p += b_coord;
     float *d_rad = (float *)p; p += b_rad;
@@ -126,7 +131,7 @@ extern "C" int pc_expand_batch(pc_index *cloud, pc_index *nodes, const pc_node_s
     float *d_r = (float *)p; p += b_r;
     uint8_t *d_ok = (uint8_t *)p; p += b_ok;
     uint32_t *d_ctile = (uint32_t *)p; p += b_ctile;
-    unsigned long long *d_total = (unsigned long long *)p; p += 256;
+    unsigned long long *d_total = (unsigned long long *)p; p += b_total;      // running candidate count behind every chunk
     pc_candidate_dev *d_out = (pc_candidate_dev *)p;
 
     // the frozen node set: a few bytes per node (the planner's tree has 10^3 .. 10^5 nodes), then its index
@@ -136,42 +141,70 @@ extern "C" int pc_expand_batch(pc_index *cloud, pc_index *nodes, const pc_node_s
     pc_node_pos_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(d_coord, n, d_pos);
     ix->launches++;
     if ((rc = pc_sample_launch(ix, S, k, B, d_xyz, d_q, st)) != PC_OK) return rc;
-    // the node index and the nearest-vertex batch run on the nodes handle (its own stream), ordered by events
+    PC_CUDA(ix, cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
+    // the node index and the nearest-vertex batches run on the nodes handle (its own stream), ordered by events
     PC_CUDA(ix, cudaEventRecord(ix->ev_in, st));
     PC_CUDA(ix, cudaStreamWaitEvent(nodes->stream, ix->ev_in, 0));
     if ((rc = pc_index_build(nodes, (const float *)d_pos, n, 4, PC_DEVICE)) != PC_OK) return pc_fail(ix, rc, "pc_expand_batch: node index: %s", nodes->err);
-    {
+
+    // Large batches go through in chunks: while chunk c is searched, the candidates of chunk c - 1 travel to the host on a
+    // side stream, and the nearest-vertex search of chunk c + 1 (nodes handle's stream) overlaps the radius search of chunk c.
+    const int64_t chunk = k > PC_EXPAND_CHUNK + PC_EXPAND_CHUNK / 2 ? PC_EXPAND_CHUNK : k;
+    const int64_t n_chunks = (k + chunk - 1) / chunk;
+    if (!ix->h_totals) {
+        PC_CUDA(ix, cudaHostAlloc((void **)&ix->h_totals, (PC_EXPAND_MAX_CHUNKS + 2) * sizeof(unsigned long long), cudaHostAllocDefault));
+        for (int i = 0; i < 2; i++) PC_CUDA(ix, cudaEventCreateWithFlags(&ix->ev_chunk[i], cudaEventDisableTiming));
+    }
+    cudaStream_t copy_st = ix->lane[1].stream;
+    uint32_t state = 0;
+    unsigned long long copied = 0, total = 0;
+    const bool eager = n_chunks == 1 && want_out * (int64_t)sizeof(pc_candidate_dev) <= ((int64_t)1 << 20);
+    auto drain = [&](int64_t c) -> int {          // chunk c is done on the device: send its candidates home
+        PC_CUDA(ix, cudaEventSynchronize(ix->ev_chunk[c & 1]));
+        total = ix->h_totals[c + 1];
+        const unsigned long long upto = total < (unsigned long long)cap ? total : (unsigned long long)cap;
+        if (upto > copied && !eager)
+            PC_CUDA(ix, cudaMemcpyAsync(out + copied, d_out + copied, (size_t)(upto - copied) * sizeof(pc_candidate_dev), cudaMemcpyDeviceToHost, copy_st));
+        if (upto > copied) copied = upto;
+        return PC_OK;
+    };
+    for (int64_t c = 0; c < n_chunks; c++) {
+        const int64_t off = c * chunk, kc = k - off < chunk ? k - off : chunk;
         pc_qargs NA;
         memset(&NA, 0, sizeof NA);
         NA.kind = PC_Q_NEAREST; NA.flags = PC_QUERY_AUTO;
-        if ((rc = pc_run_batch(nodes, nodes->lane[0], NA, (const float *)d_q, k, 4, d_nn, nullptr)) != PC_OK) return pc_fail(ix, rc, "pc_expand_batch: nearest vertex: %s", nodes->err);
+        if ((rc = pc_run_batch(nodes, nodes->lane[0], NA, (const float *)(d_q + off), kc, 4, d_nn + off, nullptr)) != PC_OK)
+            return pc_fail(ix, rc, "pc_expand_batch: nearest vertex: %s", nodes->err);
+        PC_CUDA(ix, cudaEventRecord(nodes->ev_in, nodes->stream));
+        PC_CUDA(ix, cudaStreamWaitEvent(st, nodes->ev_in, 0));
+        pc_steer_kernel<<<(int)((kc + 255) / 256), 256, 0, st>>>(d_xyz + 3 * off, d_q + off, d_nn + off, kc, d_coord, d_rad, d_valid, d_ok + off);
+        ix->launches++;
+        PC_CHECK_LAUNCH(ix);
+        // the steering overwrote this chunk's samples with the centres: the nodes stream must not run ahead into them -- it does
+        // not, its next chunk reads other entries of d_q.  radiusSearch for every centre (a sample without a valid nearest
+        // vertex keeps its own position: answered and dropped)
+        if ((rc = pc_run_batch(ix, ix->lane[0], RA, (const float *)(d_q + off), kc, 4, nullptr, d_r + off)) != PC_OK) return rc;
+        const int64_t n_ct = (kc + PC_CAND_TILE - 1) / PC_CAND_TILE;
+        pc_cand_count_kernel<<<(int)n_ct, PC_CAND_THREADS, 0, st>>>(d_xyz + 3 * off, d_r + off, d_ok + off, kc, z_l, safety_margin, d_ctile);
+        pc_cand_scan_kernel<<<1, 1024, 0, st>>>(d_ctile, n_ct, d_total + c, d_total + c + 1);
+        pc_cand_write_kernel<<<(int)n_ct, PC_CAND_THREADS, 0, st>>>(d_xyz + 3 * off, d_r + off, d_ok + off, d_nn + off, kc, z_l, safety_margin, d_ctile, d_out, (uint64_t)want_out);
+        ix->launches += 3;
+        PC_CHECK_LAUNCH(ix);
+        PC_CUDA(ix, cudaMemcpyAsync(ix->h_totals + c + 1, d_total + c + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        if (c == n_chunks - 1) {
+            PC_CUDA(ix, cudaMemcpyAsync(ix->h_totals + PC_EXPAND_MAX_CHUNKS + 1, B.state, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            // a planner-sized batch comes back with its count in one round trip
+            if (eager && want_out > 0) PC_CUDA(ix, cudaMemcpyAsync(out, d_out, (size_t)want_out * sizeof(pc_candidate_dev), cudaMemcpyDeviceToHost, st));
+        }
+        PC_CUDA(ix, cudaEventRecord(ix->ev_chunk[c & 1], st));
+        if (c > 0 && (rc = drain(c - 1)) != PC_OK) return rc;
     }
-    PC_CUDA(ix, cudaEventRecord(nodes->ev_in, nodes->stream));
-    PC_CUDA(ix, cudaStreamWaitEvent(st, nodes->ev_in, 0));
-    pc_steer_kernel<<<(int)((k + 255) / 256), 256, 0, st>>>(d_xyz, d_q, d_nn, k, d_coord, d_rad, d_valid, d_ok);
-    ix->launches++;
-    PC_CHECK_LAUNCH(ix);
-    // radiusSearch for every centre (samples without a valid nearest vertex keep their own position: answered and dropped)
-    if ((rc = pc_run_batch(ix, ix->lane[0], RA, (const float *)d_q, k, 4, nullptr, d_r)) != PC_OK) return rc;
-    pc_cand_count_kernel<<<(int)n_ctile, PC_CAND_THREADS, 0, st>>>(d_xyz, d_r, d_ok, k, z_l, safety_margin, d_ctile);
-    pc_cand_scan_kernel<<<1, 1024, 0, st>>>(d_ctile, n_ctile, d_total);
-    pc_cand_write_kernel<<<(int)n_ctile, PC_CAND_THREADS, 0, st>>>(d_xyz, d_r, d_ok, d_nn, k, z_l, safety_margin, d_ctile, d_out, (uint64_t)want_out);
-    ix->launches += 3;
-    PC_CHECK_LAUNCH(ix);
-    unsigned long long total = 0;
-    uint32_t state = 0;
-    PC_CUDA(ix, cudaMemcpyAsync(&total, d_total, sizeof total, cudaMemcpyDeviceToHost, st));
-    PC_CUDA(ix, cudaMemcpyAsync(&state, B.state, sizeof state, cudaMemcpyDeviceToHost, st));
-    // a planner-sized batch comes back with the count in one round trip; a large one first learns how much to copy
-    const bool eager = want_out * (int64_t)sizeof(pc_candidate_dev) <= ((int64_t)1 << 20);
-    if (eager && want_out > 0) PC_CUDA(ix, cudaMemcpyAsync(out, d_out, (size_t)want_out * sizeof(pc_candidate_dev), cudaMemcpyDeviceToHost, st));
+    if ((rc = drain(n_chunks - 1)) != PC_OK) return rc;
     PC_CUDA(ix, cudaStreamSynchronize(st));
+    if (!eager) PC_CUDA(ix, cudaStreamSynchronize(copy_st));
+    state = *(const uint32_t *)(ix->h_totals + PC_EXPAND_MAX_CHUNKS + 1);
     *out_count = (int64_t)total;
     if (out_engine_state) *out_engine_state = state;
     if ((int64_t)total > cap) return pc_fail(ix, PC_ECAP, "pc_expand_batch: %lld candidates exceed cap %lld", (long long)total, (long long)cap);
-    if (!eager && total > 0) {
-        PC_CUDA(ix, cudaMemcpyAsync(out, d_out, (size_t)total * sizeof(pc_candidate_dev), cudaMemcpyDeviceToHost, st));
-        PC_CUDA(ix, cudaStreamSynchronize(st));
-    }
     return PC_OK;
 }

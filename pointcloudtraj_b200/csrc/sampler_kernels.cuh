@@ -288,9 +288,10 @@ pc_cand_count_kernel(const double *__restrict__ xyz, const float *__restrict__ r
     if (threadIdx.x == 0) tile_count[blockIdx.x] = s_sum;
 }
 
-// one CTA: exclusive scan of the tile counts in place; total[0] = number of candidates
+// one CTA: exclusive scan of the tile counts in place, on top of *base (the candidates of the chunks in front of this one);
+// *total = *base + the candidates of this chunk
 __global__ void __launch_bounds__(1024)
-pc_cand_scan_kernel(uint32_t *__restrict__ tile_count, int64_t n_tiles, unsigned long long *__restrict__ total)
+pc_cand_scan_kernel(uint32_t *__restrict__ tile_count, int64_t n_tiles, const unsigned long long *__restrict__ base, unsigned long long *__restrict__ total)
 {
     __shared__ unsigned long long s_warp[32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -310,7 +311,7 @@ pc_cand_scan_kernel(uint32_t *__restrict__ tile_count, int64_t n_tiles, unsigned
         s_warp[lane] = t;
     }
     __syncthreads();
-    unsigned long long run = v - mine + (w > 0 ? s_warp[w - 1] : 0ull);
+    unsigned long long run = *base + v - mine + (w > 0 ? s_warp[w - 1] : 0ull);
     for (int64_t t = t0; t < t1; t++) { const uint32_t c = tile_count[t]; tile_count[t] = (uint32_t)run; run += c; }
     if (threadIdx.x == blockDim.x - 1) *total = run;
 }

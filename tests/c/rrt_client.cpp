@@ -6,8 +6,10 @@
 //   D  as C + the batch's nearest-vertex queries on the GPU (pc::NodeSnapshotIndex), checked against the CPU node tree
 //   E  as C + the 2 x radius neighbourhoods of treeRewire (kd_nearest_rangef, corridor_finder.cpp:462-464) answered for the
 //      whole batch by ONE pc_range_batch on the snapshot index: must reproduce C bit for bit
+//   F  as D, but while no path is known the whole snapshot phase of a batch (samples, nearest vertex, steering, radius, the
+//      loop's early rejections) is ONE pc_expand_batch call that generates the sample stream on the device: must reproduce D
 // A and B must produce bit-identical corridors (replay mode); C is validated by the pytest against the oracle.
-// usage: rrt_client <in.bin> <out.bin>      file formats: rrt_io.hpp; output = the records of A, then B, then C, then D, then E
+// usage: rrt_client <in.bin> <out.bin>      file formats: rrt_io.hpp; output = the records of A, then B, then C, then D, then E, then F
 #include <cstdlib>
 #include "pc_corridor.hpp"
 #include "rrt_io.hpp"
@@ -110,6 +112,32 @@ int main(int argc, char **argv)
         for (size_t i = 0; i < k; i++)
             if (ex.path_x[i + 1] != E.path[3 * i] || ex.path_y[i + 1] != E.path[3 * i + 1] || ex.path_z[i + 1] != E.path[3 * i + 2] || ex.radii[i + 1] != E.radius[i]) return 12;
         if (k && (ex.path_x[0] != E.path[0] || ex.path_y[0] != E.path[1] || ex.path_z[0] != E.path[2] || ex.radii[0] != E.radius[0])) return 12;
+    }
+    // F: the device-generated batch path
+    {
+        pc::SafeRegionRrtStarDriver F([&](const double *c, int m, double *out) {
+            qf.resize((size_t)m * 3); rf.resize((size_t)m);
+            for (size_t i = 0; i < qf.size(); i++) qf[i] = (float)c[i];
+            if (cloud.radiusSearch(qf.data(), m, 3, rf.data()) != PC_OK) exit(8);
+            for (int i = 0; i < m; i++) out[i] = rf[(size_t)i];
+        });
+        pc::NodeSnapshotIndex nodes_f(0, 1 << 16), nodes_dev(0, 1 << 16);
+        F.setSnapshotNearest([&](const float *node_pos, int n_nodes, const float *samples, int k, int32_t *out_nearest) {
+            if (nodes_f.nearest(node_pos, n_nodes, samples, k, out_nearest, nullptr) != PC_OK) exit(9);
+        });
+        pc::DeviceExpansion dev(cloud, nodes_dev);
+        F.setDeviceBatch([&](const pc::SafeRegionRrtStarDriver::DeviceBatchRequest &rq, std::vector<double> &centers, std::vector<double> &radii) {
+            pc_sampler sm;
+            sm.engine_state = rq.engine_state; sm.reserved = 0; sm.goal_ratio = rq.goal_ratio; sm.inlier_ratio = rq.inlier_ratio;
+            for (int a = 0; a < 3; a++) { sm.end_pt[a] = rq.end_pt[a]; sm.lo[a] = rq.lo[a]; sm.hi[a] = rq.hi[a]; sm.in_lo[a] = rq.in_lo[a]; sm.in_hi[a] = rq.in_hi[a]; }
+            pc_node_set set{ rq.n_nodes, rq.node_coord, rq.node_radius, rq.node_valid };
+            uint32_t after = 0;
+            if (dev.run(sm, set, rq.z_l, rq.k, centers, radii, &after) != PC_OK) { fprintf(stderr, "device batch: %s\n", cloud.lastError()); exit(13); }
+            return after;
+        });
+        rrt_run(o, F, in, true, gpu_cloud);
+        if (F.device_batches == 0) return 14;
+        fprintf(stderr, "F: %lld device batches\n", (long long)F.device_batches);
     }
     fclose(o);
     kdo_free(kt[0]); kdo_free(kt[1]);
