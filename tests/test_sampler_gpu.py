@@ -96,3 +96,56 @@ def test_expand_batch_vs_buffer_api(ix, n_nodes, k):
         with pytest.raises(PcError) as e:
             ix.expand_batch(nodes, node_coord, node_radius, node_valid, ps, P, BOX[4], PRM["safety_margin"], k, cap=3, advance=False)
         assert e.value.code == -4
+
+
+def test_expand_batch_edge_cases(ix):
+    P = PcRadiusParams.make(PRM["search_margin"], PRM["max_radius"], PRM["sample_range"], START)
+    node_coord = np.array([START, (3.0, 1.0, 2.0)], np.float64)
+    node_radius = np.array([1.0, 0.8], np.float32)
+    with PointCloudIndex(max_points=1 << 12, device=0) as nodes:
+        # empty cloud: radiusSearch answers max_radius - search_margin everywhere (corridor_finder.cpp:118-120), nothing is dropped
+        # for its radius; candidates below the floor still are
+        ix.build(np.zeros((0, 3), np.float32))
+        ps, os_ = _samplers(0.3, 0.15)
+        cand = ix.expand_batch(nodes, node_coord, node_radius, np.ones(2, np.uint8), ps, P, BOX[4], PRM["safety_margin"], 3000)
+        s = oracle.gen_samples(os_, 3000)
+        d0 = ((s.astype(np.float32).astype(np.float64) - node_coord[0].astype(np.float32)) ** 2).sum(1)
+        d1 = ((s.astype(np.float32).astype(np.float64) - node_coord[1].astype(np.float32)) ** 2).sum(1)
+        nn = (d1 < d0).astype(np.int32)
+        c = oracle.steer(s, node_coord, node_radius, nn)
+        keep = ~(c[:, 2] < BOX[4])
+        assert len(cand) == int(keep.sum()) and (cand["center"] == c[keep]).all() and (cand["nearest"] == nn[keep]).all()
+        assert (cand["radius"] == np.float32(PRM["max_radius"] - PRM["search_margin"])).all()
+        # no valid vertex: every sample is dropped, the engine still advances past the k samples
+        ps2, os2 = _samplers(0.3, 0.15, state=99)
+        cand = ix.expand_batch(nodes, node_coord, node_radius, np.zeros(2, np.uint8), ps2, P, BOX[4], PRM["safety_margin"], 1000)
+        oracle.gen_samples(os2, 1000)
+        assert len(cand) == 0 and ps2.engine_state == os2.engine_state
+        # every sample is the goal (goal_ratio 1): k identical candidates steered from the same vertex
+        ps3, _ = _samplers(0.0, 1.0)
+        cand = ix.expand_batch(nodes, node_coord, node_radius, np.ones(2, np.uint8), ps3, P, BOX[4], PRM["safety_margin"], 500)
+        assert len(cand) == 500 and (cand["center"] == cand["center"][0]).all()
+        # k = 0, and bad arguments
+        ps4, _ = _samplers(0.3, 0.15)
+        assert len(ix.expand_batch(nodes, node_coord, node_radius, np.ones(2, np.uint8), ps4, P, BOX[4], PRM["safety_margin"], 0)) == 0 and ps4.engine_state == 1
+        with pytest.raises(PcError):
+            ix.expand_batch(ix, node_coord, node_radius, np.ones(2, np.uint8), ps4, P, BOX[4], PRM["safety_margin"], 10)      # nodes == cloud
+        with pytest.raises(PcError):
+            ix.expand_batch(nodes, node_coord[:0], node_radius[:0], np.ones(0, np.uint8), ps4, P, BOX[4], PRM["safety_margin"], 10)   # empty node set
+
+
+def test_sample_batch_device_buffer(ix):
+    """PC_DEVICE: the samples stay in device memory (a torch tensor), the engine state still comes back to the host."""
+    import ctypes as C
+    import torch
+    from pointcloudtraj_b200 import PC_DEVICE
+    ps, os_ = _samplers(0.3, 0.15, state=777)
+    k = 123_457
+    out = torch.empty((k, 3), dtype=torch.float64, device="cuda:0")
+    torch.cuda.synchronize()
+    st = C.c_uint32(0)
+    rc = ix._L.pc_sample_batch(ix._h, C.byref(ps), k, PC_DEVICE, C.c_void_p(out.data_ptr()), C.byref(st))
+    assert rc == 0
+    ix.sync()
+    want = oracle.gen_samples(os_, k)
+    assert (out.cpu().numpy() == want).all() and st.value == os_.engine_state
