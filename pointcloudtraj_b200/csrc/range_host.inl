@@ -37,8 +37,14 @@ extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64
     const int64_t b_cnt = pc_align_up((m + 1) * (int64_t)sizeof(int64_t), 256);
     const int64_t b_tile = pc_align_up((n_tiles + 1) * (int64_t)sizeof(int64_t), 256);
     const int64_t b_long = pc_align_up((m + 1) * (int64_t)sizeof(int64_t), 256);      // queue of lists too long for the in-warp sort
+    // the counting pass of a call that wants the lists parks the short ones (<= PC_RCAP_HITS hits) in a staging buffer
+    const bool capture = out_idx && cap > 0 && m > 0;
+    const int64_t stage_cap = capture ? (cap < m * PC_RCAP_HITS ? cap : m * PC_RCAP_HITS) : 0;
+    const int64_t b_stage = capture ? pc_align_up(stage_cap * (int64_t)sizeof(int32_t), 256) : 0;
+    const int64_t b_pos = capture ? pc_align_up(m * (int64_t)sizeof(int64_t), 256) : 0;
+    const int64_t b_todo = capture ? pc_align_up((m + 1) * (int64_t)sizeof(int64_t), 256) : 0;
     void *base = nullptr;
-    if ((rc = pc_scratch(ix, b_q + b_r + b_off + b_cnt + b_tile + b_long, &base)) != PC_OK) return rc;
+    if ((rc = pc_scratch(ix, b_q + b_r + b_off + b_cnt + b_tile + b_long + b_stage + b_pos + b_todo + 256, &base)) != PC_OK) return rc;
     char *p = (char *)base;
     const float *d_q = q_xyz; const double *d_r = range; int64_t *d_off = out_offsets;
     if (space == PC_HOST) {
@@ -53,7 +59,15 @@ extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64
     int64_t *d_cnt = (int64_t *)p; p += b_cnt;
     int64_t *d_tile = (int64_t *)p; p += b_tile;
     unsigned long long *d_long_count = (unsigned long long *)p;
-    int64_t *d_long_list = (int64_t *)p + 1;
+    int64_t *d_long_list = (int64_t *)p + 1; p += b_long;
+    pc_range_stage S;
+    S.stage = (int32_t *)p; p += b_stage;
+    S.stage_cap = (unsigned long long)stage_cap;
+    S.pos = (int64_t *)p; p += b_pos;
+    unsigned long long *d_todo_count = (unsigned long long *)p;
+    int64_t *d_todo_list = (int64_t *)p + 1; p += b_todo;
+    S.cursor = (unsigned long long *)p;
+    const pc_range_stage no_stage = { nullptr, 0ull, nullptr, nullptr };
 
     int64_t total = 0;
     if (m == 0) {
@@ -63,7 +77,12 @@ extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64
     }
     pc_tree T = pc_tree_of(ix);
     const int cgrid = (int)((m + PC_RCOOP_WARPS - 1) / PC_RCOOP_WARPS);      // one warp per query
-    pc_range_coop_kernel<false><<<cgrid, 32 * PC_RCOOP_WARPS, 0, st>>>(T, d_q, m, qs, d_r, range_is_scalar ? 1 : 0, d_cnt, nullptr, nullptr, nullptr, nullptr);
+    if (capture) {
+        PC_CUDA(ix, cudaMemsetAsync(S.cursor, 0, sizeof(unsigned long long), st));
+        pc_range_coop_kernel<PC_RANGE_CAPTURE><<<cgrid, 32 * PC_RCOOP_WARPS, 0, st>>>(T, d_q, m, qs, d_r, range_is_scalar ? 1 : 0, d_cnt, nullptr, nullptr, nullptr, nullptr, S, nullptr, nullptr);
+    } else {
+        pc_range_coop_kernel<PC_RANGE_COUNT><<<cgrid, 32 * PC_RCOOP_WARPS, 0, st>>>(T, d_q, m, qs, d_r, range_is_scalar ? 1 : 0, d_cnt, nullptr, nullptr, nullptr, nullptr, no_stage, nullptr, nullptr);
+    }
     pc_scan_tile_sums<<<(int)n_tiles, PC_SCAN_THREADS, 0, st>>>(d_cnt, m, d_tile);
     pc_scan_tile_offsets<<<1, PC_SCAN_THREADS, 0, st>>>(d_tile, n_tiles);
     pc_scan_write_offsets<<<(int)n_tiles, PC_SCAN_THREADS, 0, st>>>(d_cnt, m, d_tile, d_off);
@@ -86,9 +105,19 @@ extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64
         d_out = L.d_i32;
     }
     PC_CUDA(ix, cudaMemsetAsync(d_long_count, 0, sizeof(unsigned long long), st));
-    pc_range_coop_kernel<true><<<cgrid, 32 * PC_RCOOP_WARPS, 0, st>>>(T, d_q, m, qs, d_r, range_is_scalar ? 1 : 0, nullptr, d_off, d_out, d_long_count, d_long_list);
+    PC_CUDA(ix, cudaMemsetAsync(d_todo_count, 0, sizeof(unsigned long long), st));
+    pc_range_place_kernel<<<(int)((m + PC_RPLACE_WARPS - 1) / PC_RPLACE_WARPS), 32 * PC_RPLACE_WARPS, 0, st>>>(m, d_off, S.stage, S.pos, d_out, d_todo_count, d_todo_list);
     ix->launches++;
     PC_CHECK_LAUNCH(ix);
+    // the lists that were too long to park (each > PC_RCAP_HITS hits, so at most total / (PC_RCAP_HITS + 1) of them): second walk
+    const int64_t max_todo = total / (PC_RCAP_HITS + 1) < m ? total / (PC_RCAP_HITS + 1) : m;
+    if (max_todo > 0) {
+        const int tgrid = (int)((max_todo + PC_RCOOP_WARPS - 1) / PC_RCOOP_WARPS);
+        pc_range_coop_kernel<PC_RANGE_FILL><<<tgrid, 32 * PC_RCOOP_WARPS, 0, st>>>(T, d_q, m, qs, d_r, range_is_scalar ? 1 : 0, nullptr, d_off, d_out, d_long_count, d_long_list,
+                                                                                  no_stage, d_todo_list, d_todo_count);
+        ix->launches++;
+        PC_CHECK_LAUNCH(ix);
+    }
     if (total > PC_RCOOP_CAP) {          // only then can a list be longer than the in-warp sort takes
         static bool attr_set[64] = { false };
         if (ix->device >= 64 || !attr_set[ix->device]) {

@@ -4,8 +4,11 @@
 // iteration (kdtree.c:613-650).  The hit test is the reference's inclusive `dist_sq <= SQ(range)` (kdtree.c:273)
 // evaluated in fp64 in its operation order; unlike the reference the far side of a split is never skipped, so a
 // point at exactly `range` is always reported (the reference misses it from one side, kdtree.c:283 -- SURVEY 8c-5).
-// Two passes over the same traversal: count, (scan on the device), fill; every list is then sorted by original
-// index so the output is canonical.  One WARP per query in both passes.
+// One WARP per query.  The walk runs ONCE for almost every query: the counting pass also captures the hits of lists up to
+// PC_RCAP_HITS entries in shared memory, sorts them by original index there and parks them in a staging buffer (one
+// atomicAdd per query for the place); after the scan of the counts a copy kernel moves every parked list to its CSR
+// position.  Only lists longer than that are walked a second time (fill pass, given their offsets).  A call that asks for
+// the offsets only runs the plain counting pass.
 #pragma once
 #include "query_kernels.cuh"
 
@@ -42,24 +45,59 @@ __device__ __forceinline__ void pc_sort_list(int32_t *__restrict__ a, int64_t n)
 // Same frontier walk as pc_query_coop_kernel (query_kernels.cuh), without a bound to tighten: the open inner nodes sit on a
 // LIFO frontier in shared memory, every step each lane takes one of them and tests its two child boxes; a child that is a
 // leaf is scanned on the spot (only its own `count` points: its neighbours' points belong to other leaves) and the hits are
-// appended at ballot-computed positions, inner children are pushed.  The count pass and the fill pass are the same walk; the
-// fill pass then sorts its list by original index with a bitonic network in the same shared memory (lists up to 1024 hits);
+// appended at ballot-computed positions, inner children are pushed.  The count / capture pass and the fill pass are the same
+// walk; the fill pass then sorts its list by original index with a bitonic network in the same shared memory (lists up to 1024 hits);
 // longer lists are queued and sorted afterwards by pc_range_sort_long_kernel, one CTA per list (up to 32768 hits in shared
 // memory; beyond that a single-thread heap sort -- a query that returns more than that is a job for pc_sphere_gather).
 #define PC_RCOOP_CAP 1024
 #define PC_RCOOP_WARPS 4
+#define PC_RCAP_HITS 256         // lists up to this length are captured by the counting pass
+#define PC_RANGE_COUNT 0
+#define PC_RANGE_FILL 1
+#define PC_RANGE_CAPTURE 2
 
-template <bool FILL>
+// bitonic sort of N (power of two >= 32) words in a warp's shared memory
+__device__ __forceinline__ void pc_warp_bitonic(uint32_t *F, int N, int lane)
+{
+    for (int k2 = 2; k2 <= N; k2 <<= 1) {
+        for (int j = k2 >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (N >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+                const uint32_t a = F[i], b = F[l];
+                if ((a > b) == ((i & k2) == 0)) { F[i] = b; F[l] = a; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+struct pc_range_stage {                // PC_RANGE_CAPTURE: where the counting pass parks the short lists
+    int32_t *stage;                    // stage_cap entries
+    unsigned long long stage_cap;
+    unsigned long long *cursor;        // next free entry
+    int64_t *pos;                      // per query: start of its parked list, -1 = not parked (walk it again)
+};
+
+template <int MODE>
 __global__ void __launch_bounds__(32 * PC_RCOOP_WARPS)
 pc_range_coop_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstride,
                      const double *__restrict__ range, int range_is_scalar,
                      int64_t *__restrict__ counts, const int64_t *__restrict__ offsets, int32_t *__restrict__ out_idx,
-                     unsigned long long *__restrict__ long_count, int64_t *__restrict__ long_list)
+                     unsigned long long *__restrict__ long_count, int64_t *__restrict__ long_list,
+                     pc_range_stage S, const int64_t *__restrict__ qlist, const unsigned long long *__restrict__ qlist_count)
 {
+    constexpr bool FILL = MODE == PC_RANGE_FILL;
+    constexpr bool CAPTURE = MODE == PC_RANGE_CAPTURE;
     __shared__ uint32_t s_front[PC_RCOOP_WARPS][PC_RCOOP_CAP];
+    __shared__ uint32_t s_hits[CAPTURE ? PC_RCOOP_WARPS : 1][CAPTURE ? PC_RCAP_HITS : 1];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t k = (int64_t)blockIdx.x * PC_RCOOP_WARPS + w;
+    int64_t k = (int64_t)blockIdx.x * PC_RCOOP_WARPS + w;
+    if (qlist) {                       // fill pass over the queries the capture left behind
+        if ((unsigned long long)k >= *qlist_count) return;
+        k = qlist[k];
+    }
     if (k >= m) return;
+    uint32_t *H = s_hits[CAPTURE ? w : 0];
     int64_t begin = 0, want = 0;
     if (FILL) {
         begin = offsets[k]; want = offsets[k + 1] - begin;
@@ -105,6 +143,7 @@ pc_range_coop_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstr
             for (int i = 0; i < PC_LEAF; i++) {
                 const uint32_t mask = __ballot_sync(PC_FULL_MASK, hit[i]);
                 if (FILL && hit[i]) out_idx[begin + total + __popc(mask & lt)] = id[i];
+                if (CAPTURE && hit[i]) { const int64_t at = total + __popc(mask & lt); if (at < PC_RCAP_HITS) H[at] = (uint32_t)id[i]; }
                 total += __popc(mask);
             }
         }
@@ -156,6 +195,7 @@ pc_range_coop_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstr
             for (int i = 0; i < 2 * PC_LEAF; i++) {
                 const uint32_t mask = __ballot_sync(PC_FULL_MASK, hit[i]);
                 if (FILL && hit[i]) out_idx[begin + total + __popc(mask & lt)] = id[i];
+                if (CAPTURE && hit[i]) { const int64_t at = total + __popc(mask & lt); if (at < PC_RCAP_HITS) H[at] = (uint32_t)id[i]; }
                 total += __popc(mask);
             }
         }
@@ -168,6 +208,25 @@ pc_range_coop_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstr
     }
     if (!FILL) {
         if (lane == 0) counts[k] = total;
+        if (CAPTURE) {
+            // a short list: canonical order (ascending original index) here, then parked until its CSR position is known
+            long long start = -1;
+            if (total > 0 && total <= PC_RCAP_HITS) {
+                int N = 32;
+                while (N < total) N <<= 1;
+                __syncwarp();
+                for (int i = (int)total + lane; i < N; i += 32) H[i] = 0x7fffffffu;
+                __syncwarp();
+                pc_warp_bitonic(H, N, lane);
+                if (lane == 0) {
+                    const unsigned long long at = atomicAdd(S.cursor, (unsigned long long)total);
+                    start = at + (unsigned long long)total <= S.stage_cap ? (long long)at : -1;
+                }
+                start = __shfl_sync(PC_FULL_MASK, start, 0);
+                if (start >= 0) for (int i = lane; i < total; i += 32) S.stage[start + i] = (int32_t)H[i];
+            }
+            if (lane == 0) S.pos[k] = start;
+        }
         return;
     }
     // canonical order: ascending original index
@@ -177,20 +236,31 @@ pc_range_coop_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstr
         __syncwarp();
         for (int i = lane; i < N; i += 32) F[i] = i < want ? (uint32_t)out_idx[begin + i] : 0x7fffffffu;
         __syncwarp();
-        for (int k2 = 2; k2 <= N; k2 <<= 1) {
-            for (int j = k2 >> 1; j > 0; j >>= 1) {
-                for (int t = lane; t < (N >> 1); t += 32) {
-                    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
-                    const uint32_t a = F[i], b = F[l];
-                    if ((a > b) == ((i & k2) == 0)) { F[i] = b; F[l] = a; }
-                }
-                __syncwarp();
-            }
-        }
+        pc_warp_bitonic(F, N, lane);
         for (int i = lane; i < want; i += 32) out_idx[begin + i] = (int32_t)F[i];
     } else if (lane == 0) {
         long_list[atomicAdd(long_count, 1ull)] = k;            // sorted by pc_range_sort_long_kernel
     }
+}
+
+// after the scan: every parked list moves to its CSR position (one warp per query, coalesced); the queries whose lists were
+// too long to park are queued for the fill pass
+#define PC_RPLACE_WARPS 8
+__global__ void __launch_bounds__(32 * PC_RPLACE_WARPS)
+pc_range_place_kernel(int64_t m, const int64_t *__restrict__ offsets, const int32_t *__restrict__ stage, const int64_t *__restrict__ pos,
+                      int32_t *__restrict__ out_idx, unsigned long long *__restrict__ todo_count, int64_t *__restrict__ todo_list)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t k = (int64_t)blockIdx.x * PC_RPLACE_WARPS + (threadIdx.x >> 5);
+    if (k >= m) return;
+    const int64_t begin = offsets[k], n = offsets[k + 1] - begin;
+    if (n == 0) return;
+    const int64_t p = pos[k];
+    if (p < 0) {
+        if (lane == 0) todo_list[atomicAdd(todo_count, 1ull)] = k;
+        return;
+    }
+    for (int64_t i = lane; i < n; i += 32) out_idx[begin + i] = stage[p + i];
 }
 
 // lists the fill pass could not sort inside a warp's shared memory: one CTA per queued list, bitonic network over up to
