@@ -118,13 +118,13 @@ extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64
         ix->launches++;
         PC_CHECK_LAUNCH(ix);
     }
-    if (total > PC_RCOOP_CAP) {          // only then can a list be longer than the in-warp sort takes
+    if (max_todo > 0) {                  // only the lists of the fill pass can be longer than what a warp sorts
         static bool attr_set[64] = { false };
         if (ix->device >= 64 || !attr_set[ix->device]) {
             PC_CUDA(ix, cudaFuncSetAttribute(pc_range_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_RLONG_CAP * (int)sizeof(uint32_t)));
             if (ix->device < 64) attr_set[ix->device] = true;
         }
-        const int64_t max_long = total / PC_RCOOP_CAP < m ? total / PC_RCOOP_CAP : m;
+        const int64_t max_long = max_todo;
         const int lgrid = (int)(max_long < (int64_t)ix->sm_count ? (max_long > 0 ? max_long : 1) : (int64_t)ix->sm_count);
         pc_range_sort_long_kernel<<<lgrid, PC_RLONG_THREADS, PC_RLONG_CAP * sizeof(uint32_t), st>>>(d_long_count, d_long_list, d_off, d_out);
         ix->launches++;

@@ -51,7 +51,13 @@ __device__ __forceinline__ void pc_sort_list(int32_t *__restrict__ a, int64_t n)
 // memory; beyond that a single-thread heap sort -- a query that returns more than that is a job for pc_sphere_gather).
 #define PC_RCOOP_CAP 1024
 #define PC_RCOOP_WARPS 4
-#define PC_RCAP_HITS 256         // lists up to this length are captured by the counting pass
+#define PC_RCAP_HITS 512         // lists up to this length are captured by the counting pass (C1: 99.9 % of them)
+#ifndef PC_RCAP_MIN_CTAS
+#define PC_RCAP_MIN_CTAS 8       // resident CTAs per SM the capturing pass is compiled for (64 registers).  C1 range batch: 7 CTAs
+                                 // (66 registers, no spill) 0.93 ms, 8: 0.80, 9: 0.93, 10 (48 registers): 1.01, 12: 1.13
+#endif
+#define PC_RFILL_WARP_SORT 256   // fill pass: longer lists are sorted by a whole CTA each (pc_range_sort_long_kernel) -- a 1024-entry
+                                 // bitonic network run by ONE warp was a 100 us tail for a handful of lists
 #define PC_RANGE_COUNT 0
 #define PC_RANGE_FILL 1
 #define PC_RANGE_CAPTURE 2
@@ -71,6 +77,51 @@ __device__ __forceinline__ void pc_warp_bitonic(uint32_t *F, int N, int lane)
     }
 }
 
+// LSD radix sort of n <= 512 distinct ids (< 2^bits) by one warp in its shared memory: A holds the keys, B is a second buffer
+// of the same size, hist 256 words.  Digits of <= 8 bits, counted with shared-memory atomics, scanned (8 bins per lane),
+// scattered stably 32 keys at a time (__match_any_sync ranks the keys of equal digit).  Returns the buffer with the result.
+// For the list lengths range queries produce (tens to a few hundred) this takes a third of the instructions of the
+// bitonic network.
+__device__ __forceinline__ uint32_t *pc_warp_radix_sort(uint32_t *A, uint32_t *B, uint32_t *hist, int n, int bits, int lane)
+{
+    const int passes = (bits + 7) / 8, db = (bits + passes - 1) / passes, bins = 1 << db;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int p = 0; p < passes; p++) {
+        const int shift = p * db;
+        for (int i = lane; i < bins; i += 32) hist[i] = 0u;
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) atomicAdd(&hist[(A[i] >> shift) & (bins - 1)], 1u);
+        __syncwarp();
+        {   // exclusive scan of the bins: bins / 32 consecutive ones per lane
+            const int per = bins >> 5 ? bins >> 5 : 1, b0 = lane * per;
+            uint32_t sum = 0u;
+            if (b0 < bins) for (int t = 0; t < per; t++) sum += hist[b0 + t];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(PC_FULL_MASK, incl, d); if (lane >= d) incl += v; }
+            uint32_t run = incl - sum;
+            if (b0 < bins) for (int t = 0; t < per; t++) { const uint32_t c = hist[b0 + t]; hist[b0 + t] = run; run += c; }
+        }
+        __syncwarp();
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const bool valid = i < n;
+            const uint32_t key = valid ? A[i] : 0u;
+            const uint32_t d = valid ? (key >> shift) & (uint32_t)(bins - 1) : 0x10000u | (uint32_t)lane;      // idle lanes match nobody
+            const uint32_t peers = __match_any_sync(PC_FULL_MASK, d);
+            const uint32_t rank = __popc(peers & lt);
+            uint32_t pos = 0u;
+            if (valid) pos = hist[d] + rank;
+            __syncwarp();
+            if (valid && rank == 0u) hist[d] += __popc(peers);
+            if (valid) B[pos] = key;
+            __syncwarp();
+        }
+        uint32_t *t = A; A = B; B = t;
+    }
+    return A;
+}
+
 struct pc_range_stage {                // PC_RANGE_CAPTURE: where the counting pass parks the short lists
     int32_t *stage;                    // stage_cap entries
     unsigned long long stage_cap;
@@ -78,8 +129,9 @@ struct pc_range_stage {                // PC_RANGE_CAPTURE: where the counting p
     int64_t *pos;                      // per query: start of its parked list, -1 = not parked (walk it again)
 };
 
+#define PC_RCAP_FRONT 768         // frontier entries of the capturing pass: 512 double as the sort's second buffer, 256 as its histogram
 template <int MODE>
-__global__ void __launch_bounds__(32 * PC_RCOOP_WARPS)
+__global__ void __launch_bounds__(32 * PC_RCOOP_WARPS, MODE == PC_RANGE_CAPTURE ? PC_RCAP_MIN_CTAS : (MODE == PC_RANGE_COUNT ? 12 : 8))
 pc_range_coop_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstride,
                      const double *__restrict__ range, int range_is_scalar,
                      int64_t *__restrict__ counts, const int64_t *__restrict__ offsets, int32_t *__restrict__ out_idx,
@@ -88,7 +140,8 @@ pc_range_coop_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstr
 {
     constexpr bool FILL = MODE == PC_RANGE_FILL;
     constexpr bool CAPTURE = MODE == PC_RANGE_CAPTURE;
-    __shared__ uint32_t s_front[PC_RCOOP_WARPS][PC_RCOOP_CAP];
+    constexpr int FCAP = CAPTURE ? PC_RCAP_FRONT : PC_RCOOP_CAP;
+    __shared__ uint32_t s_front[PC_RCOOP_WARPS][FCAP];
     __shared__ uint32_t s_hits[CAPTURE ? PC_RCOOP_WARPS : 1][CAPTURE ? PC_RCAP_HITS : 1];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int64_t k = (int64_t)blockIdx.x * PC_RCOOP_WARPS + w;
@@ -154,7 +207,7 @@ pc_range_coop_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstr
     while (size > 0) {
         // every lane takes one node and pushes at most two; close to the capacity: one node per step (depth-first, at most
         // one more entry per tree level)
-        const int take = (size + 64 + PC_STACK <= PC_RCOOP_CAP) ? min(size, 32) : 1;
+        const int take = (size + 64 + PC_STACK <= FCAP) ? min(size, 32) : 1;
         const bool active = lane < take;
         uint32_t node = 0;
         if (active) node = F[size - 1 - lane];
@@ -212,25 +265,23 @@ pc_range_coop_kernel(pc_tree T, const float *__restrict__ q, int64_t m, int qstr
             // a short list: canonical order (ascending original index) here, then parked until its CSR position is known
             long long start = -1;
             if (total > 0 && total <= PC_RCAP_HITS) {
-                int N = 32;
-                while (N < total) N <<= 1;
                 __syncwarp();
-                for (int i = (int)total + lane; i < N; i += 32) H[i] = 0x7fffffffu;
-                __syncwarp();
-                pc_warp_bitonic(H, N, lane);
+                // the walk is over: its frontier buffer is free -- second key buffer and the digit histogram
+                const int bits = 64 - __clzll((unsigned long long)(T.n_points > 1 ? T.n_points - 1 : 1));
+                const uint32_t *sorted = pc_warp_radix_sort(H, F, F + PC_RCAP_HITS, (int)total, bits, lane);
                 if (lane == 0) {
                     const unsigned long long at = atomicAdd(S.cursor, (unsigned long long)total);
                     start = at + (unsigned long long)total <= S.stage_cap ? (long long)at : -1;
                 }
                 start = __shfl_sync(PC_FULL_MASK, start, 0);
-                if (start >= 0) for (int i = lane; i < total; i += 32) S.stage[start + i] = (int32_t)H[i];
+                if (start >= 0) for (int i = lane; i < total; i += 32) S.stage[start + i] = (int32_t)sorted[i];
             }
             if (lane == 0) S.pos[k] = start;
         }
         return;
     }
     // canonical order: ascending original index
-    if (want <= PC_RCOOP_CAP) {
+    if (want <= PC_RFILL_WARP_SORT) {
         int N = 32;
         while (N < want) N <<= 1;
         __syncwarp();
@@ -281,7 +332,7 @@ pc_range_sort_long_kernel(const unsigned long long *__restrict__ long_count, con
             if (threadIdx.x == 0) pc_sort_list(out_idx + begin, want);
             continue;
         }
-        int N = 2048;
+        int N = 512;
         while (N < want) N <<= 1;
         for (int i = threadIdx.x; i < N; i += PC_RLONG_THREADS) s_ids[i] = i < want ? (uint32_t)out_idx[begin + i] : 0x7fffffffu;
         __syncthreads();
