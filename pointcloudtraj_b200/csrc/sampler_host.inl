@@ -44,9 +44,15 @@ static char *pc_sample_carve(char *p, int64_t k, pc_sample_bufs *B)
 // the three kernels of the stream; d_state receives the engine state behind the k-th sample
 static int pc_sample_launch(pc_index *ix, const pc_sampler_dev &S, int64_t k, const pc_sample_bufs &B, double *d_xyz, float4 *d_q, cudaStream_t st)
 {
+    if (4 * k + 1 <= (int64_t)PC_SMP_SCAN_THREADS * PC_SMP_CHUNK) {        // a planner-sized batch: one CTA does it all
+        pc_sample_emit_kernel<true><<<1, PC_SMP_SCAN_THREADS, 0, st>>>(S, nullptr, nullptr, (uint64_t)k, d_xyz, d_q, B.state);
+        ix->launches++;
+        PC_CHECK_LAUNCH(ix);
+        return PC_OK;
+    }
     pc_sample_mask_kernel<<<(int)B.n_tiles, PC_SMP_THREADS, 0, st>>>(S.state, S.goal_ratio, B.masks, B.tile_map);
     pc_sample_tile_kernel<<<1, PC_SMP_SCAN_THREADS, 0, st>>>(B.tile_map, B.n_tiles, B.tile_entry);
-    pc_sample_emit_kernel<<<(int)B.n_tiles, PC_SMP_THREADS, 0, st>>>(S, B.masks, B.tile_entry, (uint64_t)k, d_xyz, d_q, B.state);
+    pc_sample_emit_kernel<false><<<(int)B.n_tiles, PC_SMP_THREADS, 0, st>>>(S, B.masks, B.tile_entry, (uint64_t)k, d_xyz, d_q, B.state);
     ix->launches += 3;
     PC_CHECK_LAUNCH(ix);
     return PC_OK;
@@ -185,10 +191,16 @@ extern "C" int pc_expand_batch(pc_index *cloud, pc_index *nodes, const pc_node_s
         // vertex keeps its own position: answered and dropped)
         if ((rc = pc_run_batch(ix, ix->lane[0], RA, (const float *)(d_q + off), kc, 4, nullptr, d_r + off)) != PC_OK) return rc;
         const int64_t n_ct = (kc + PC_CAND_TILE - 1) / PC_CAND_TILE;
-        pc_cand_count_kernel<<<(int)n_ct, PC_CAND_THREADS, 0, st>>>(d_xyz + 3 * off, d_r + off, d_ok + off, kc, z_l, safety_margin, d_ctile);
-        pc_cand_scan_kernel<<<1, 1024, 0, st>>>(d_ctile, n_ct, d_total + c, d_total + c + 1);
-        pc_cand_write_kernel<<<(int)n_ct, PC_CAND_THREADS, 0, st>>>(d_xyz + 3 * off, d_r + off, d_ok + off, d_nn + off, kc, z_l, safety_margin, d_ctile, d_out, (uint64_t)want_out);
-        ix->launches += 3;
+        if (kc <= PC_CAND_SMALL_MAX) {
+            pc_cand_small_kernel<<<1, 1024, 0, st>>>(d_xyz + 3 * off, d_r + off, d_ok + off, d_nn + off, kc, z_l, safety_margin, d_total + c, d_total + c + 1,
+                                                     d_out, (uint64_t)want_out);
+            ix->launches++;
+        } else {
+            pc_cand_count_kernel<<<(int)n_ct, PC_CAND_THREADS, 0, st>>>(d_xyz + 3 * off, d_r + off, d_ok + off, kc, z_l, safety_margin, d_ctile);
+            pc_cand_scan_kernel<<<1, 1024, 0, st>>>(d_ctile, n_ct, d_total + c, d_total + c + 1);
+            pc_cand_write_kernel<<<(int)n_ct, PC_CAND_THREADS, 0, st>>>(d_xyz + 3 * off, d_r + off, d_ok + off, d_nn + off, kc, z_l, safety_margin, d_ctile, d_out, (uint64_t)want_out);
+            ix->launches += 3;
+        }
         PC_CHECK_LAUNCH(ix);
         PC_CUDA(ix, cudaMemcpyAsync(ix->h_totals + c + 1, d_total + c + 1, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         if (c == n_chunks - 1) {

@@ -181,16 +181,30 @@ pc_sample_tile_kernel(const pc_jump *__restrict__ tile_map, int64_t n_tiles, uin
 // the samples: thread = 32 positions; sample j < k goes to out_xyz[3j..] (double, the planner's Vector3d) and, cast to
 // float32 like findNearstVertex does (corridor_finder.cpp:430), to out_q[j] = (x, y, z, 0).  The thread that meets the start of
 // sample k stores the engine state in front of it: the state the host engine continues from.
-__global__ void __launch_bounds__(PC_SMP_THREADS)
+// FUSED: a planner-sized batch (4k + 1 <= 32768 positions) is ONE CTA of 1024 threads that computes its masks itself -- one launch
+// instead of three.
+template <bool FUSED>
+__global__ void __launch_bounds__(FUSED ? PC_SMP_SCAN_THREADS : PC_SMP_THREADS)
 pc_sample_emit_kernel(pc_sampler_dev S, const uint32_t *__restrict__ masks, const uint2 *__restrict__ tile_entry, uint64_t k,
                       double *__restrict__ out_xyz, float4 *__restrict__ out_q, uint32_t *__restrict__ out_state)
 {
     __shared__ pc_jump s_warp[32];
-    const uint64_t chunk = (uint64_t)blockIdx.x * PC_SMP_THREADS + threadIdx.x;
-    const uint32_t mask = masks[chunk];
+    const uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t mask = 0u;
+    if (FUSED) {
+        uint32_t st0 = pc_lcg_skip(S.state, 2ull * PC_SMP_CHUNK * chunk);
+#pragma unroll 4
+        for (int i = 0; i < PC_SMP_CHUNK; i++) {
+            const uint32_t x1 = pc_lcg_mulmod(st0, PC_LCG_A), x2 = pc_lcg_mulmod(x1, PC_LCG_A);
+            st0 = x2;
+            if (pc_canonical(x1, x2) <= S.goal_ratio) mask |= 1u << i;
+        }
+    } else {
+        mask = masks[chunk];
+    }
     pc_jump excl;
     pc_jump_block_scan(pc_jump_of_mask(mask), &excl, s_warp);
-    const uint2 te = tile_entry[blockIdx.x];
+    const uint2 te = FUSED ? make_uint2(0u, 0u) : tile_entry[blockIdx.x];
     const uint32_t e0 = te.x;
     int pos = (int)((excl.exit >> (2 * e0)) & 3u);
     uint64_t j = (uint64_t)te.y + (e0 == 0 ? excl.cnt[0] : e0 == 1 ? excl.cnt[1] : e0 == 2 ? excl.cnt[2] : excl.cnt[3]);
@@ -317,6 +331,41 @@ pc_cand_scan_kernel(uint32_t *__restrict__ tile_count, int64_t n_tiles, const un
 }
 
 struct pc_candidate_dev { double center[3]; float radius; int32_t nearest; };      // = pc_candidate (pc_index.h)
+
+// planner-sized batches: count, scan and write in ONE CTA of 1024 threads (one launch instead of three)
+#define PC_CAND_SMALL_MAX 32768
+__global__ void __launch_bounds__(1024)
+pc_cand_small_kernel(const double *__restrict__ xyz, const float *__restrict__ radius, const uint8_t *__restrict__ ok,
+                     const int32_t *__restrict__ nearest, int64_t k, double z_l, double safety_margin,
+                     const unsigned long long *__restrict__ base, unsigned long long *__restrict__ total,
+                     pc_candidate_dev *__restrict__ out, uint64_t cap)
+{
+    __shared__ uint32_t s_warp[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned long long run = *base;
+    for (int64_t j0 = 0; j0 < k; j0 += 1024) {
+        const int64_t j = j0 + threadIdx.x;
+        const bool keep = j < k && pc_cand_keep(j, xyz, radius, ok, z_l, safety_margin);
+        const uint32_t bal = __ballot_sync(PC_FULL_MASK, keep);
+        if (lane == 0) s_warp[w] = __popc(bal);
+        __syncthreads();
+        uint32_t before = 0, all = 0;
+#pragma unroll
+        for (int x = 0; x < 32; x++) { const uint32_t c = s_warp[x]; if (x < w) before += c; all += c; }
+        if (keep) {
+            const uint64_t dst = run + before + __popc(bal & ((1u << lane) - 1u));
+            if (dst < cap) {
+                pc_candidate_dev c;
+                c.center[0] = xyz[3 * j]; c.center[1] = xyz[3 * j + 1]; c.center[2] = xyz[3 * j + 2];
+                c.radius = radius[j]; c.nearest = nearest[j];
+                out[dst] = c;
+            }
+        }
+        run += all;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = run;
+}
 
 __global__ void __launch_bounds__(PC_CAND_THREADS)
 pc_cand_write_kernel(const double *__restrict__ xyz, const float *__restrict__ radius, const uint8_t *__restrict__ ok,
