@@ -1,5 +1,5 @@
 // clearance_kernels.cuh -- trajectory clearance: Bezier sampling fused with the nearest-obstacle query and a
-// per-trajectory reduction.  One warp per trajectory.
+// per-trajectory reduction.  Flat path (schedule / eval / finish kernels, bottom of this file) or one warp per trajectory.
 //
 // Replaces checkSafeTrajectory (Planner/src/sim_planning_demo.cpp:729-781), getPosFromBezier (:715-727) and
 // safeRegionRrtStar::checkTrajPtCol (Planner/src/corridor_finder.cpp:412-416).
@@ -149,4 +149,109 @@ pc_clearance_kernel(pc_tree T, pc_radius_dev R, const pc_traj_dev *__restrict__ 
         if (out_first_hit) out_first_hit[tr] = my_first == 0x7fffffff ? -1 : my_first;
         if (out_n_samples) out_n_samples[tr] = (int32_t)chunk_base;
     }
+}
+
+// ---- the flat path: every sample of every trajectory is its own unit of work ------------------------------------------------
+// One warp per trajectory serialises a trajectory's samples: ONE trajectory of 600 samples (what the planner checks per call,
+// sim_planning_demo.cpp:729-781) took 19 dependent packet walks, 0.32 ms.  Three kernels instead:
+//   pc_clearance_schedule_kernel   one THREAD per trajectory replays the time walk (the only sequential part: repeated fp64
+//                                  additions) and writes the (t, segment) schedule, `stride` slots per trajectory
+//   pc_clearance_eval_kernel       one WARP per 32 consecutive samples of a trajectory, any trajectory: Bezier position,
+//                                  float32 cast, packet walk, per-packet minimum and first colliding sample
+//   pc_clearance_finish_kernel     one thread per trajectory reduces its packets
+// Same arithmetic per sample as pc_clearance_kernel, so the results are identical (tests run both).
+__global__ void pc_clearance_schedule_kernel(const pc_traj_dev *__restrict__ traj, int64_t n_traj, const double *__restrict__ seg_T,
+                                             double dt, double horizon, int64_t stride,
+                                             double *__restrict__ sched_t, int32_t *__restrict__ sched_seg, int32_t *__restrict__ n_samples)
+{
+    const int64_t tr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tr >= n_traj) return;
+    const pc_traj_dev tj = traj[tr];
+    const int32_t seg0 = tj.first_seg, nseg = tj.num_seg;
+    // sim_planning_demo.cpp:735-749
+    int i = 0;
+    double t_s = tj.t_now > 0.0 ? tj.t_now : 0.0;
+    for (i = 0; i < nseg; ++i) {
+        if (t_s > seg_T[seg0 + i] && i + 1 < nseg) t_s = __dsub_rn(t_s, seg_T[seg0 + i]);
+        else break;
+    }
+    double tt = t_s, t_accu = 0.0;
+    int64_t cnt = 0;
+    double *st = sched_t + tr * stride;
+    int32_t *ss = sched_seg + tr * stride;
+    while (i < nseg && cnt < stride) {
+        const double Ti = seg_T[seg0 + i];
+        if (!(tt < Ti)) { i++; tt = 0.0; continue; }
+        t_accu = __dadd_rn(t_accu, dt);
+        if (t_accu > horizon) { i++; tt = 0.0; continue; }
+        st[cnt] = tt; ss[cnt] = seg0 + i; cnt++;
+        tt = __dadd_rn(tt, dt);
+    }
+    n_samples[tr] = (int32_t)cnt;
+}
+
+__global__ void __launch_bounds__(PC_CLR_THREADS)
+pc_clearance_eval_kernel(pc_tree T, pc_radius_dev R, int64_t n_traj, int64_t stride, int64_t packets_per_traj,
+                         const int32_t *__restrict__ seg_order, const double *__restrict__ seg_T,
+                         const int64_t *__restrict__ seg_coef_off, const double *__restrict__ coef,
+                         const double *__restrict__ sched_t, const int32_t *__restrict__ sched_seg, const int32_t *__restrict__ n_samples,
+                         double *__restrict__ packet_min, int32_t *__restrict__ packet_first)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t pk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (pk >= n_traj * packets_per_traj) return;
+    const int64_t tr = pk / packets_per_traj, base = (pk - tr * packets_per_traj) * 32;
+    const int64_t cnt = n_samples[tr];
+    if (base >= cnt) return;                               // (the finish kernel reads only the packets that exist)
+    const int64_t k = base + lane;
+    const bool have = k < cnt;
+    double radius = INFINITY;
+    pc_best b[1];
+    b[0].d2 = INFINITY; b[0].idx = -1; b[0].thr = -1.0f;
+    float qv[1][3] = { { 0.f, 0.f, 0.f } };
+    bool search = false;
+    if (have) {
+        const int32_t sg = sched_seg[tr * stride + k];
+        const double Ti = seg_T[sg];
+        double pos[3];
+        pc_bezier_pos(coef + seg_coef_off[sg], seg_order[sg], __ddiv_rn(sched_t[tr * stride + k], Ti), Ti, pos);
+        if (T.n_points == 0 || pc_radius_early_out(pos[0], pos[1], pos[2], R)) {
+            radius = __dsub_rn(R.max_radius, R.search_margin);
+        } else {
+            qv[0][0] = (float)pos[0]; qv[0][1] = (float)pos[1]; qv[0][2] = (float)pos[2];
+            search = qv[0][0] == qv[0][0] && qv[0][1] == qv[0][1] && qv[0][2] == qv[0][2];
+            if (search) b[0].thr = R.bound_thr;
+        }
+    }
+    pc_packet_traverse<1>(T, qv, b, lane);
+    double my_min = INFINITY;
+    int my_first = 0x7fffffff;
+    if (have) {
+        if (search || !(radius < INFINITY)) radius = pc_radius_epilogue(b[0], R);
+        my_min = radius;
+        if (radius < 0.0) my_first = (int)k;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        my_min = fmin(my_min, __shfl_xor_sync(PC_FULL_MASK, my_min, o));
+        my_first = min(my_first, __shfl_xor_sync(PC_FULL_MASK, my_first, o));
+    }
+    if (lane == 0) { packet_min[pk] = my_min; packet_first[pk] = my_first; }
+}
+
+__global__ void pc_clearance_finish_kernel(int64_t n_traj, int64_t packets_per_traj, const int32_t *__restrict__ n_samples,
+                                           const double *__restrict__ packet_min, const int32_t *__restrict__ packet_first,
+                                           int32_t *__restrict__ out_first_hit, float *__restrict__ out_min_radius)
+{
+    const int64_t tr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tr >= n_traj) return;
+    const int64_t np = ((int64_t)n_samples[tr] + 31) / 32;
+    double mn = INFINITY;
+    int first = 0x7fffffff;
+    for (int64_t p = 0; p < np; p++) {
+        mn = fmin(mn, packet_min[tr * packets_per_traj + p]);
+        first = min(first, packet_first[tr * packets_per_traj + p]);
+    }
+    if (out_min_radius) out_min_radius[tr] = (float)mn;
+    if (out_first_hit) out_first_hit[tr] = first == 0x7fffffff ? -1 : first;
 }

@@ -85,6 +85,7 @@ struct pc_index {
     // generic device scratch for range / clearance / expansion batches
     void *scratch = nullptr; int64_t scratch_cap = 0;
     // pc_expand_batch: running candidate totals per chunk (pinned) and the events the host waits on before copying a chunk back
+    char *h_stage = nullptr;           // pc_clearance_batch: pinned staging block of small PC_HOST calls
     unsigned long long *h_totals = nullptr;
     cudaEvent_t ev_chunk[2] = { nullptr, nullptr };
 
@@ -318,6 +319,7 @@ extern "C" void pc_index_destroy(pc_index *ix)
     }
     if (ix->h_bbox) cudaFreeHost(ix->h_bbox);
     if (ix->h_totals) cudaFreeHost(ix->h_totals);
+    if (ix->h_stage) cudaFreeHost(ix->h_stage);
     for (int i = 0; i < 2; i++) if (ix->ev_chunk[i]) cudaEventDestroy(ix->ev_chunk[i]);
     if (ix->tiny_q) cudaFreeHost(ix->tiny_q);
     if (ix->tiny_f) cudaFreeHost(ix->tiny_f);
