@@ -141,9 +141,18 @@ extern "C" int pc_expand_batch(pc_index *cloud, pc_index *nodes, const pc_node_s
     pc_candidate_dev *d_out = (pc_candidate_dev *)p;
 
     // the frozen node set: a few bytes per node (the planner's tree has 10^3 .. 10^5 nodes), then its index
-    PC_CUDA(ix, cudaMemcpyAsync(d_coord, set->coord, (size_t)(3 * n) * sizeof(double), cudaMemcpyHostToDevice, st));
-    PC_CUDA(ix, cudaMemcpyAsync(d_rad, set->radius, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, st));
-    PC_CUDA(ix, cudaMemcpyAsync(d_valid, set->valid, (size_t)n, cudaMemcpyHostToDevice, st));
+    if (b_coord + b_rad + b_valid <= PC_CLR_STAGE_BYTES) {
+        // a planner-sized node set: one copy from the pinned staging block instead of three pageable ones (~10 us each)
+        if (!ix->h_stage) PC_CUDA(ix, cudaHostAlloc((void **)&ix->h_stage, 2 * PC_CLR_STAGE_BYTES, cudaHostAllocDefault));
+        memcpy(ix->h_stage, set->coord, (size_t)(3 * n) * sizeof(double));
+        memcpy(ix->h_stage + b_coord, set->radius, (size_t)n * sizeof(float));
+        memcpy(ix->h_stage + b_coord + b_rad, set->valid, (size_t)n);
+        PC_CUDA(ix, cudaMemcpyAsync(d_coord, ix->h_stage, (size_t)(b_coord + b_rad + b_valid), cudaMemcpyHostToDevice, st));
+    } else {
+        PC_CUDA(ix, cudaMemcpyAsync(d_coord, set->coord, (size_t)(3 * n) * sizeof(double), cudaMemcpyHostToDevice, st));
+        PC_CUDA(ix, cudaMemcpyAsync(d_rad, set->radius, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, st));
+        PC_CUDA(ix, cudaMemcpyAsync(d_valid, set->valid, (size_t)n, cudaMemcpyHostToDevice, st));
+    }
     pc_node_pos_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(d_coord, n, d_pos);
     ix->launches++;
     if ((rc = pc_sample_launch(ix, S, k, B, d_xyz, d_q, st)) != PC_OK) return rc;
