@@ -8,8 +8,9 @@
 //      whole batch by ONE pc_range_batch on the snapshot index: must reproduce C bit for bit
 //   F  as D, but while no path is known the whole snapshot phase of a batch (samples, nearest vertex, steering, radius, the
 //      loop's early rejections) is ONE pc_expand_batch call that generates the sample stream on the device: must reproduce D
+//   G  F + E: device-generated batches and the rewire neighbourhoods from one pc_range_batch per batch: must reproduce F
 // A and B must produce bit-identical corridors (replay mode); C is validated by the pytest against the oracle.
-// usage: rrt_client <in.bin> <out.bin>      file formats: rrt_io.hpp; output = the records of A, then B, then C, then D, then E, then F
+// usage: rrt_client <in.bin> <out.bin>      file formats: rrt_io.hpp; output = the records of A, then B, then C, then D, then E, then F, then G
 #include <cstdlib>
 #include "pc_corridor.hpp"
 #include "rrt_io.hpp"
@@ -138,6 +139,32 @@ int main(int argc, char **argv)
         rrt_run(o, F, in, true, gpu_cloud);
         if (F.device_batches == 0) return 14;
         fprintf(stderr, "F: %lld device batches\n", (long long)F.device_batches);
+        // G: F + E -- device-generated batches AND the 2 x radius neighbourhoods of treeRewire from one pc_range_batch per batch:
+        //    no per-sample work left on the host but the sequential insertion itself.  Must reproduce F.
+        pc::SafeRegionRrtStarDriver G([&](const double *c, int m, double *out) {
+            qf.resize((size_t)m * 3); rf.resize((size_t)m);
+            for (size_t i = 0; i < qf.size(); i++) qf[i] = (float)c[i];
+            if (cloud.radiusSearch(qf.data(), m, 3, rf.data()) != PC_OK) exit(8);
+            for (int i = 0; i < m; i++) out[i] = rf[(size_t)i];
+        });
+        pc::NodeSnapshotIndex nodes_g(0, 1 << 16);
+        G.setSnapshotNearest([&](const float *node_pos, int n_nodes, const float *samples, int k, int32_t *out_nearest) {
+            if (nodes_f.nearest(node_pos, n_nodes, samples, k, out_nearest, nullptr) != PC_OK) exit(9);
+        });
+        G.setSnapshotRange([&](const float *node_pos, int n_nodes, const float *centers, const float *ranges, int k,
+                               std::vector<int64_t> &offsets, std::vector<int32_t> &idx) {
+            if (nodes_g.build(node_pos, n_nodes) != PC_OK || nodes_g.range(centers, ranges, k, offsets, idx) != PC_OK) exit(11);
+        });
+        G.setDeviceBatch([&](const pc::SafeRegionRrtStarDriver::DeviceBatchRequest &rq, std::vector<double> &centers, std::vector<double> &radii) {
+            pc_sampler sm;
+            sm.engine_state = rq.engine_state; sm.reserved = 0; sm.goal_ratio = rq.goal_ratio; sm.inlier_ratio = rq.inlier_ratio;
+            for (int a = 0; a < 3; a++) { sm.end_pt[a] = rq.end_pt[a]; sm.lo[a] = rq.lo[a]; sm.hi[a] = rq.hi[a]; sm.in_lo[a] = rq.in_lo[a]; sm.in_hi[a] = rq.in_hi[a]; }
+            pc_node_set set{ rq.n_nodes, rq.node_coord, rq.node_radius, rq.node_valid };
+            uint32_t after = 0;
+            if (dev.run(sm, set, rq.z_l, rq.k, centers, radii, &after) != PC_OK) { fprintf(stderr, "device batch: %s\n", cloud.lastError()); exit(13); }
+            return after;
+        });
+        rrt_run(o, G, in, true, gpu_cloud);
     }
     fclose(o);
     kdo_free(kt[0]); kdo_free(kt[1]);

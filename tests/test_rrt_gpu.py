@@ -40,7 +40,7 @@ def _same_tree(a, b):
 
 def test_replay_parity_and_batched_growth(client):
     pts, half = synth.forest_cloud(200_000, seed=6, variant="J", return_half=True)      # the clean_demo-sized map
-    gpu, cpu, bat, bat_nodes, bat_range, bat_dev = client(6, pts, half, max_iter=20_000, K=512)
+    gpu, cpu, bat, bat_nodes, bat_range, bat_dev, bat_all = client(7, pts, half, max_iter=20_000, K=512)
     # replay mode: the GPU radius provider and the CPU oracle drive the SAME planner logic to bit-identical corridors
     assert gpu["k"] >= 2 and _same(gpu, cpu)
     validate_corridor(gpu, pts)
@@ -54,20 +54,25 @@ def test_replay_parity_and_batched_growth(client):
     # ... and with the snapshot phase of every batch generated and answered on the device (pc_expand_batch): the same tree and
     # corridor as the buffer-API batches with GPU nearest-vertex answers, bit for bit
     assert _same_tree(bat_dev, bat_nodes)
+    # ... and with both: device-generated batches + the rewire neighbourhoods from the GPU -- only the sequential insertion is
+    # left on the host; the same tree again
+    assert _same_tree(bat_all, bat_dev)
     print(f"corridor growth, 20k iterations: one query per iteration GPU {gpu['ms']:.1f} ms, CPU oracle {cpu['ms']:.1f} ms; "
           f"batches of 512: {bat['ms']:.1f} ms ({bat['nodes']} nodes, {bat['k']} spheres); "
           f"+ node-tree nearest on the GPU: {bat_nodes['ms']:.1f} ms ({bat_nodes['nodes']} nodes); "
-          f"+ node-tree range on the GPU instead: {bat_range['ms']:.1f} ms; device-generated batches: {bat_dev['ms']:.1f} ms")
+          f"+ node-tree range on the GPU instead: {bat_range['ms']:.1f} ms; device-generated batches: {bat_dev['ms']:.1f} ms; "
+          f"device-generated batches + node-tree range on the GPU: {bat_all['ms']:.1f} ms")
 
     # a second cloud message with new obstacles ON a middle sphere of each corridor: index rebuild, SafeRegionEvaluate
     # (batched re-query of the path nodes), refinement -- again bit-identical between the GPU and the oracle provider
     blocked = [gpu["path"][gpu["k"] // 2], bat["path"][bat["k"] // 2]]
     pts2 = blocked_cloud(pts, blocked)
-    recs = client(18, pts, half, max_iter=20_000, K=512, pts2=pts2, refine_iter=5000)
-    g, c, b, bn, br, bd = recs[0:3], recs[3:6], recs[6:9], recs[9:12], recs[12:15], recs[15:18]
+    recs = client(21, pts, half, max_iter=20_000, K=512, pts2=pts2, refine_iter=5000)
+    g, c, b, bn, br, bd, ba = recs[0:3], recs[3:6], recs[6:9], recs[9:12], recs[12:15], recs[15:18], recs[18:21]
     for phase in range(3):
         assert _same(br[phase], b[phase])                                               # GPU node-tree range == CPU node tree
         assert _same_tree(bd[phase], bn[phase])                                         # device-generated batches == buffer-API batches
+        assert _same_tree(ba[phase], bd[phase])                                         # ... with the GPU range provider on top
     for rec in bn[1:]:
         if rec["k"]:
             validate_corridor(rec, pts2, float_centres=True)
