@@ -17,14 +17,16 @@
 #include "build_kernels.cuh"
 #include "radix_sort.cuh"
 
+#ifndef PC_QUERY_THREADS
 #define PC_QUERY_THREADS 128
+#endif
 #define PC_STACK 96                            // tree depth <= key bits (<= 63) + position bits of coincident points (<= 31)
 #define PC_THR_SLACK 1.00000095367431640625f   // 1 + 2^-20
 #define PC_NO_NODE 0xffffffffu
 #ifndef PC_PACKET_MIN_CTAS
 #define PC_PACKET_MIN_CTAS 10       // resident CTAs per SM the packet kernels are compiled for (<= 48 registers).  With the packed
-                                    // arithmetic the kernel waits on record loads more than on issue slots: 10 CTAs 0.81 ms,
-                                    // 9: 0.82, 8: 0.85, 6: 0.87, 12 (40 registers, spills): 0.97 (profiles/r2_variants_ab.txt)
+                                    // arithmetic the kernel waits on record loads more than on issue slots: 10 CTAs 0.77 ms,
+                                    // 9: 0.80, 8: 0.82, 12 (40 registers, the hot loop spills): 1.03 (profiles/r2_variants_ab.txt)
 #endif
 #ifndef PC_PACKET_PREFETCH
 #define PC_PACKET_PREFETCH 0        // 1: when a record arrives, pull the records of its two children towards L1 (measured:
@@ -303,11 +305,11 @@ pc_query_simple_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, 
 
 // ---- warp packets ---------------------------------------------------------------------------------------------------
 // After the ordering pass the 32 * NQ queries of a warp lie in one small cell of the curve, so their searches visit almost
-// the same nodes.  The warp therefore walks the tree ONCE for all of them: one shared stack (kept in registers, entry i in
-// lane i mod 32, read back with a shuffle), every node record loaded once at a warp-uniform address, each lane testing its
-// own NQ queries against it; a child is entered when ANY query still needs it (ballot), the nearer child is chosen by a
-// majority vote of the lanes' first queries.  Control flow is warp-uniform, so all 32 lanes are active at every step and
-// there is no per-lane stack in local memory; the price is that a lane also visits nodes only its neighbours needed.
+// the same nodes.  The warp therefore walks the tree ONCE for all of them: one stack of postponed children for the whole warp
+// (local memory at a warp-uniform index, see below), every node record loaded once at a warp-uniform address, each lane
+// testing its own NQ queries against it; a child is entered when ANY query still needs it (ballot), the nearer child is
+// chosen by a majority vote of the lanes' first queries.  Control flow is warp-uniform, so all 32 lanes are active at every
+// step; the price is that a lane also visits nodes only its neighbours needed.
 // NQ = 2 halves the record bytes and the control instructions per query-visit (dense batches); NQ = 1 keeps packets small
 // for sparser batches.  A child that is a leaf is scanned on the spot; only inner nodes are pushed.
 // Measured and dropped in round 1 (profiles/r1_sweep3/4/6/8*): rejecting stale stack entries with per-entry minimum
