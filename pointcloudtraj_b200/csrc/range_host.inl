@@ -101,7 +101,7 @@ extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64
     if (space == PC_HOST) {
         // the lists are staged in the (idle) lane-0 int32 buffer
         pc_lane &L = ix->lane[0];
-        if ((rc = pc_grow(ix, &L.d_i32, &L.i32_cap, total)) != PC_OK) return rc;
+        if ((rc = pc_grow(ix, &L.d_i32, &L.i32_cap, total, total + total / 2)) != PC_OK) return rc;
         d_out = L.d_i32;
     }
     PC_CUDA(ix, cudaMemsetAsync(d_long_count, 0, sizeof(unsigned long long), st));
