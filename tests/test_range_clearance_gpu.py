@@ -180,3 +180,33 @@ def test_sphere_gather_matches_brute_force(ix):
         assert got.dtype == np.int32 and (got == want).all() if len(got) == len(want) else False
     ix.build(np.zeros((0, 3), np.float32))
     assert ix.sphere_gather((0, 0, 0), 5.0).size == 0
+
+
+def test_clearance_flat_path_equals_warp_per_trajectory_path(ix, tmp_path):
+    """The flat path (schedule / eval / finish kernels) and the one-warp-per-trajectory kernel (PC_CLEARANCE_FLAT=0, also the
+    path for schedules beyond 2^27 samples) return identical arrays; the latter runs in a subprocess (the switch is read once)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from pointcloudtraj_b200 import PcRadiusParams, PointCloudIndex, synth\n"
+        "pts, half = synth.forest_cloud(150_000, seed=6, variant='J', return_half=True)\n"
+        "tr = synth.bezier_trajectories(700, half * 0.9, seed=9)\n"
+        "tn = np.where(np.arange(700) % 3 == 0, 0.7, 0.0)\n"
+        "P = PcRadiusParams.make(0.25, 1.5, 30.0, (0.0, 0.0, 2.0))\n"
+        "ix = PointCloudIndex(max_points=len(pts), device=0); ix.build(pts)\n"
+        "fh, mr, ns = ix.clearance(tr['traj_first_seg'], tr['seg_order'], tr['seg_T'], tr['seg_coef_off'], tr['coef'], P, t_now=tn, dt=0.02, horizon=7.0)\n"
+        "np.savez(sys.argv[1], fh=fh, mr=mr, ns=ns)\n")
+    outs = []
+    for flat in ("1", "0"):
+        path = str(tmp_path / f"clr{flat}.npz")
+        env = dict(os.environ, PC_CLEARANCE_FLAT=flat)
+        p = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr
+        outs.append(np.load(path))
+    a, b = outs
+    assert (a["ns"] == b["ns"]).all() and (a["fh"] == b["fh"]).all() and (a["mr"] == b["mr"]).all()
+    assert a["ns"].max() > 300 and (a["fh"] >= 0).any() and (a["fh"] < 0).any()
