@@ -157,10 +157,14 @@ extern "C" int pc_expand_batch(pc_index *cloud, pc_index *nodes, const pc_node_s
     ix->launches++;
     if ((rc = pc_sample_launch(ix, S, k, B, d_xyz, d_q, st)) != PC_OK) return rc;
     PC_CUDA(ix, cudaMemsetAsync(d_total, 0, sizeof(unsigned long long), st));
-    // the node index and the nearest-vertex batches run on the nodes handle (its own stream), ordered by events
-    PC_CUDA(ix, cudaEventRecord(ix->ev_in, st));
-    PC_CUDA(ix, cudaStreamWaitEvent(nodes->stream, ix->ev_in, 0));
-    if ((rc = pc_index_build(nodes, (const float *)d_pos, n, 4, PC_DEVICE)) != PC_OK) return pc_fail(ix, rc, "pc_expand_batch: node index: %s", nodes->err);
+    // a planner-sized batch against a planner-sized node set needs no index: exact brute force, one launch (sampler_kernels.cuh)
+    const bool brute = k * n <= PC_BRUTE_MAX_PAIRS;
+    if (!brute) {
+        // the node index and the nearest-vertex batches run on the nodes handle (its own stream), ordered by events
+        PC_CUDA(ix, cudaEventRecord(ix->ev_in, st));
+        PC_CUDA(ix, cudaStreamWaitEvent(nodes->stream, ix->ev_in, 0));
+        if ((rc = pc_index_build(nodes, (const float *)d_pos, n, 4, PC_DEVICE)) != PC_OK) return pc_fail(ix, rc, "pc_expand_batch: node index: %s", nodes->err);
+    }
 
     // Large batches go through in chunks: while chunk c is searched, the candidates of chunk c - 1 travel to the host on a
     // side stream, and the nearest-vertex search of chunk c + 1 (nodes handle's stream) overlaps the radius search of chunk c.
@@ -185,13 +189,18 @@ extern "C" int pc_expand_batch(pc_index *cloud, pc_index *nodes, const pc_node_s
     };
     for (int64_t c = 0; c < n_chunks; c++) {
         const int64_t off = c * chunk, kc = k - off < chunk ? k - off : chunk;
-        pc_qargs NA;
-        memset(&NA, 0, sizeof NA);
-        NA.kind = PC_Q_NEAREST; NA.flags = PC_QUERY_AUTO;
-        if ((rc = pc_run_batch(nodes, nodes->lane[0], NA, (const float *)(d_q + off), kc, 4, d_nn + off, nullptr)) != PC_OK)
-            return pc_fail(ix, rc, "pc_expand_batch: nearest vertex: %s", nodes->err);
-        PC_CUDA(ix, cudaEventRecord(nodes->ev_in, nodes->stream));
-        PC_CUDA(ix, cudaStreamWaitEvent(st, nodes->ev_in, 0));
+        if (brute) {
+            pc_nearest_brute_kernel<<<(int)((kc * 32 + 255) / 256), 256, 0, st>>>(d_pos, n, d_q + off, kc, d_nn + off);
+            ix->launches++;
+        } else {
+            pc_qargs NA;
+            memset(&NA, 0, sizeof NA);
+            NA.kind = PC_Q_NEAREST; NA.flags = PC_QUERY_AUTO;
+            if ((rc = pc_run_batch(nodes, nodes->lane[0], NA, (const float *)(d_q + off), kc, 4, d_nn + off, nullptr)) != PC_OK)
+                return pc_fail(ix, rc, "pc_expand_batch: nearest vertex: %s", nodes->err);
+            PC_CUDA(ix, cudaEventRecord(nodes->ev_in, nodes->stream));
+            PC_CUDA(ix, cudaStreamWaitEvent(st, nodes->ev_in, 0));
+        }
         pc_steer_kernel<<<(int)((kc + 255) / 256), 256, 0, st>>>(d_xyz + 3 * off, d_q + off, d_nn + off, kc, d_coord, d_rad, d_valid, d_ok + off);
         ix->launches++;
         PC_CHECK_LAUNCH(ix);

@@ -244,6 +244,36 @@ __global__ void pc_node_pos_kernel(const double *__restrict__ coord, int64_t n, 
     if (i < n) pos[i] = make_float4((float)coord[3 * i], (float)coord[3 * i + 1], (float)coord[3 * i + 2], 0.f);
 }
 
+// findNearstVertex for a planner-sized batch against a planner-sized node set, without an index: one WARP per sample, the
+// lanes stride over the nodes, exact fp64 distances in the reference's operation order (kd_nearestf on float positions:
+// kdtree.c:379-382), ties to the lowest index -- the very definition the tree kernels implement, so the answers are identical.
+// k x n pair evaluations at the fp64 rate: 4096 samples x 4096 nodes take a few microseconds, where building the node index
+// (9 launches) and walking it took ~90 us of a 260 us call.
+#define PC_BRUTE_MAX_PAIRS ((int64_t)1 << 26)
+__global__ void __launch_bounds__(256)
+pc_nearest_brute_kernel(const float4 *__restrict__ pos, int64_t n, const float4 *__restrict__ q, int64_t k, int32_t *__restrict__ out_idx)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t j = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= k) return;
+    const float4 qq = q[j];
+    const double qx = (double)qq.x, qy = (double)qq.y, qz = (double)qq.z;
+    double best = INFINITY;
+    int32_t bi = -1;
+    for (int64_t i = lane; i < n; i += 32) {
+        const float4 p = __ldg(pos + i);
+        const double e = pc_exact_d2(p.x, p.y, p.z, qx, qy, qz);
+        if (e < best) { best = e; bi = (int32_t)i; }          // a lane's indices ascend: the lowest index of equal distances stays
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(PC_FULL_MASK, best, o);
+        const int32_t oi = __shfl_xor_sync(PC_FULL_MASK, bi, o);
+        if (ob < best || (ob == best && (uint32_t)oi < (uint32_t)bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) out_idx[j] = bi;
+}
+
 // genNewNode's steering (corridor_finder.cpp:385-402): the sample is pulled onto the surface of the nearest node's sphere.
 // In place: xyz[j] sample -> centre, q[j] -> float32 centre for the cloud query.  ok[j] = the nearest vertex exists and is valid
 // (:726).

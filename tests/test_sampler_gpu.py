@@ -72,9 +72,10 @@ def _host_pipeline(ix, nodes, node_coord, node_radius, node_valid, osamp, P, z_l
     return c[keep], r[keep], nn[keep]
 
 
-@pytest.mark.parametrize("n_nodes,k", [(1, 5000), (37, 4096), (3000, 200_000), (20_000, 1_000_000), (500, 5_000_000)])
+@pytest.mark.parametrize("n_nodes,k", [(1, 5000), (37, 4096), (3000, 20_000), (3000, 200_000), (20_000, 1_000_000), (500, 5_000_000)])
 def test_expand_batch_vs_buffer_api(ix, n_nodes, k):
-    """(the 5 M-sample case runs as three pipelined chunks)"""
+    """(the 5 M-sample case runs as three pipelined chunks; up to 2^26 sample-node pairs the nearest vertex is found by exact
+    brute force instead of through the node index: the first three cases)"""
     pts, half = synth.forest_cloud(200_000, seed=6, variant="J", return_half=True)
     ix.build(pts)
     rng = np.random.default_rng(n_nodes)
