@@ -97,14 +97,20 @@ int main(int argc, char **argv)
         for (int i = 0; i < m; i++) out[i] = rf[(size_t)i];
     });
     pc::NodeSnapshotIndex nodes_e(0, 1 << 16);
+    double e_build_ms = 0.0, e_range_ms = 0.0, e_max_ms = 0.0;
+    int e_calls = 0;
     E.setSnapshotRange([&](const float *node_pos, int n_nodes, const float *centers, const float *ranges, int k,
                            std::vector<int64_t> &offsets, std::vector<int32_t> &idx) {
-        if (nodes_e.build(node_pos, n_nodes) != PC_OK || nodes_e.range(centers, ranges, k, offsets, idx) != PC_OK) {
-            fprintf(stderr, "snapshot range: %s\n", nodes_e.lastError());
-            exit(11);
-        }
+        RrtTimer t;
+        if (nodes_e.build(node_pos, n_nodes) != PC_OK) { fprintf(stderr, "snapshot build: %s\n", nodes_e.lastError()); exit(11); }
+        const double b = t.ms();
+        if (nodes_e.range(centers, ranges, k, offsets, idx) != PC_OK) { fprintf(stderr, "snapshot range: %s\n", nodes_e.lastError()); exit(11); }
+        const double r = t.ms();
+        e_build_ms += b; e_range_ms += r; e_calls++;
+        if (b + r > e_max_ms) e_max_ms = b + r;
     });
     rrt_run(o, E, in, true, gpu_cloud);
+    fprintf(stderr, "E: %d range batches, node index builds %.1f ms, range calls %.1f ms, slowest batch %.1f ms\n", e_calls, e_build_ms, e_range_ms, e_max_ms);
     // the corridor as the planner publishes it (PolynomialTrajectoryExtra.path_* / radii): first sphere repeated
     {
         const pc::CorridorExport ex = pc::exportCorridor(E.path.data(), E.radius.data(), (int64_t)E.radius.size());

@@ -25,6 +25,7 @@ def client(tmp_path_factory):
         write_input(os.path.join(tmp, "in.bin"), *args, **kw)
         p = subprocess.run([exe, os.path.join(tmp, "in.bin"), os.path.join(tmp, "out.bin")], capture_output=True, text=True, timeout=900)
         assert p.returncode == 0, (p.returncode, p.stderr)
+        print(p.stderr.strip())
         return read_records(os.path.join(tmp, "out.bin"), n_rec)
     return run
 
