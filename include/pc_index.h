@@ -247,6 +247,10 @@ int  pc_profile_last_batch(pc_index *ix, float *order_ms, float *search_ms);
 /* Detail of that ordering pass (ms): out[0] clearing the sort scratch, out[1] the key kernel (curve keys, sensing-range
  * early-outs, compaction, digit histograms), out[2] the radix-sort passes. */
 int  pc_profile_last_order_detail(pc_index *ix, float out[3]);
+/* Number of warp packets of the last PC_DEVICE pc_nearest_batch on this handle that were not walked as a packet because
+ * their queries lay too far apart (a packet cut across a jump of the curve order, or across two cells of a pc_batch_shard
+ * share): their queries were answered by one independent walk each (pc_query_deferred_kernel).  Waits for the batch. */
+int  pc_profile_last_deferred_packets(pc_index *ix, int64_t *packets);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "pc_host_alloc", "pc_host_free",
     "pc_comm_unique_id", "pc_comm_init", "pc_comm_destroy", "pc_index_broadcast", "pc_shard_range",
     "pc_launch_count", "pc_profile_enable", "pc_profile_last_batch", "pc_batch_shard", "pc_index_set_radius_arith",
-    "pc_profile_last_order_detail", "pc_sample_batch", "pc_expand_batch",
+    "pc_profile_last_order_detail", "pc_profile_last_deferred_packets", "pc_sample_batch", "pc_expand_batch",
 ]
 
 
@@ -141,6 +141,7 @@ def load():
     L.pc_profile_enable.argtypes = [vp, i32]
     L.pc_profile_last_batch.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.pc_profile_last_order_detail.argtypes = [vp, C.POINTER(C.c_float)]
+    L.pc_profile_last_deferred_packets.argtypes = [vp, C.POINTER(C.c_int64)]
     L.pc_sample_batch.argtypes = [vp, C.POINTER(PcSampler), i64, i32, vp, C.POINTER(C.c_uint32)]
     L.pc_expand_batch.argtypes = [vp, vp, C.POINTER(PcNodeSet), C.POINTER(PcSampler), C.POINTER(PcRadiusParams), C.c_double, C.c_double,
                                   i64, vp, i64, C.POINTER(i64), C.POINTER(C.c_uint32)]

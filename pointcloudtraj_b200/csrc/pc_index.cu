@@ -31,6 +31,7 @@
 #define PC_SORT_MIN_NEAREST 360000      // query on the UNORDERED batch is faster on the prefix-split tree (profiles/r2_mid_batch_ab.txt)
 #define PC_COOP_MAX_BATCH 24576         // unordered batches up to this size: a group of lanes per query (profiles/r2_small_batch_ab.txt)
 #define PC_SORT_MIN_BATCH (1 << 17)     // smallest chunk of a pipelined PC_HOST call
+#define PC_SHARD_EXACT_MIN (1 << 20)    // pc_batch_shard: batches at least this large read their share's size back (see pc_share_size)
 
 static thread_local char g_create_error[256] = "";
 
@@ -104,6 +105,9 @@ struct pc_index {
     bool sort_bits_auto = true;   // no PC_SORT_BITS in the environment: pick 24 or 32 from the batch density
     int next_lane = 0;        // PC_HOST_ASYNC: lane of the next batch
     int shard_rank = 0, shard_n = 1;   // pc_batch_shard
+    int key_ctas_per_sm_shard = 0, sortkey_ctas_per_sm_shard = 0;   // occupancy of the pc_batch_shard variants of the key kernels
+    float packet_split = 8.f;          // unbounded packet walks: queries farther than this many packet extents from the first one walk separately (PC_PACKET_SPLIT, 0 = off)
+    bool shard_exact = true;           // pc_batch_shard: read the size of the share back (8 bytes, one stream sync) and size the sort / search launches by it
     int radius_arith = PC_ARITH_FP64;  // pc_index_set_radius_arith
     // experiment (PC_GRID=1): the voxel grid of grid_kernels.cuh next to the tree, used by bounded radius batches
     bool use_grid = false, grid_ready = false;
@@ -239,6 +243,8 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         if (const char *v = getenv("PC_GRID")) ix->use_grid = atoi(v) != 0;
         if (const char *v = getenv("PC_GRID_CELL")) { double c_ = atof(v); if (c_ > 0.0) ix->grid_cell = c_; }
         if (const char *v = getenv("PC_SORT_ITEMS")) ix->sort_items = atoi(v) == 8 ? 8 : 16;
+        if (const char *v = getenv("PC_SHARD_EXACT")) ix->shard_exact = atoi(v) != 0;
+        if (const char *v = getenv("PC_PACKET_SPLIT")) { double c_ = atof(v); ix->packet_split = c_ > 0.0 ? (float)c_ : 0.f; }
         if (const char *v = getenv("PC_HOST_CHUNK_QUERIES")) { long long b_ = atoll(v); if (b_ >= 1024) ix->host_chunk = b_; }
         if (const char *v = getenv("PC_COOP_GROUP")) { int b_ = atoi(v); ix->coop_group = (b_ == 32 || b_ == 16 || b_ == 8) ? b_ : 0; }
         if (const char *v = getenv("PC_COOP_MAX_BATCH")) { long long b_ = atoll(v); ix->coop_max = b_ < 0 ? 0 : b_; }
@@ -577,10 +583,27 @@ struct pc_qargs {
 
 // Morton-order a device-resident batch on lane L: *perm = permutation (device), L.counter[1] = number of leading
 // entries that still need a search (radius batches answer the sensing-range early-outs in this pass)
-static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const float *d_q, int64_t m, int qstride,
-                           int32_t *d_idx, float *d_f, const uint32_t **perm, const float4 **ordered)
+// pc_batch_shard: the number of queries of this rank's share (L.counter[1], written by the ordering kernels queued on L.os)
+static int pc_share_size(pc_index *ix, pc_lane &L, int64_t m, int64_t *out)
 {
-    *perm = nullptr; *ordered = nullptr;
+    unsigned long long h = 0;
+    PC_CUDA(ix, cudaMemcpyAsync(&h, L.counter + 1, sizeof h, cudaMemcpyDeviceToHost, L.os));
+    PC_CUDA(ix, cudaStreamSynchronize(L.os));
+    *out = (int64_t)h < m ? (int64_t)h : m;
+    return PC_OK;
+}
+
+// *m_launch: host-side bound of the number of entries to search (m, or the exact share in pc_batch_shard mode)
+static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const float *d_q, int64_t m, int qstride,
+                           int32_t *d_idx, float *d_f, const uint32_t **perm, const float4 **ordered, int64_t *m_launch, bool may_sync)
+{
+    *perm = nullptr; *ordered = nullptr; *m_launch = m;
+    // pc_batch_shard: a rank searches about 1 / shard_n of the batch, but how many exactly is known on the device only, and
+    // launches sized for the whole batch are mostly CTAs that find nothing to do (C5 on 8 GPUs: 683 k of 781 k search CTAs and
+    // 7 of 8 sort tiles; more than a millisecond of an 8 ms call).  Large sharded batches therefore read the count back --
+    // 8 bytes and one synchronisation of the ordering stream -- and size every later launch by it.  PC_DEVICE calls only:
+    // the pipelined spaces (chunked PC_HOST, the ASYNC ones) must not stall the host between their copies.
+    const bool exact = may_sync && ix->shard_n > 1 && ix->shard_exact && m >= PC_SHARD_EXACT_MIN;
     if (m > L.sort_cap) {
         int64_t c = m;
         cudaFree(L.keys_a); cudaFree(L.keys_b); cudaFree(L.vals_a); cudaFree(L.vals_b);
@@ -628,58 +651,91 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
         if ((rcb = pc_grow(ix, &L.ordered, &L.ordered_cap, m)) != PC_OK) return rcb;
         if (ix->key_ctas_per_sm == 0) {
             int a = 0, b = 0;
-            PC_CUDA(ix, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, pc_bin_count_kernel<PC_KIND_RADIUS>, 256, 0));
-            PC_CUDA(ix, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, pc_bin_count_kernel<PC_KIND_NEAREST>, 256, 0));
+            int c = 0, d = 0;
+            PC_CUDA(ix, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, pc_bin_count_kernel<PC_KIND_RADIUS, false>, 256, 0));
+            PC_CUDA(ix, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, pc_bin_count_kernel<PC_KIND_NEAREST, false>, 256, 0));
+            PC_CUDA(ix, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, pc_bin_count_kernel<PC_KIND_RADIUS, true>, 256, 0));
+            PC_CUDA(ix, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, pc_bin_count_kernel<PC_KIND_NEAREST, true>, 256, 0));
             ix->key_ctas_per_sm = a < b ? a : b;
+            ix->key_ctas_per_sm_shard = c < d ? c : d;
+            if (ix->key_ctas_per_sm_shard < 1) ix->key_ctas_per_sm_shard = 1;
             if (ix->key_ctas_per_sm < 1) ix->key_ctas_per_sm = 1;
         }
         const int64_t rounds = (m + 256 * PC_KEY_ITEMS - 1) / (256 * PC_KEY_ITEMS);
-        const int64_t wave = (int64_t)ix->sm_count * ix->key_ctas_per_sm;
+        const bool sharded = ix->shard_n > 1;
+        const int64_t wave = (int64_t)ix->sm_count * (sharded ? ix->key_ctas_per_sm_shard : ix->key_ctas_per_sm);
         const int grid = (int)(rounds < wave ? rounds : wave);
         uint32_t *tile_sum = L.bins + n_bins;
         const int n_tiles = (int)(n_bins / PC_BIN_SCAN_TILE);
         PC_CUDA(ix, cudaMemsetAsync(L.bins, 0, (size_t)n_bins * sizeof(uint32_t), L.os));
         if (prof) PC_CUDA(ix, cudaEventRecord(L.ta, L.os));
-        if (A.kind == PC_Q_RADIUS)
-            pc_bin_count_kernel<PC_KIND_RADIUS><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, A.R, d_idx, d_f, L.keys_a, L.bins, bin_bits, ix->shard_rank, ix->shard_n, ix->hilbert_lut);
-        else
-            pc_bin_count_kernel<PC_KIND_NEAREST><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, A.R, d_idx, d_f, L.keys_a, L.bins, bin_bits, ix->shard_rank, ix->shard_n, ix->hilbert_lut);
+#define PC_BIN_COUNT(K, S) pc_bin_count_kernel<K, S><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, A.R, d_idx, d_f, L.keys_a, L.bins, bin_bits, ix->shard_rank, ix->shard_n, ix->hilbert_lut)
+        if (A.kind == PC_Q_RADIUS) { if (sharded) PC_BIN_COUNT(PC_KIND_RADIUS, true); else PC_BIN_COUNT(PC_KIND_RADIUS, false); }
+        else { if (sharded) PC_BIN_COUNT(PC_KIND_NEAREST, true); else PC_BIN_COUNT(PC_KIND_NEAREST, false); }
+#undef PC_BIN_COUNT
         if (prof) PC_CUDA(ix, cudaEventRecord(L.tb, L.os));
         pc_bin_scan_tiles<<<n_tiles, 256, 0, L.os>>>(L.bins, tile_sum);
         pc_bin_scan_top<<<1, 1024, 0, L.os>>>(tile_sum, n_tiles, L.counter + 1);
         pc_bin_scan_apply<<<n_tiles, 256, 0, L.os>>>(L.bins, tile_sum);
-        pc_bin_scatter_kernel<<<grid, 256, 0, L.os>>>(d_q, m, qstride, L.keys_a, L.bins, L.ordered);
+        // (sharded: a query of another rank costs the scatter its 4-byte cell key only)
+        if (sharded)
+            pc_bin_scatter_kernel<true><<<grid, 256, 0, L.os>>>(d_q, m, qstride, L.keys_a, L.bins, L.ordered);
+        else
+            pc_bin_scatter_kernel<false><<<grid, 256, 0, L.os>>>(d_q, m, qstride, L.keys_a, L.bins, L.ordered);
         ix->launches += 5;
         PC_CHECK_LAUNCH(ix);
         *ordered = L.ordered;
+        if (exact) return pc_share_size(ix, L, m, m_launch);
         return PC_OK;
     }
     const int drop = 30 - bits > 0 ? 30 - bits : 0;     // 24-bit sort = top 24 curve bits, 32-bit sort = all 30
     // one wave of CTAs (as many as the key kernel's occupancy allows), each striding over the batch
     if (ix->sortkey_ctas_per_sm == 0) {
         int a = 0, b = 0;
-        PC_CUDA(ix, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, pc_query_key_kernel<PC_KIND_RADIUS>, 256, 0));
-        PC_CUDA(ix, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, pc_query_key_kernel<PC_KIND_NEAREST>, 256, 0));
+        int c = 0, d = 0;
+        PC_CUDA(ix, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, pc_query_key_kernel<PC_KIND_RADIUS, false>, 256, 0));
+        PC_CUDA(ix, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, pc_query_key_kernel<PC_KIND_NEAREST, false>, 256, 0));
+        PC_CUDA(ix, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, pc_query_key_kernel<PC_KIND_RADIUS, true>, 256, 0));
+        PC_CUDA(ix, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d, pc_query_key_kernel<PC_KIND_NEAREST, true>, 256, 0));
         ix->sortkey_ctas_per_sm = a < b ? a : b;
         if (ix->sortkey_ctas_per_sm < 1) ix->sortkey_ctas_per_sm = 1;
+        ix->sortkey_ctas_per_sm_shard = c < d ? c : d;
+        if (ix->sortkey_ctas_per_sm_shard < 1) ix->sortkey_ctas_per_sm_shard = 1;
     }
+    const bool sharded = ix->shard_n > 1;
     const int64_t key_ctas = (m + 256 * PC_KEY_ITEMS - 1) / (256 * PC_KEY_ITEMS);
-    const int grid = (int)(key_ctas < (int64_t)ix->sm_count * ix->sortkey_ctas_per_sm ? key_ctas : (int64_t)ix->sm_count * ix->sortkey_ctas_per_sm);
+    const int64_t key_wave = (int64_t)ix->sm_count * (sharded ? ix->sortkey_ctas_per_sm_shard : ix->sortkey_ctas_per_sm);
+    const int grid = (int)(key_ctas < key_wave ? key_ctas : key_wave);
     const int items = ix->sort_items;
     const bool fused_hist = ix->onesweep && m < OS_MAX_N;
     uint32_t *gh = fused_hist ? os_ghist(L.tile_hist) : nullptr;
-    if (fused_hist) os_clear(L.tile_hist, m, items, bits / 8, L.os);
+    if (fused_hist) {
+        // (exact share: tickets and digit histograms now, the tile status words once the number of tiles is known)
+        if (exact) PC_CUDA(ix, cudaMemsetAsync(L.tile_hist, 0, (size_t)os_scratch_words(0, bits / 8) * sizeof(uint32_t), L.os));
+        else os_clear(L.tile_hist, m, items, bits / 8, L.os);
+    }
     if (prof) PC_CUDA(ix, cudaEventRecord(L.ta, L.os));
-    if (A.kind == PC_Q_RADIUS)
-        pc_query_key_kernel<PC_KIND_RADIUS><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n, gh, bits / 8);
-    else
-        pc_query_key_kernel<PC_KIND_NEAREST><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n, gh, bits / 8);
+#define PC_QUERY_KEY(K, S) pc_query_key_kernel<K, S><<<grid, 256, 0, L.os>>>(d_q, m, qstride, ix->d_bbox, drop, A.R, d_idx, d_f, L.keys_a, L.vals_a, L.counter + 1, ix->shard_rank, ix->shard_n, gh, bits / 8)
+    if (A.kind == PC_Q_RADIUS) { if (sharded) PC_QUERY_KEY(PC_KIND_RADIUS, true); else PC_QUERY_KEY(PC_KIND_RADIUS, false); }
+    else { if (sharded) PC_QUERY_KEY(PC_KIND_NEAREST, true); else PC_QUERY_KEY(PC_KIND_NEAREST, false); }
+#undef PC_QUERY_KEY
     ix->launches++;
     PC_CHECK_LAUNCH(ix);
     if (prof) PC_CUDA(ix, cudaEventRecord(L.tb, L.os));
-    // only the L.counter[1] compacted entries (device-side count <= m) are sorted
-    int which = items == 8 ? pc_sort_pairs<uint32_t, 8>(ix, L.keys_a, L.vals_a, L.keys_b, L.vals_b, m, 0, bits, L.tile_hist, L.digit_total, L.os, L.counter + 1, fused_hist)
-                           : pc_sort_pairs<uint32_t, 16>(ix, L.keys_a, L.vals_a, L.keys_b, L.vals_b, m, 0, bits, L.tile_hist, L.digit_total, L.os, L.counter + 1, fused_hist);
+    int64_t n_sort = m;
+    if (exact) {
+        int rcs = pc_share_size(ix, L, m, &n_sort);
+        if (rcs != PC_OK) return rcs;
+        *m_launch = n_sort;
+        if (n_sort == 0) { *perm = L.vals_a; return PC_OK; }
+        if (fused_hist) {
+            const int64_t tiles = (n_sort + (int64_t)RS_THREADS * items - 1) / ((int64_t)RS_THREADS * items);
+            PC_CUDA(ix, cudaMemsetAsync(L.tile_hist + os_scratch_words(0, bits / 8), 0, (size_t)(os_scratch_words(tiles, bits / 8) - os_scratch_words(0, bits / 8)) * sizeof(uint32_t), L.os));
+        }
+    }
+    // only the L.counter[1] compacted entries (device-side count <= m; n_sort bounds it on the host) are sorted
+    int which = items == 8 ? pc_sort_pairs<uint32_t, 8>(ix, L.keys_a, L.vals_a, L.keys_b, L.vals_b, n_sort, 0, bits, L.tile_hist, L.digit_total, L.os, L.counter + 1, fused_hist)
+                           : pc_sort_pairs<uint32_t, 16>(ix, L.keys_a, L.vals_a, L.keys_b, L.vals_b, n_sort, 0, bits, L.tile_hist, L.digit_total, L.os, L.counter + 1, fused_hist);
     PC_CHECK_LAUNCH(ix);
     *perm = which ? L.vals_b : L.vals_a;
     return PC_OK;
@@ -720,7 +776,7 @@ static void pc_launch_coop(const pc_index *ix, const pc_qargs &A, const pc_tree 
 
 // run one device-resident batch on lane L
 static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float *d_q, int64_t m, int qstride,
-                        int32_t *d_idx, float *d_f, bool split_streams = false)
+                        int32_t *d_idx, float *d_f, bool split_streams = false, bool may_sync = false)
 {
     if (m == 0) return PC_OK;
     // Pipelined (ASYNC) batches run their ordering pass on the lane's high-priority stream: its short, memory-bound kernels
@@ -739,8 +795,9 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
     if (prof) PC_CUDA(ix, cudaEventRecord(L.t0, L.stream));
     // counter[1]: queries that need a search after the ordering pass
     PC_CUDA(ix, cudaMemsetAsync(L.counter, 0, 2 * sizeof(unsigned long long), L.os));
+    int64_t m_launch = m;             // launches of the search are sized by this (the exact share in pc_batch_shard mode)
     if (pc_want_sort(ix, A.flags, m, A.kind == PC_Q_NEAREST || !A.R.bounded)) {
-        int rc = pc_sort_queries(ix, L, A, d_q, m, qstride, d_idx, d_f, &perm, &ordered);
+        int rc = pc_sort_queries(ix, L, A, d_q, m, qstride, d_idx, d_f, &perm, &ordered, &m_launch, may_sync);
         if (rc != PC_OK) return rc;
         m_eff = L.counter + 1;
     }
@@ -754,39 +811,60 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
     // (profiles/r1_sweep5*: +10 % radius, +18 % nearest at 10 M queries; -3 % at 2 M, hence the threshold)
     const bool two_per_lane = ix->query_kernel == 4 || (ix->query_kernel == 3 && ix->query_kernel_auto && L.per_cell >= 3.0);
     const bool is_ordered = perm || ordered;
-    if (ix->grid_ready && is_ordered && A.kind == PC_Q_RADIUS && A.R.bounded) {
+    const int64_t ml = is_ordered ? m_launch : m;        // entries the search launch has to cover
+    // unbounded packet walks are shared by queries within a few packet extents of each other only (pc_query_packet_kernel):
+    // 64 queries fill a cube of edge e0 = cell * cbrt(64 / per_cell) at the batch's density (cell = 1/256 of the cloud's extent)
+    pc_radius_dev RN = A.R;
+    if (A.kind == PC_Q_NEAREST && ix->packet_split > 0.f && L.per_cell > 0.0) {
+        float emax = 0.f;
+        for (int a = 0; a < 3; a++) { const float e = pc_ordered_to_float(ix->h_bbox[3 + a]) - pc_ordered_to_float(ix->h_bbox[a]); emax = e > emax ? e : emax; }
+        RN.packet_split = ix->packet_split * (emax / 256.f) * (float)cbrt(64.0 / L.per_cell);
+        RN.defer_count = L.counter;             // zeroed above
+        RN.defer_list = L.keys_a;               // the ordering pass is done with its key buffer; one entry per packet at most
+        if (!(RN.packet_split > 0.f) || !is_ordered) RN.packet_split = 0.f;
+    }
+    if (ml == 0) {
+        // pc_batch_shard: nothing of this batch belongs to this rank
+    } else if (ix->grid_ready && is_ordered && A.kind == PC_Q_RADIUS && A.R.bounded) {
         // experiment (PC_GRID=1): ring search over the voxel grid instead of the tree walk
-        const int grid = (int)((m + PC_QUERY_THREADS - 1) / PC_QUERY_THREADS);
+        const int grid = (int)((ml + PC_QUERY_THREADS - 1) / PC_QUERY_THREADS);
         pc_radius_grid_kernel<<<grid, PC_QUERY_THREADS, 0, L.stream>>>(ix->grid, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
     } else if (ix->query_kernel >= 3 && is_ordered) {
         // curve-ordered batch: one warp walks the tree once for its 32 or 64 neighbouring queries
         const int per_cta = (ix->query_kernel == 5 ? 4 : (two_per_lane ? 2 : 1)) * PC_QUERY_THREADS;
-        const int grid = (int)((m + per_cta - 1) / per_cta);
+        const int grid = (int)((ml + per_cta - 1) / per_cta);
         if (ix->query_kernel == 5) {           // experiment: 128-query packets, four queries per lane
             if (A.kind == PC_Q_NEAREST)
-                pc_query_packet_kernel<PC_KIND_NEAREST, 4><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
+                pc_query_packet_kernel<PC_KIND_NEAREST, 4><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, RN, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
             else
                 pc_query_packet_kernel<PC_KIND_RADIUS, 4><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
         } else if (two_per_lane) {
             if (A.kind == PC_Q_NEAREST)
-                pc_query_packet_kernel<PC_KIND_NEAREST, 2><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
+                pc_query_packet_kernel<PC_KIND_NEAREST, 2><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, RN, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
             else
                 pc_query_packet_kernel<PC_KIND_RADIUS, 2><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
         } else if (A.kind == PC_Q_NEAREST)
-            pc_query_packet_kernel<PC_KIND_NEAREST, 1><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
+            pc_query_packet_kernel<PC_KIND_NEAREST, 1><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, RN, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
         else
             pc_query_packet_kernel<PC_KIND_RADIUS, 1><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
     } else if (ix->query_kernel >= 3 && !is_ordered && m <= ix->coop_max) {
         // small unordered batch: one warp per query (a thread-per-query search is a chain of dependent loads)
         pc_launch_coop(ix, A, T, d_q, m, qstride, d_idx, d_f, L.stream);
     } else {
-        const int grid = (int)((m + PC_QUERY_THREADS - 1) / PC_QUERY_THREADS);
+        const int grid = (int)((ml + PC_QUERY_THREADS - 1) / PC_QUERY_THREADS);
         if (A.kind == PC_Q_NEAREST)
             pc_query_simple_kernel<PC_KIND_NEAREST><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
         else
             pc_query_simple_kernel<PC_KIND_RADIUS><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
     }
-    ix->launches++;
+    if (ml > 0) ix->launches++;
+    if (ml > 0 && RN.packet_split > 0.f && ix->query_kernel >= 3 && is_ordered && !ix->grid_ready) {
+        // the packets the walk above put aside as incoherent (normally none or a handful: the kernel then costs its launch)
+        const int dgrid = ix->sm_count * PC_DEFER_CTAS_PER_SM;
+        const int per_packet = 32 * (ix->query_kernel == 5 ? 4 : (two_per_lane ? 2 : 1));
+        pc_query_deferred_kernel<<<dgrid, PC_QUERY_THREADS, 0, L.stream>>>(T, RN, d_q, m, qstride, per_packet, perm, ordered, m_eff, d_idx, d_f);
+        ix->launches++;
+    }
     PC_CHECK_LAUNCH(ix);
     if (prof) { PC_CUDA(ix, cudaEventRecord(L.t2, L.stream)); ix->profiled = true; }
     return PC_OK;
@@ -831,6 +909,19 @@ extern "C" int pc_profile_last_order_detail(pc_index *ix, float out[3])
         cudaGetLastError();
         return pc_fail(ix, PC_EINVAL, "pc_profile_last_order_detail: the last batch was not ordered");
     }
+    return PC_OK;
+}
+
+extern "C" int pc_profile_last_deferred_packets(pc_index *ix, int64_t *packets)
+{
+    if (!ix || !packets) return PC_EINVAL;
+    PC_CUDA(ix, cudaSetDevice(ix->device));
+    pc_lane &L = ix->lane[0];
+    unsigned long long h = 0;
+    // counter[0] of the lane: zeroed at the start of every batch, bumped by pc_query_packet_kernel<PC_KIND_NEAREST> only
+    PC_CUDA(ix, cudaMemcpyAsync(&h, L.counter, sizeof h, cudaMemcpyDeviceToHost, L.stream));
+    PC_CUDA(ix, cudaStreamSynchronize(L.stream));
+    *packets = (int64_t)h;
     return PC_OK;
 }
 
@@ -885,7 +976,7 @@ static int pc_query_dispatch(pc_index *ix, const pc_qargs &A, const float *q, in
     PC_CUDA(ix, cudaSetDevice(ix->device));
     if (m == 0) return PC_OK;
     const int qs = (int)q_stride;
-    if (space == PC_DEVICE) return pc_run_batch(ix, ix->lane[0], A, q, m, qs, out_idx, out_f);
+    if (space == PC_DEVICE) return pc_run_batch(ix, ix->lane[0], A, q, m, qs, out_idx, out_f, false, true);
     if (space == PC_HOST && m <= ix->tiny_batch && !pc_want_sort(ix, A.flags, m, A.kind == PC_Q_NEAREST || !A.R.bounded)) return pc_tiny_host_batch(ix, A, q, m, qs, out_idx, out_f);
 
     // order the side lanes after the last (possibly still running) index build / broadcast on the handle's stream

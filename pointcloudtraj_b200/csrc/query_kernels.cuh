@@ -226,6 +226,9 @@ struct pc_radius_dev {
     int bounded;        // PC_RADIUS_BOUNDED: out_idx = -1 wherever the radius clamps to max_radius
     int pcl_float;      // PC_ARITH_PCL_FLOAT: d2 rounded to float32 and float32 sqrt, as PCL's interface makes the reference compute
     double range_lo2, range_hi2;   // (sample_range + max_radius)^2 * (1 -+ 1e-12): outside this band the early-out needs no sqrt
+    float packet_split;            // unbounded packet walks: largest Chebyshev distance inside one shared walk (0 = no limit); packets
+    unsigned long long *defer_count;   // beyond it are queued here by pc_query_packet_kernel<PC_KIND_NEAREST> for
+    uint32_t *defer_list;              // pc_query_deferred_kernel
 };
 
 // radiusSearch epilogue on a finished search (corridor_finder.cpp:131-132); nothing found inside the bound => clamp
@@ -438,10 +441,57 @@ pc_query_packet_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, 
             else { pc_write_trivial<KIND>(R, k[j], out_idx, out_f); valid[j] = false; }
         }
     }
+    if (KIND == PC_KIND_NEAREST && R.packet_split > 0.f) {
+        // An UNBOUNDED walk is shared well only by queries that lie close together: a lane far from the others keeps an
+        // infinite (then very loose) bound until the walk -- steered by the majority -- happens to come near it, and until then
+        // it wants every node.  Packets are cut from the curve order at fixed positions, so a few straddle a jump of the curve
+        // (the 3-D Hilbert order of a flat map leaves and re-enters the slab of the map) or, in pc_batch_shard mode, two cells of
+        // the rank's share that are not neighbours; one such packet can walk a large part of the tree, alone, for milliseconds
+        // (C5 split over 8 ranks: half of the ranks took 12 ms instead of 6).  A packet with a query farther than packet_split
+        // (Chebyshev; some packet extents at the batch's density) from its first one is not walked here: it is queued for
+        // pc_query_deferred_kernel, where every query walks alone.
+        const float ax = __shfl_sync(PC_FULL_MASK, qv[0][0], 0), ay = __shfl_sync(PC_FULL_MASK, qv[0][1], 0), az = __shfl_sync(PC_FULL_MASK, qv[0][2], 0);
+        bool far = false;
+#pragma unroll
+        for (int j = 0; j < NQ; j++)
+            far = far || (b[j].thr >= 0.f && fmaxf(fmaxf(fabsf(qv[j][0] - ax), fabsf(qv[j][1] - ay)), fabsf(qv[j][2] - az)) > R.packet_split);
+        if (__any_sync(PC_FULL_MASK, far)) {
+            if (lane == 0) R.defer_list[atomicAdd(R.defer_count, 1ull)] = (uint32_t)warp_id;
+            return;
+        }
+    }
     pc_packet_traverse<NQ>(T, qv, b, lane);
 #pragma unroll
     for (int j = 0; j < NQ; j++)
         if (valid[j]) pc_write_result<KIND>(R, b[j], k[j], out_idx, out_f);
+}
+
+// The packets pc_query_packet_kernel<PC_KIND_NEAREST, NQ> put aside (R.defer_list / R.defer_count; `per_packet` = 32 NQ queries
+// each): every query walks the tree on its own, one thread per query (pc_nearest_traverse, the walk of
+// pc_query_simple_kernel) -- robust whatever the shape of the packet, and the few thousand walks of a typical call run side
+// by side.  (Measured alternative: walking such a packet in groups of nearby queries -- a group that is still spread out is
+// as slow as the packet was, and at a tight grouping distance thousands of packets queue for a handful of warps.)
+#define PC_DEFER_CTAS_PER_SM 4
+
+__global__ void __launch_bounds__(PC_QUERY_THREADS)
+pc_query_deferred_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, int64_t m, int qstride, int per_packet,
+                         const uint32_t *__restrict__ perm, const float4 *__restrict__ ordered, const unsigned long long *__restrict__ m_eff,
+                         int32_t *__restrict__ out_idx, float *__restrict__ out_f)
+{
+    const long long m_search = m_eff ? (long long)*m_eff : (long long)m;
+    const unsigned long long total = *R.defer_count * (unsigned long long)per_packet;
+    const unsigned long long n_threads = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += n_threads) {
+        const long long t = (long long)R.defer_list[e / (unsigned)per_packet] * per_packet + (long long)(e % (unsigned)per_packet);
+        if (t >= m_search) continue;
+        uint32_t k;
+        float qx, qy, qz;
+        if (ordered) { const float4 v = ordered[t]; qx = v.x; qy = v.y; qz = v.z; k = __float_as_uint(v.w); }
+        else { k = perm ? perm[t] : (uint32_t)t; const float *qq = q + (size_t)k * qstride; qx = qq[0]; qy = qq[1]; qz = qq[2]; }
+        pc_best b; b.d2 = INFINITY; b.idx = -1; b.thr = FLT_MAX;
+        pc_nearest_traverse(T, qx, qy, qz, b);
+        pc_write_result<PC_KIND_NEAREST>(R, b, k, out_idx, out_f);
+    }
 }
 
 // ---- a GROUP of lanes per query (small batches) -----------------------------------------------------------------------
@@ -580,7 +630,61 @@ __device__ __forceinline__ int pc_shard_level(const uint32_t *__restrict__ bbox,
 
 #define PC_KEY_ITEMS 8          // queries per thread and round of the key kernel: eight loads in flight, one atomic per 2048 queries
 
-template <int KIND>
+// pc_batch_shard: the rank that owns a cell of the index's cubic frame (cell coordinates at 10 bits per axis, `sh` low bits
+// dropped): a murmur-style finaliser of the packed coordinates, mapped to [0, shard_n) by a multiply-shift (no division)
+__device__ __forceinline__ int pc_shard_owner(uint32_t cx, uint32_t cy, uint32_t cz, int sh, int shard_n)
+{
+    uint32_t h = (cx >> sh) | ((cy >> sh) << 10) | ((cz >> sh) << 20);
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    return (int)__umulhi(h, (uint32_t)shard_n);
+}
+
+// pc_batch_shard, first half of a round of the key / bin-count kernels: which of the CTA's 256 x PC_KEY_ITEMS queries does this
+// rank own?  The batch is in arbitrary order, so the owned queries (1 / shard_n of them) are scattered over all lanes: running
+// the expensive part of the pass (early-out test in fp64, curve key) in place would cost every warp the full instruction count
+// with a few lanes active -- measured: 845 M warp instructions for a rank's pass over 8 x 10^7 queries, 10 of 32 lanes active,
+// as slow as keying the whole batch.  So the owned queries are compacted into shared memory (x, y, z, slot) and handed back
+// densely, entry j * 256 + thread: the rest of the round runs on full warps and costs in proportion to the share.
+// Returns the number of owned queries; x / y / z / slot / have are rewritten.  Two barriers; s_warp is free again afterwards.
+__device__ __forceinline__ uint32_t pc_shard_compact(float (&x)[PC_KEY_ITEMS], float (&y)[PC_KEY_ITEMS], float (&z)[PC_KEY_ITEMS],
+                                                     uint32_t (&slot)[PC_KEY_ITEMS], bool (&have)[PC_KEY_ITEMS], const pc_frame &f, int sh,
+                                                     int shard_rank, int shard_n, float4 *s_list, uint32_t *s_warp)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = pc_lanemask_lt();
+    uint32_t om[PC_KEY_ITEMS], warp_total = 0;
+#pragma unroll
+    for (int j = 0; j < PC_KEY_ITEMS; j++) {
+        bool own = have[j];
+        if (own) {
+            const uint32_t cx = pc_cell_coord(x[j], f.lo[0], f.inv_cell, f.max_cell), cy = pc_cell_coord(y[j], f.lo[1], f.inv_cell, f.max_cell),
+                           cz = pc_cell_coord(z[j], f.lo[2], f.inv_cell, f.max_cell);
+            own = pc_shard_owner(cx, cy, cz, sh, shard_n) == shard_rank;
+        }
+        om[j] = __ballot_sync(PC_FULL_MASK, own);
+        warp_total += __popc(om[j]);
+    }
+    if (lane == 0) s_warp[warp] = warp_total;
+    __syncthreads();
+    uint32_t off = 0, count = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { const uint32_t t = s_warp[w]; if (w < warp) off += t; count += t; }
+#pragma unroll
+    for (int j = 0; j < PC_KEY_ITEMS; j++) {
+        if ((om[j] >> lane) & 1u) s_list[off + __popc(om[j] & lt)] = make_float4(x[j], y[j], z[j], __uint_as_float(slot[j]));
+        off += __popc(om[j]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PC_KEY_ITEMS; j++) {
+        const uint32_t e = (uint32_t)j * 256u + threadIdx.x;
+        have[j] = e < count;
+        if (have[j]) { const float4 v = s_list[e]; x[j] = v.x; y[j] = v.y; z[j] = v.z; slot[j] = __float_as_uint(v.w); }
+    }
+    return count;
+}
+
+template <int KIND, bool SHARDED>
 __global__ void __launch_bounds__(256)
 pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const uint32_t *__restrict__ bbox, int drop_bits,
                     pc_radius_dev R, int32_t *__restrict__ out_idx, float *__restrict__ out_f,
@@ -595,43 +699,41 @@ pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
     __shared__ uint32_t s_warp[8];
     __shared__ unsigned long long s_base;
     __shared__ int s_shard_shift;
+    __shared__ float4 s_list[SHARDED ? 256 * PC_KEY_ITEMS : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt = pc_lanemask_lt();
     if (ghist) for (int j = threadIdx.x; j < hist_passes * RS_RADIX; j += 256) (&s_hist[0][0])[j] = 0;
-    if (shard_n > 1 && threadIdx.x == 0) s_shard_shift = 10 - pc_shard_level(bbox, m);      // cell coordinate bits dropped per axis
+    if (SHARDED && threadIdx.x == 0) s_shard_shift = 10 - pc_shard_level(bbox, m);      // cell coordinate bits dropped per axis
     __syncthreads();
     const pc_frame f = pc_make_frame(bbox, 10);
-    const int sh = shard_n > 1 ? s_shard_shift : 0;
+    const int sh = SHARDED ? s_shard_shift : 0;
     for (int64_t base = (int64_t)blockIdx.x * (256 * PC_KEY_ITEMS); base < m; base += (int64_t)gridDim.x * (256 * PC_KEY_ITEMS)) {
         float x[PC_KEY_ITEMS], y[PC_KEY_ITEMS], z[PC_KEY_ITEMS];
+        uint32_t slot[PC_KEY_ITEMS];
+        bool have[PC_KEY_ITEMS];
 #pragma unroll
         for (int j = 0; j < PC_KEY_ITEMS; j++) {
             const int64_t i = base + j * 256 + threadIdx.x;
-            if (i < m) { const float *p = q + i * qstride; x[j] = p[0]; y[j] = p[1]; z[j] = p[2]; }
+            have[j] = i < m;
+            slot[j] = (uint32_t)i;
+            if (have[j]) { const float *p = q + i * qstride; x[j] = p[0]; y[j] = p[1]; z[j] = p[2]; }
             else x[j] = y[j] = z[j] = 0.f;
         }
+        if (SHARDED) pc_shard_compact(x, y, z, slot, have, f, sh, shard_rank, shard_n, s_list, s_warp);
         uint32_t key[PC_KEY_ITEMS], mask[PC_KEY_ITEMS];
         uint32_t warp_total = 0;
 #pragma unroll
         for (int j = 0; j < PC_KEY_ITEMS; j++) {
-            const int64_t i = base + j * 256 + threadIdx.x;
-            bool search = i < m;
+            bool search = have[j];
             key[j] = 0;
             if (search) {
-                const uint32_t cx = pc_cell_coord(x[j], f.lo[0], f.inv_cell, f.max_cell), cy = pc_cell_coord(y[j], f.lo[1], f.inv_cell, f.max_cell),
-                               cz = pc_cell_coord(z[j], f.lo[2], f.inv_cell, f.max_cell);
-                if (shard_n > 1) {
-                    uint32_t h = (cx >> sh) | ((cy >> sh) << 10) | ((cz >> sh) << 20);       // the cell, then a murmur-style finaliser
-                    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
-                    search = (int)(h % (uint32_t)shard_n) == shard_rank;
-                }
-                if (search) {
-                    if (KIND == PC_KIND_RADIUS && pc_radius_early_out((double)x[j], (double)y[j], (double)z[j], R)) {
-                        search = false;
-                        pc_write_trivial<KIND>(R, (uint32_t)i, out_idx, out_f);
-                    } else {
-                        key[j] = pc_hilbert30_cells(cx, cy, cz) >> drop_bits;
-                    }
+                if (KIND == PC_KIND_RADIUS && pc_radius_early_out((double)x[j], (double)y[j], (double)z[j], R)) {
+                    search = false;
+                    pc_write_trivial<KIND>(R, slot[j], out_idx, out_f);
+                } else {
+                    const uint32_t cx = pc_cell_coord(x[j], f.lo[0], f.inv_cell, f.max_cell), cy = pc_cell_coord(y[j], f.lo[1], f.inv_cell, f.max_cell),
+                                   cz = pc_cell_coord(z[j], f.lo[2], f.inv_cell, f.max_cell);
+                    key[j] = pc_hilbert30_cells(cx, cy, cz) >> drop_bits;
                 }
             }
             mask[j] = __ballot_sync(PC_FULL_MASK, search);
@@ -653,7 +755,7 @@ pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
             if ((mask[j] >> lane) & 1u) {
                 const unsigned long long p = pos + __popc(mask[j] & lt);
                 keys[p] = key[j];
-                vals[p] = (uint32_t)(base + j * 256 + threadIdx.x);
+                vals[p] = slot[j];
                 if (ghist) for (int h = 0; h < hist_passes; h++) atomicAdd(&s_hist[h][(key[j] >> (8 * h)) & (RS_RADIX - 1)], 1u);
             }
             pos += __popc(mask[j]);
@@ -816,7 +918,7 @@ pc_hilbert_lut_kernel(uint16_t *__restrict__ lut4, uint16_t *__restrict__ lut5)
     if (i < PC_LUT5_WORDS) lut5[i] = (uint16_t)pc_hilbert_cells_n<5>(i & 31u, (i >> 5) & 31u, (i >> 10) & 31u);
 }
 
-template <int KIND>
+template <int KIND, bool SHARDED>
 __global__ void __launch_bounds__(256)
 pc_bin_count_kernel(const float *__restrict__ q, int64_t m, int qstride, const uint32_t *__restrict__ bbox,
                     pc_radius_dev R, int32_t *__restrict__ out_idx, float *__restrict__ out_f,
@@ -825,44 +927,50 @@ pc_bin_count_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
 {
     __shared__ int s_shard_shift;
     __shared__ pc_bin_frame s_frame;
+    __shared__ uint32_t s_warp[8];
+    __shared__ float4 s_list[SHARDED ? 256 * PC_KEY_ITEMS : 1];
     if (threadIdx.x == 0) {
         s_frame = pc_make_bin_frame(bbox, bin_bits);
-        if (shard_n > 1) s_shard_shift = 10 - pc_shard_level(bbox, m);
+        if (SHARDED) s_shard_shift = 10 - pc_shard_level(bbox, m);
     }
     __syncthreads();
     const pc_bin_frame F = s_frame;
     const pc_frame f = pc_make_frame(bbox, 10);
-    const int sh = shard_n > 1 ? s_shard_shift : 0;
+    const int sh = SHARDED ? s_shard_shift : 0;
     for (int64_t base = (int64_t)blockIdx.x * (256 * PC_KEY_ITEMS); base < m; base += (int64_t)gridDim.x * (256 * PC_KEY_ITEMS)) {
         float x[PC_KEY_ITEMS], y[PC_KEY_ITEMS], z[PC_KEY_ITEMS];
+        uint32_t slot[PC_KEY_ITEMS];
+        bool have[PC_KEY_ITEMS];
 #pragma unroll
         for (int j = 0; j < PC_KEY_ITEMS; j++) {
             const int64_t i = base + j * 256 + threadIdx.x;
-            if (i < m) { const float *p = q + i * qstride; x[j] = __ldcs(p); y[j] = __ldcs(p + 1); z[j] = __ldcs(p + 2); }   // read once: evict first
+            have[j] = i < m;
+            slot[j] = (uint32_t)i;
+            if (have[j]) { const float *p = q + i * qstride; x[j] = __ldcs(p); y[j] = __ldcs(p + 1); z[j] = __ldcs(p + 2); }   // read once: evict first
             else x[j] = y[j] = z[j] = 0.f;
+        }
+        if (SHARDED) {
+            // every query's cell key is written (the scatter pass reads them all): "skip" for the whole round here, coalesced;
+            // the owned queries overwrite theirs below, after the barriers of the compaction
+#pragma unroll
+            for (int j = 0; j < PC_KEY_ITEMS; j++)
+                if (have[j]) cellkey[slot[j]] = PC_BIN_SKIP;
+            pc_shard_compact(x, y, z, slot, have, f, sh, shard_rank, shard_n, s_list, s_warp);
         }
 #pragma unroll
         for (int j = 0; j < PC_KEY_ITEMS; j++) {
-            const int64_t i = base + j * 256 + threadIdx.x;
-            if (i >= m) continue;
+            if (!have[j]) continue;
             bool search = true;
-            if (shard_n > 1) {
-                const uint32_t cx = pc_cell_coord(x[j], f.lo[0], f.inv_cell, f.max_cell), cy = pc_cell_coord(y[j], f.lo[1], f.inv_cell, f.max_cell),
-                               cz = pc_cell_coord(z[j], f.lo[2], f.inv_cell, f.max_cell);
-                uint32_t h = (cx >> sh) | ((cy >> sh) << 10) | ((cz >> sh) << 20);       // the cell, then a murmur-style finaliser
-                h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
-                search = (int)(h % (uint32_t)shard_n) == shard_rank;
-            }
-            if (search && KIND == PC_KIND_RADIUS && pc_radius_early_out((double)x[j], (double)y[j], (double)z[j], R)) {
+            if (KIND == PC_KIND_RADIUS && pc_radius_early_out((double)x[j], (double)y[j], (double)z[j], R)) {
                 search = false;
-                pc_write_trivial<KIND>(R, (uint32_t)i, out_idx, out_f);
+                pc_write_trivial<KIND>(R, slot[j], out_idx, out_f);
             }
             uint32_t key = PC_BIN_SKIP;
             if (search) {
                 key = pc_bin_of(x[j], y[j], z[j], F, lut);
                 atomicAdd(bins + key, 1u);
             }
-            cellkey[i] = key;
+            if (!SHARDED || search) cellkey[slot[j]] = key;
         }
     }
 }
@@ -930,6 +1038,9 @@ pc_bin_scan_apply(uint32_t *__restrict__ bins, const uint32_t *__restrict__ tile
     p[0] = a; p[1] = b;
 }
 
+// OWNED_ONLY (pc_batch_shard): most queries belong to other ranks -- their coordinates are not read again; otherwise the
+// coordinate loads are issued together with the key loads (one round trip instead of two).
+template <bool OWNED_ONLY>
 __global__ void __launch_bounds__(256)
 pc_bin_scatter_kernel(const float *__restrict__ q, int64_t m, int qstride, const uint32_t *__restrict__ cellkey,
                       uint32_t *__restrict__ cursor, float4 *__restrict__ ordered)
@@ -941,10 +1052,16 @@ pc_bin_scatter_kernel(const float *__restrict__ q, int64_t m, int qstride, const
         for (int j = 0; j < PC_KEY_ITEMS; j++) {
             const int64_t i = base + j * 256 + threadIdx.x;
             key[j] = PC_BIN_SKIP;
+            if (OWNED_ONLY) x[j] = y[j] = z[j] = 0.f;
             if (i < m) {
                 key[j] = __ldcs(cellkey + i);
-                const float *p = q + i * qstride; x[j] = __ldcs(p); y[j] = __ldcs(p + 1); z[j] = __ldcs(p + 2);
+                if (!OWNED_ONLY) { const float *p = q + i * qstride; x[j] = __ldcs(p); y[j] = __ldcs(p + 1); z[j] = __ldcs(p + 2); }
             }
+        }
+        if (OWNED_ONLY) {
+#pragma unroll
+            for (int j = 0; j < PC_KEY_ITEMS; j++)
+                if (key[j] != PC_BIN_SKIP) { const float *p = q + (base + j * 256 + threadIdx.x) * qstride; x[j] = __ldcs(p); y[j] = __ldcs(p + 1); z[j] = __ldcs(p + 2); }
         }
         // all of a thread's cursor atomics first, then the stores: eight round trips in flight instead of eight in a row
         uint32_t pos[PC_KEY_ITEMS];

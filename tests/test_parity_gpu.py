@@ -336,3 +336,79 @@ def test_async_device_batches(ix):
         for r, o in zip(ref, outs):
             assert (r == o).all().item()
         h.close()
+
+
+def test_batch_shard_exact_share_sizing(ix):
+    """Large PC_DEVICE batches in pc_batch_shard mode read the size of the rank's share back and size the sort and search
+    launches by it (pc_share_size): the shares still partition the batch with the unsharded results -- on the radix-ordered
+    path (nearest), the binned path (bounded radius), and when a rank's share is empty or the whole batch."""
+    torch = pytest.importorskip("torch")
+    pts, half = synth.forest_cloud(200_000, seed=6, variant="J", return_half=True)
+    q = torch.from_numpy(synth.rrt_queries(1_300_000, half, seed=13)).cuda()      # >= PC_SHARD_EXACT_MIN (1 Mi)
+    P = PcRadiusParams.make(start=(0, 0, 2), **CLEAN_DEMO)
+    ix.build(pts)
+    ref_idx, ref_d2 = ix.nearest(q)
+    ref_r = ix.radius(q, P)
+    n_ranks = 3
+    owners = torch.zeros(len(q), dtype=torch.int32, device="cuda")
+    got_idx = torch.full((len(q),), -9, dtype=torch.int32, device="cuda")
+    got_r = torch.full((len(q),), float("nan"), device="cuda")
+    try:
+        for r in range(n_ranks):
+            ix.batch_shard(r, n_ranks)
+            idx, d2 = ix.nearest(q)
+            mine = idx != PointCloudIndex.NOT_MINE_IDX
+            owners += mine
+            got_idx[mine] = idx[mine]
+            assert bool((d2[mine] == ref_d2[mine]).all())
+            rad = ix.radius(q, P)
+            have = ~torch.isnan(rad)
+            got_r[have] = rad[have]
+        assert bool((owners == 1).all())
+        assert bool((got_idx == ref_idx).all()) and bool((got_r == ref_r).all())
+        # one cell holds the whole batch: one rank owns everything, the others nothing (zero-size launches are skipped)
+        one = q[:1].repeat(1_100_000, 1).contiguous()
+        ix.batch_shard(0, 1)
+        want_idx, _ = ix.nearest(one)
+        total = 0
+        for r in range(4):
+            ix.batch_shard(r, 4)
+            idx, _ = ix.nearest(one)
+            mine = idx != PointCloudIndex.NOT_MINE_IDX
+            k = int(mine.sum().item())
+            assert k in (0, len(one))
+            total += k
+            if k:
+                assert bool((idx == want_idx).all())
+        assert total == len(one)
+    finally:
+        ix.batch_shard(0, 1)
+
+
+def test_incoherent_packets_walk_alone(ix):
+    """A dense batch with a hole: the queries fill two boxes at opposite ends of the map, so the curve order jumps between
+    them and the packets cut across the jump hold queries tens of metres apart.  An unbounded packet walk of such a packet can
+    run for milliseconds; pc_query_packet_kernel puts it aside and pc_query_deferred_kernel answers its queries one by one --
+    with the same results as the unordered batch and as the reference kd-tree."""
+    torch = pytest.importorskip("torch")
+    import ctypes as C
+    pts, half = synth.forest_cloud(200_000, seed=6, variant="J", return_half=True)
+    rng = np.random.default_rng(31)
+    n = 150_011                                      # not a multiple of the packet size
+    a = rng.uniform([-half, -half, 0.6], [-half / 2, -half / 2, 4.0], (n, 3))
+    b = rng.uniform([half / 2, half / 2, 0.6], [half, half, 4.0], (n, 3))
+    q = np.concatenate([a, b]).astype(np.float32)
+    q = q[rng.permutation(len(q))]
+    ix.build(pts)
+    tq = torch.from_numpy(q).cuda()
+    idx_s, d2_s = ix.nearest(tq, flags=PC_QUERY_SORTED)
+    deferred = C.c_int64(-1)
+    assert ix._L.pc_profile_last_deferred_packets(ix._h, C.byref(deferred)) == 0
+    assert deferred.value >= 1, "the batch was built to have packets across the gap"
+    assert deferred.value < 200, "only the packets at the jumps of the order are put aside"
+    idx_u, d2_u = ix.nearest(tq, flags=PC_QUERY_UNSORTED)
+    assert bool((idx_s == idx_u).all()) and bool((d2_s == d2_u).all())
+    ko = oracle.KdOracle().build(pts, np.random.default_rng(0).permutation(len(pts)))
+    sub = rng.choice(len(q), 20_000, replace=False)
+    ridx, rd2 = ko.nearest(q[sub])
+    check_nearest(pts, q[sub], idx_s.cpu().numpy()[sub], d2_s.cpu().numpy()[sub], ridx, rd2)
