@@ -602,14 +602,21 @@ pc_query_coop_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, in
 // cell coordinates; a query that another rank owns is dropped right after its 12 bytes were read (no early-out test, no
 // curve key), so the pass over the full batch that every rank makes stays cheap.  A
 // rank's share is then as dense in space as the whole batch (dense packets) and spread over the whole map (equal cost per
-// rank).  The level is computed HERE, from the index's bounding box and the batch size only -- both identical on every
-// rank that holds a replica -- so all ranks agree on the owner of every query whatever the state of their host-side caches:
-// the finest cells (<= 1024 per axis) that still hold >= 128 queries (two packets) each -- finer cells balance the ranks
-// better, coarser ones keep more packets inside one cell.
+// rank).  The level is computed HERE, from the index's bounding box, the batch size and the number of ranks only -- all
+// identical on every rank that holds a replica -- so all ranks agree on the owner of every query whatever the state of their
+// host-side caches: the finest cells (<= 1024 per axis) that still hold >= 1024 queries each, refined (down to 128 queries
+// per cell) while a rank would get fewer than 256 of them.  Finer cells balance the ranks better, coarser ones cut fewer
+// packets at a cell's end, where the next query of the share lies some cells away (C5 on 8 ranks, cells of 735 / 5 880 /
+// 47 000 queries: 6.85 / 6.43 / 6.45 ms for the slowest rank, shares 12.3-12.7 / 12.1-12.8 / 11.5-13.1 % of the batch).
 // Measured on C5 with 8 GPUs: array slices 37 ms; contiguous stretches of the curve 41 ms and round-robin 32^3 cells 43 ms
 // (both unbalanced: 18..42 ms per rank -- on a flat map the low bits of the cell index encode the z layer); hashed cells:
 // profiles/r1_c5_strong_scaling.jsonl.
-__device__ __forceinline__ int pc_shard_level(const uint32_t *__restrict__ bbox, int64_t m)
+#ifndef PC_SHARD_CELL_QUERIES
+#define PC_SHARD_CELL_QUERIES 1024     // queries a cell of the share grid should hold (16 packets: one in 16 is cut by the cell's end)
+#endif
+#define PC_SHARD_CELL_MIN_QUERIES 128  // ... and never fewer than this
+#define PC_SHARD_CELLS_PER_RANK 256    // cells a rank should own at least (balance: the shares differ by ~ 1 / sqrt(cells))
+__device__ __forceinline__ int pc_shard_level(const uint32_t *__restrict__ bbox, int64_t m, int shard_n)
 {
     float ext[3], emax = 0.f;
 #pragma unroll
@@ -618,14 +625,27 @@ __device__ __forceinline__ int pc_shard_level(const uint32_t *__restrict__ bbox,
         emax = fmaxf(emax, ext[a]);
     }
     if (!(emax > 0.f) || !(emax < INFINITY)) return 2;
-    for (int lv = 10; lv > 2; lv--) {
+    // queries per cell at level lv (2^lv cells per axis of the cubic frame; the batch is taken to fill the bounding box)
+    auto per_cell = [&](int lv, double *cells) {
         const double c = (double)emax / (double)(1 << lv);
         double v = 1.0;
 #pragma unroll
         for (int a = 0; a < 3; a++) v *= (double)ext[a] > c ? (double)ext[a] : c;
-        if ((double)m * c * c * c / v >= 128.0) return lv;
+        *cells = v / (c * c * c);
+        return (double)m / *cells;
+    };
+    int lv = 2;
+    double cells = 0.0;
+    for (int l = 10; l > 2; l--)
+        if (per_cell(l, &cells) >= (double)PC_SHARD_CELL_QUERIES) { lv = l; break; }
+    // too few cells to deal out evenly: finer ones, as long as they still hold a couple of packets
+    while (lv < 10) {
+        per_cell(lv, &cells);
+        if (cells >= (double)PC_SHARD_CELLS_PER_RANK * shard_n) break;
+        if (per_cell(lv + 1, &cells) < (double)PC_SHARD_CELL_MIN_QUERIES) break;
+        lv++;
     }
-    return 2;
+    return lv;
 }
 
 #define PC_KEY_ITEMS 8          // queries per thread and round of the key kernel: eight loads in flight, one atomic per 2048 queries
@@ -703,7 +723,7 @@ pc_query_key_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt = pc_lanemask_lt();
     if (ghist) for (int j = threadIdx.x; j < hist_passes * RS_RADIX; j += 256) (&s_hist[0][0])[j] = 0;
-    if (SHARDED && threadIdx.x == 0) s_shard_shift = 10 - pc_shard_level(bbox, m);      // cell coordinate bits dropped per axis
+    if (SHARDED && threadIdx.x == 0) s_shard_shift = 10 - pc_shard_level(bbox, m, shard_n);      // cell coordinate bits dropped per axis
     __syncthreads();
     const pc_frame f = pc_make_frame(bbox, 10);
     const int sh = SHARDED ? s_shard_shift : 0;
@@ -931,7 +951,7 @@ pc_bin_count_kernel(const float *__restrict__ q, int64_t m, int qstride, const u
     __shared__ float4 s_list[SHARDED ? 256 * PC_KEY_ITEMS : 1];
     if (threadIdx.x == 0) {
         s_frame = pc_make_bin_frame(bbox, bin_bits);
-        if (SHARDED) s_shard_shift = 10 - pc_shard_level(bbox, m);
+        if (SHARDED) s_shard_shift = 10 - pc_shard_level(bbox, m, shard_n);
     }
     __syncthreads();
     const pc_bin_frame F = s_frame;

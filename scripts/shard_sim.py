@@ -7,6 +7,14 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
+from pointcloudtraj_b200 import _lib
+if os.environ.get("SHARD_SIM_DEFS"):      # A/B builds of the library: SHARD_SIM_DEFS="-DPC_SHARD_CELL_QUERIES=512"
+    import subprocess
+    defs = os.environ["SHARD_SIM_DEFS"]
+    out = os.path.join(ROOT, "gpurun_out", "libsim_" + "".join(c if c.isalnum() else "_" for c in defs) + ".so")
+    subprocess.run(["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"] + defs.split() +
+                   ["-o", out, os.path.join(ROOT, "pointcloudtraj_b200", "csrc", "pc_index.cu"), "-lcudart", "-ldl"], check=True, capture_output=True)
+    _lib.LIB_PATH = out
 from pointcloudtraj_b200 import PcRadiusParams, PointCloudIndex, synth
 
 what, G = sys.argv[1], int(sys.argv[2])
