@@ -226,12 +226,16 @@ void pc_comm_destroy(pc_comm *c);
 int  pc_index_broadcast(pc_index *ix, pc_comm *c, int root);
 /* Spatial sharding of query batches: after pc_batch_shard(ix, rank, n_ranks) every pc_nearest_batch / pc_radius_batch on
  * this handle expects the SAME full batch on every rank and answers only this rank's share: the cubic cells of the index's
- * curve frame (at a level chosen on the device from the index's bounding box and the batch size, so that a cell holds a few
- * hundred queries and all ranks agree) are dealt to the ranks by a hash of the cell coordinates.  Every query is answered by
+ * curve frame (at a level chosen on the device from the index's bounding box, the batch size and n_ranks, so that a cell holds
+ * about a thousand queries, a rank gets a few hundred cells and all ranks agree) are dealt to the ranks by a hash of the
+ * cell coordinates.  Every query is answered by
  * exactly one rank; entries of other ranks' queries are left untouched in the output arrays (pre-fill them, e.g. out_idx
  * with INT32_MIN, to tell them apart).  A rank's share is as dense in space as the whole batch and spread over the whole
  * map, which keeps the search efficient and balanced when one batch is split over many GPUs.  n_ranks = 1 switches back.
- * Needs the ordering pass (PC_EINVAL when PC_SORT_BITS=0 disabled it). */
+ * Needs the ordering pass (PC_EINVAL when PC_SORT_BITS=0 disabled it).
+ * A PC_DEVICE call of >= 2^20 queries in this mode synchronises the handle's stream once, in the middle of the call (it
+ * reads the size of the share back, 8 bytes, and sizes the sort and search launches by it; PC_SHARD_EXACT=0 keeps the call
+ * fully asynchronous with launches sized for the whole batch); the pipelined spaces never do. */
 int  pc_batch_shard(pc_index *ix, int rank, int n_ranks);
 /* contiguous slice [begin, end) of m units owned by `rank` (queries or trajectories) */
 void pc_shard_range(int64_t m, int rank, int n_ranks, int64_t *begin, int64_t *end);
@@ -247,7 +251,8 @@ int  pc_profile_last_batch(pc_index *ix, float *order_ms, float *search_ms);
 /* Detail of that ordering pass (ms): out[0] clearing the sort scratch, out[1] the key kernel (curve keys, sensing-range
  * early-outs, compaction, digit histograms), out[2] the radix-sort passes. */
 int  pc_profile_last_order_detail(pc_index *ix, float out[3]);
-/* Number of warp packets of the last PC_DEVICE pc_nearest_batch on this handle that were not walked as a packet because
+/* Number of warp packets of the last PC_DEVICE pc_nearest_batch (or PC_RADIUS_FULL_NN pc_radius_batch) on this handle that
+ * were not walked as a packet because
  * their queries lay too far apart (a packet cut across a jump of the curve order, or across two cells of a pc_batch_shard
  * share): their queries were answered by one independent walk each (pc_query_deferred_kernel).  Waits for the batch. */
 int  pc_profile_last_deferred_packets(pc_index *ix, int64_t *packets);

@@ -815,7 +815,7 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
     // unbounded packet walks are shared by queries within a few packet extents of each other only (pc_query_packet_kernel):
     // 64 queries fill a cube of edge e0 = cell * cbrt(64 / per_cell) at the batch's density (cell = 1/256 of the cloud's extent)
     pc_radius_dev RN = A.R;
-    if (A.kind == PC_Q_NEAREST && ix->packet_split > 0.f && L.per_cell > 0.0) {
+    if ((A.kind == PC_Q_NEAREST || !A.R.bounded) && ix->packet_split > 0.f && L.per_cell > 0.0) {
         float emax = 0.f;
         for (int a = 0; a < 3; a++) { const float e = pc_ordered_to_float(ix->h_bbox[3 + a]) - pc_ordered_to_float(ix->h_bbox[a]); emax = e > emax ? e : emax; }
         RN.packet_split = ix->packet_split * (emax / 256.f) * (float)cbrt(64.0 / L.per_cell);
@@ -837,16 +837,16 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
             if (A.kind == PC_Q_NEAREST)
                 pc_query_packet_kernel<PC_KIND_NEAREST, 4><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, RN, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
             else
-                pc_query_packet_kernel<PC_KIND_RADIUS, 4><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
+                pc_query_packet_kernel<PC_KIND_RADIUS, 4><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, RN, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
         } else if (two_per_lane) {
             if (A.kind == PC_Q_NEAREST)
                 pc_query_packet_kernel<PC_KIND_NEAREST, 2><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, RN, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
             else
-                pc_query_packet_kernel<PC_KIND_RADIUS, 2><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
+                pc_query_packet_kernel<PC_KIND_RADIUS, 2><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, RN, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
         } else if (A.kind == PC_Q_NEAREST)
             pc_query_packet_kernel<PC_KIND_NEAREST, 1><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, RN, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
         else
-            pc_query_packet_kernel<PC_KIND_RADIUS, 1><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, A.R, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
+            pc_query_packet_kernel<PC_KIND_RADIUS, 1><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, RN, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
     } else if (ix->query_kernel >= 3 && !is_ordered && m <= ix->coop_max) {
         // small unordered batch: one warp per query (a thread-per-query search is a chain of dependent loads)
         pc_launch_coop(ix, A, T, d_q, m, qstride, d_idx, d_f, L.stream);
@@ -862,7 +862,8 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
         // the packets the walk above put aside as incoherent (normally none or a handful: the kernel then costs its launch)
         const int dgrid = ix->sm_count * PC_DEFER_CTAS_PER_SM;
         const int per_packet = 32 * (ix->query_kernel == 5 ? 4 : (two_per_lane ? 2 : 1));
-        pc_query_deferred_kernel<<<dgrid, PC_QUERY_THREADS, 0, L.stream>>>(T, RN, d_q, m, qstride, per_packet, perm, ordered, m_eff, d_idx, d_f);
+        if (A.kind == PC_Q_NEAREST) pc_query_deferred_kernel<PC_KIND_NEAREST><<<dgrid, PC_QUERY_THREADS, 0, L.stream>>>(T, RN, d_q, m, qstride, per_packet, perm, ordered, m_eff, d_idx, d_f);
+        else pc_query_deferred_kernel<PC_KIND_RADIUS><<<dgrid, PC_QUERY_THREADS, 0, L.stream>>>(T, RN, d_q, m, qstride, per_packet, perm, ordered, m_eff, d_idx, d_f);
         ix->launches++;
     }
     PC_CHECK_LAUNCH(ix);

@@ -441,7 +441,7 @@ pc_query_packet_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, 
             else { pc_write_trivial<KIND>(R, k[j], out_idx, out_f); valid[j] = false; }
         }
     }
-    if (KIND == PC_KIND_NEAREST && R.packet_split > 0.f) {
+    if ((KIND == PC_KIND_NEAREST || !R.bounded) && R.packet_split > 0.f) {
         // An UNBOUNDED walk is shared well only by queries that lie close together: a lane far from the others keeps an
         // infinite (then very loose) bound until the walk -- steered by the majority -- happens to come near it, and until then
         // it wants every node.  Packets are cut from the curve order at fixed positions, so a few straddle a jump of the curve
@@ -473,6 +473,7 @@ pc_query_packet_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, 
 // as slow as the packet was, and at a tight grouping distance thousands of packets queue for a handful of warps.)
 #define PC_DEFER_CTAS_PER_SM 4
 
+template <int KIND>
 __global__ void __launch_bounds__(PC_QUERY_THREADS)
 pc_query_deferred_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q, int64_t m, int qstride, int per_packet,
                          const uint32_t *__restrict__ perm, const float4 *__restrict__ ordered, const unsigned long long *__restrict__ m_eff,
@@ -490,7 +491,7 @@ pc_query_deferred_kernel(pc_tree T, pc_radius_dev R, const float *__restrict__ q
         else { k = perm ? perm[t] : (uint32_t)t; const float *qq = q + (size_t)k * qstride; qx = qq[0]; qy = qq[1]; qz = qq[2]; }
         pc_best b; b.d2 = INFINITY; b.idx = -1; b.thr = FLT_MAX;
         pc_nearest_traverse(T, qx, qy, qz, b);
-        pc_write_result<PC_KIND_NEAREST>(R, b, k, out_idx, out_f);
+        pc_write_result<KIND>(R, b, k, out_idx, out_f);
     }
 }
 

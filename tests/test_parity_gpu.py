@@ -412,3 +412,11 @@ def test_incoherent_packets_walk_alone(ix):
     sub = rng.choice(len(q), 20_000, replace=False)
     ridx, rd2 = ko.nearest(q[sub])
     check_nearest(pts, q[sub], idx_s.cpu().numpy()[sub], d2_s.cpu().numpy()[sub], ridx, rd2)
+    # the unbounded radius search (PC_RADIUS_FULL_NN) takes the same route
+    P = PcRadiusParams.make(start=(0, 0, 2), search_margin=0.25, max_radius=1.5, sample_range=-1.0)
+    rad_s = ix.radius(tq, P, flags=PC_RADIUS_FULL_NN | PC_QUERY_SORTED)
+    assert ix._L.pc_profile_last_deferred_packets(ix._h, C.byref(deferred)) == 0 and deferred.value >= 1
+    rad_u = ix.radius(tq, P, flags=PC_RADIUS_FULL_NN | PC_QUERY_UNSORTED)
+    assert bool((rad_s == rad_u).all())
+    rrad, _ = ko.radius_batch(oracle.RadiusParams.make(0.25, 1.5, -1.0, (0, 0, 2)), q[sub])
+    assert (rad_s.cpu().numpy()[sub] == rrad.astype(np.float32)).all()
