@@ -107,6 +107,7 @@ struct pc_index {
     int shard_rank = 0, shard_n = 1;   // pc_batch_shard
     int key_ctas_per_sm_shard = 0, sortkey_ctas_per_sm_shard = 0;   // occupancy of the pc_batch_shard variants of the key kernels
     float packet_split = 8.f;          // unbounded packet walks: queries farther than this many packet extents from the first one walk separately (PC_PACKET_SPLIT, 0 = off)
+    double trace_slow_ms = 0.0;        // PC_TRACE_SLOW_MS: pc_range_batch calls slower than this report their host-side phases
     bool shard_exact = true;           // pc_batch_shard: read the size of the share back (8 bytes, one stream sync) and size the sort / search launches by it
     int radius_arith = PC_ARITH_FP64;  // pc_index_set_radius_arith
     // experiment (PC_GRID=1): the voxel grid of grid_kernels.cuh next to the tree, used by bounded radius batches
@@ -153,13 +154,62 @@ static int pc_fail(pc_index *ix, int code, const char *fmt, ...)
 
 #define PC_CHECK_LAUNCH(ix) PC_CUDA(ix, cudaGetLastError())
 
+// ---- per-call buffers come from the device's stream-ordered memory pool ----------------------------------------------
+// A plain cudaMalloc is not a cheap call: on the pool's (virtualised) B200 boxes it stalls the host for 60 - 570 ms every few
+// dozen calls (PC_TRACE_SLOW_MS found it in the planner's rewire batches, whose lists grow while the tree grows: 3 of 8 runs
+// lost half a second to one allocation).  The buffers that grow with the calls are therefore taken from the default memory
+// pool of the device (cudaMallocAsync), which is told never to give memory back to the driver and is warmed at the first
+// pc_index_create: once the pool holds the working set, growing a buffer is bookkeeping in user space.  The cloud arena
+// (sized by max_points at pc_index_create) stays a plain allocation.
+#define PC_POOL_WARM_BYTES ((size_t)256 << 20)      // PC_POOL_WARM_MB overrides
+
+static void pc_pool_setup(int device)
+{
+    static bool done[64] = { false };
+    if (device < 0 || device >= 64 || done[device]) return;
+    done[device] = true;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) != cudaSuccess) { cudaGetLastError(); return; }
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    size_t warm = PC_POOL_WARM_BYTES;
+    if (const char *v = getenv("PC_POOL_WARM_MB")) { long long b_ = atoll(v); warm = b_ > 0 ? (size_t)b_ << 20 : 0; }
+    void *p = nullptr;
+    if (warm && cudaMallocAsync(&p, warm, (cudaStream_t)0) == cudaSuccess) { cudaFreeAsync(p, (cudaStream_t)0); cudaStreamSynchronize((cudaStream_t)0); }
+    cudaGetLastError();
+}
+
+// allocation usable on every stream of the handle when the call returns
+static cudaError_t pc_pool_alloc(pc_index *ix, void **p, size_t bytes)
+{
+    cudaError_t e = cudaMallocAsync(p, bytes, ix->stream);
+    if (e != cudaSuccess) { *p = nullptr; return e; }
+    return cudaStreamSynchronize(ix->stream);
+}
+
+// like cudaFree: nothing on the device may still use the buffer afterwards, whatever stream it ran on
+static void pc_pool_free(pc_index *ix, void *p)
+{
+    if (!p) return;
+    cudaDeviceSynchronize();
+    cudaFreeAsync(p, ix->stream);
+}
+
 template <typename T>
 static int pc_grow(pc_index *ix, T **ptr, int64_t *cap, int64_t want, int64_t min_cap = 0)
 {
     if (want <= *cap) return PC_OK;
+    // buffers never grow by less than a factor of two and never start below 64 Ki elements: a handle reaches its working size
+    // within a few calls
     int64_t c = want > min_cap ? want : min_cap;
-    if (*ptr) { PC_CUDA(ix, cudaFree(*ptr)); *ptr = nullptr; *cap = 0; }
-    PC_CUDA(ix, cudaMalloc((void **)ptr, (size_t)c * sizeof(T)));
+    if (c < 2 * *cap) c = 2 * *cap;
+    if (c < (1 << 16)) c = 1 << 16;
+    if (*ptr) { pc_pool_free(ix, *ptr); *ptr = nullptr; *cap = 0; }
+    if (pc_pool_alloc(ix, (void **)ptr, (size_t)c * sizeof(T)) != cudaSuccess) {
+        cudaGetLastError();                     // no room for the head-room: exactly what was asked for
+        c = want > min_cap ? want : min_cap;
+        PC_CUDA(ix, pc_pool_alloc(ix, (void **)ptr, (size_t)c * sizeof(T)));
+    }
     *cap = c;
     return PC_OK;
 }
@@ -230,6 +280,7 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
     do {
 #define TRY(call) if ((e = (call)) != cudaSuccess) { rc = pc_fail(nullptr, e == cudaErrorMemoryAllocation ? PC_ENOMEM : PC_ECUDA, "%s: %s", #call, cudaGetErrorString(e)); break; }
         TRY(cudaSetDevice(device));
+        pc_pool_setup(device);
         cudaDeviceProp prop;
         TRY(cudaGetDeviceProperties(&prop, device));
         if (prop.major < 10) { rc = pc_fail(nullptr, PC_ECUDA, "pc_index_create: device is sm_%d%d, this library is built for sm_100a only", prop.major, prop.minor); break; }
@@ -244,6 +295,7 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         if (const char *v = getenv("PC_GRID_CELL")) { double c_ = atof(v); if (c_ > 0.0) ix->grid_cell = c_; }
         if (const char *v = getenv("PC_SORT_ITEMS")) ix->sort_items = atoi(v) == 8 ? 8 : 16;
         if (const char *v = getenv("PC_SHARD_EXACT")) ix->shard_exact = atoi(v) != 0;
+        if (const char *v = getenv("PC_TRACE_SLOW_MS")) ix->trace_slow_ms = atof(v);
         if (const char *v = getenv("PC_PACKET_SPLIT")) { double c_ = atof(v); ix->packet_split = c_ > 0.0 ? (float)c_ : 0.f; }
         if (const char *v = getenv("PC_HOST_CHUNK_QUERIES")) { long long b_ = atoll(v); if (b_ >= 1024) ix->host_chunk = b_; }
         if (const char *v = getenv("PC_COOP_GROUP")) { int b_ = atoi(v); ix->coop_group = (b_ == 32 || b_ == 16 || b_ == 8) ? b_ : 0; }
@@ -606,12 +658,12 @@ static int pc_sort_queries(pc_index *ix, pc_lane &L, const pc_qargs &A, const fl
     const bool exact = may_sync && ix->shard_n > 1 && ix->shard_exact && m >= PC_SHARD_EXACT_MIN;
     if (m > L.sort_cap) {
         int64_t c = m;
-        cudaFree(L.keys_a); cudaFree(L.keys_b); cudaFree(L.vals_a); cudaFree(L.vals_b);
+        pc_pool_free(ix, L.keys_a); pc_pool_free(ix, L.keys_b); pc_pool_free(ix, L.vals_a); pc_pool_free(ix, L.vals_b);
         L.keys_a = L.keys_b = L.vals_a = L.vals_b = nullptr; L.sort_cap = 0;
-        PC_CUDA(ix, cudaMalloc((void **)&L.keys_a, (size_t)c * 4));
-        PC_CUDA(ix, cudaMalloc((void **)&L.keys_b, (size_t)c * 4));
-        PC_CUDA(ix, cudaMalloc((void **)&L.vals_a, (size_t)c * 4));
-        PC_CUDA(ix, cudaMalloc((void **)&L.vals_b, (size_t)c * 4));
+        PC_CUDA(ix, pc_pool_alloc(ix, (void **)&L.keys_a, (size_t)c * 4));
+        PC_CUDA(ix, pc_pool_alloc(ix, (void **)&L.keys_b, (size_t)c * 4));
+        PC_CUDA(ix, pc_pool_alloc(ix, (void **)&L.vals_a, (size_t)c * 4));
+        PC_CUDA(ix, pc_pool_alloc(ix, (void **)&L.vals_b, (size_t)c * 4));
         L.sort_cap = c;
     }
     int rc = pc_grow(ix, &L.tile_hist, &L.hist_cap, pc_sort_scratch_words(m, 8, 4));

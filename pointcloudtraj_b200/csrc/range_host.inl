@@ -3,9 +3,12 @@
 static int pc_scratch(pc_index *ix, int64_t bytes, void **out)
 {
     if (bytes > ix->scratch_cap) {
-        if (ix->scratch) { PC_CUDA(ix, cudaFree(ix->scratch)); ix->scratch = nullptr; ix->scratch_cap = 0; }
-        int64_t c = bytes + bytes / 4 + 4096;
-        PC_CUDA(ix, cudaMalloc(&ix->scratch, (size_t)c));
+        // (see pc_grow: reallocations are what must stay rare, not bytes -- twice the request, twice the old size, 8 MB at least)
+        int64_t c = 2 * bytes;
+        if (c < 2 * ix->scratch_cap) c = 2 * ix->scratch_cap;
+        if (c < (8 << 20)) c = 8 << 20;
+        if (ix->scratch) { pc_pool_free(ix, ix->scratch); ix->scratch = nullptr; ix->scratch_cap = 0; }
+        PC_CUDA(ix, pc_pool_alloc(ix, &ix->scratch, (size_t)c));
         ix->scratch_cap = c;
     }
     *out = ix->scratch;
@@ -26,6 +29,14 @@ extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64
         return pc_fail(ix, PC_EINVAL, "pc_range_batch: bad argument");
     PC_CUDA(ix, cudaSetDevice(ix->device));
     cudaStream_t st = ix->stream;
+    // PC_TRACE_SLOW_MS=<ms>: a call that takes longer reports where the host spent the time (stderr)
+    struct pc_trace {
+        double t[8]; int n = 0; double limit;
+        static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+        void mark() { if (limit > 0.0 && n < 8) t[n++] = now(); }
+    } tr;
+    tr.limit = ix->trace_slow_ms;
+    tr.mark();
     const int qs = (int)q_stride;
     const int64_t n_range = range_is_scalar ? 1 : m;
     const int64_t n_tiles = (m + PC_SCAN_TILE - 1) / PC_SCAN_TILE;
@@ -45,6 +56,7 @@ extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64
     const int64_t b_todo = capture ? pc_align_up((m + 1) * (int64_t)sizeof(int64_t), 256) : 0;
     void *base = nullptr;
     if ((rc = pc_scratch(ix, b_q + b_r + b_off + b_cnt + b_tile + b_long + b_stage + b_pos + b_todo + 256, &base)) != PC_OK) return rc;
+    tr.mark();            // 1: scratch
     char *p = (char *)base;
     const float *d_q = q_xyz; const double *d_r = range; int64_t *d_off = out_offsets;
     if (space == PC_HOST) {
@@ -93,6 +105,7 @@ extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64
     if (space == PC_HOST)
         PC_CUDA(ix, cudaMemcpyAsync(out_offsets, d_off, (size_t)(m + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     PC_CUDA(ix, cudaStreamSynchronize(st));
+    tr.mark();            // 2: uploads + counting / capturing walk + scan + read-back
     if (!out_idx && cap == 0) return PC_OK;              // offsets only
     if (total > cap) return pc_fail(ix, PC_ECAP, "pc_range_batch: %lld hits exceed cap %lld", (long long)total, (long long)cap);
     if (total == 0) return PC_OK;
@@ -104,6 +117,7 @@ extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64
         if ((rc = pc_grow(ix, &L.d_i32, &L.i32_cap, total, total + total / 2)) != PC_OK) return rc;
         d_out = L.d_i32;
     }
+    tr.mark();            // 3: list buffer
     PC_CUDA(ix, cudaMemsetAsync(d_long_count, 0, sizeof(unsigned long long), st));
     PC_CUDA(ix, cudaMemsetAsync(d_todo_count, 0, sizeof(unsigned long long), st));
     pc_range_place_kernel<<<(int)((m + PC_RPLACE_WARPS - 1) / PC_RPLACE_WARPS), 32 * PC_RPLACE_WARPS, 0, st>>>(m, d_off, S.stage, S.pos, d_out, d_todo_count, d_todo_list);
@@ -130,10 +144,16 @@ extern "C" int pc_range_batch(pc_index *ix, const float *q_xyz, int64_t m, int64
         ix->launches++;
         PC_CHECK_LAUNCH(ix);
     }
+    tr.mark();            // 4: place / fill / long-sort launches
     if (space == PC_HOST) {
         PC_CUDA(ix, cudaMemcpyAsync(out_idx, d_out, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         PC_CUDA(ix, cudaStreamSynchronize(st));
     }
+    tr.mark();            // 5: lists home
+    if (tr.limit > 0.0 && tr.n == 6 && tr.t[5] - tr.t[0] > tr.limit)
+        fprintf(stderr, "pcindex: slow pc_range_batch %.1f ms (m %lld, hits %lld, long lists <= %lld): scratch %.1f, walk + scan %.1f, list buffer %.1f, launches %.1f, "
+                "kernels + copy home %.1f\n", tr.t[5] - tr.t[0], (long long)m, (long long)total, (long long)max_todo,
+                tr.t[1] - tr.t[0], tr.t[2] - tr.t[1], tr.t[3] - tr.t[2], tr.t[4] - tr.t[3], tr.t[5] - tr.t[4]);
     return PC_OK;
 }
 
@@ -153,12 +173,12 @@ extern "C" int pc_sphere_gather(pc_index *ix, const double center[3], double rad
     const int64_t want = cap < n ? cap : n;
     int rc;
     if (want > L.sort_cap) {
-        cudaFree(L.keys_a); cudaFree(L.keys_b); cudaFree(L.vals_a); cudaFree(L.vals_b);
+        pc_pool_free(ix, L.keys_a); pc_pool_free(ix, L.keys_b); pc_pool_free(ix, L.vals_a); pc_pool_free(ix, L.vals_b);
         L.keys_a = L.keys_b = L.vals_a = L.vals_b = nullptr; L.sort_cap = 0;
-        PC_CUDA(ix, cudaMalloc((void **)&L.keys_a, (size_t)want * 4));
-        PC_CUDA(ix, cudaMalloc((void **)&L.keys_b, (size_t)want * 4));
-        PC_CUDA(ix, cudaMalloc((void **)&L.vals_a, (size_t)want * 4));
-        PC_CUDA(ix, cudaMalloc((void **)&L.vals_b, (size_t)want * 4));
+        PC_CUDA(ix, pc_pool_alloc(ix, (void **)&L.keys_a, (size_t)want * 4));
+        PC_CUDA(ix, pc_pool_alloc(ix, (void **)&L.keys_b, (size_t)want * 4));
+        PC_CUDA(ix, pc_pool_alloc(ix, (void **)&L.vals_a, (size_t)want * 4));
+        PC_CUDA(ix, pc_pool_alloc(ix, (void **)&L.vals_b, (size_t)want * 4));
         L.sort_cap = want;
     }
     if ((rc = pc_grow(ix, &L.tile_hist, &L.hist_cap, pc_sort_scratch_words(want > 0 ? want : 1, 16, 4))) != PC_OK) return rc;
