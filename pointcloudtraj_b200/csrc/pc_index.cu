@@ -971,7 +971,7 @@ extern "C" int pc_profile_last_deferred_packets(pc_index *ix, int64_t *packets)
     PC_CUDA(ix, cudaSetDevice(ix->device));
     pc_lane &L = ix->lane[0];
     unsigned long long h = 0;
-    // counter[0] of the lane: zeroed at the start of every batch, bumped by pc_query_packet_kernel<PC_KIND_NEAREST> only
+    // counter[0] of the lane: zeroed at the start of every batch, bumped by the unbounded pc_query_packet_kernel walks only
     PC_CUDA(ix, cudaMemcpyAsync(&h, L.counter, sizeof h, cudaMemcpyDeviceToHost, L.stream));
     PC_CUDA(ix, cudaStreamSynchronize(L.stream));
     *packets = (int64_t)h;
