@@ -30,6 +30,7 @@
 #define PC_SORT_MIN_RADIUS 640000       // PC_QUERY_AUTO orders radius / nearest batches at least this large: below, one thread per
 #define PC_SORT_MIN_NEAREST 360000      // query on the UNORDERED batch is faster on the prefix-split tree (profiles/r2_mid_batch_ab.txt)
 #define PC_COOP_MAX_BATCH 24576         // unordered batches up to this size: a group of lanes per query (profiles/r2_small_batch_ab.txt)
+#define PC_COOP_MAX_BATCH_UNBOUNDED 8192
 #define PC_SORT_MIN_BATCH (1 << 17)     // smallest chunk of a pipelined PC_HOST call
 #define PC_SHARD_EXACT_MIN (1 << 20)    // pc_batch_shard: batches at least this large read their share's size back (see pc_share_size)
 
@@ -126,6 +127,8 @@ struct pc_index {
     int coop_group = 0;                     // lanes per query of the small-batch kernel: 0 = by batch size, else 32 / 16 / 8 (PC_COOP_GROUP)
     int64_t coop_g32_max = 6144, coop_g16_max = 12288;   // batch sizes up to which 32 / 16 lanes per query are used (8 above)
     int64_t coop_max = PC_COOP_MAX_BATCH;   // unordered batches up to this size run a group of lanes per query (PC_COOP_MAX_BATCH)
+    int64_t coop_max_unbounded = PC_COOP_MAX_BATCH_UNBOUNDED;   // ... unbounded searches (nearest, PC_RADIUS_FULL_NN): their walks are long, and
+                                            // beyond 8 k queries one thread per query wins (profiles/r2_coop_group_ab.txt: 24 k nearest 0.17 -> 0.11 ms)
     int64_t sort_min_radius = PC_SORT_MIN_RADIUS, sort_min_nearest = PC_SORT_MIN_NEAREST;   // PC_SORT_MIN_BATCH sets both
     int64_t tiny_batch = PC_TINY_BATCH;   // PC_HOST calls up to this many queries take the mapped-memory path (PC_TINY_BATCH_QUERIES, 0 = off)
     bool host_ramp = false;               // PC_HOST calls: smaller first chunks (PC_HOST_RAMP=1 switches it on)
@@ -298,8 +301,8 @@ extern "C" int pc_index_create(pc_index **out, int device, int64_t max_points, v
         if (const char *v = getenv("PC_TRACE_SLOW_MS")) ix->trace_slow_ms = atof(v);
         if (const char *v = getenv("PC_PACKET_SPLIT")) { double c_ = atof(v); ix->packet_split = c_ > 0.0 ? (float)c_ : 0.f; }
         if (const char *v = getenv("PC_HOST_CHUNK_QUERIES")) { long long b_ = atoll(v); if (b_ >= 1024) ix->host_chunk = b_; }
-        if (const char *v = getenv("PC_COOP_GROUP")) { int b_ = atoi(v); ix->coop_group = (b_ == 32 || b_ == 16 || b_ == 8) ? b_ : 0; }
-        if (const char *v = getenv("PC_COOP_MAX_BATCH")) { long long b_ = atoll(v); ix->coop_max = b_ < 0 ? 0 : b_; }
+        if (const char *v = getenv("PC_COOP_GROUP")) { int b_ = atoi(v); ix->coop_group = (b_ == 32 || b_ == 16 || b_ == 8 || b_ == 4) ? b_ : 0; }
+        if (const char *v = getenv("PC_COOP_MAX_BATCH")) { long long b_ = atoll(v); ix->coop_max = ix->coop_max_unbounded = b_ < 0 ? 0 : b_; }
         if (const char *v = getenv("PC_SORT_MIN_BATCH")) { long long b_ = atoll(v); ix->sort_min_radius = ix->sort_min_nearest = b_ < 1 ? 1 : b_; }
         if (const char *v = getenv("PC_TINY_BATCH_QUERIES")) { long long b_ = atoll(v); ix->tiny_batch = b_ < 0 ? 0 : (b_ > PC_TINY_BATCH ? PC_TINY_BATCH : b_); }
         if (cuda_stream) { ix->stream = (cudaStream_t)cuda_stream; ix->own_stream = false; }
@@ -823,6 +826,7 @@ static void pc_launch_coop(const pc_index *ix, const pc_qargs &A, const pc_tree 
     if (g == 0) g = m <= ix->coop_g32_max ? 32 : (m <= ix->coop_g16_max ? 16 : 8);
     if (g == 32) pc_launch_coop_g<32>(A, T, d_q, m, qstride, d_idx, d_f, st);
     else if (g == 16) pc_launch_coop_g<16>(A, T, d_q, m, qstride, d_idx, d_f, st);
+    else if (g == 4) pc_launch_coop_g<4>(A, T, d_q, m, qstride, d_idx, d_f, st);
     else pc_launch_coop_g<8>(A, T, d_q, m, qstride, d_idx, d_f, st);
 }
 
@@ -899,7 +903,7 @@ static int pc_run_batch(pc_index *ix, pc_lane &L, const pc_qargs &A, const float
             pc_query_packet_kernel<PC_KIND_NEAREST, 1><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, RN, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
         else
             pc_query_packet_kernel<PC_KIND_RADIUS, 1><<<grid, PC_QUERY_THREADS, 0, L.stream>>>(T, RN, d_q, m, qstride, perm, ordered, m_eff, d_idx, d_f);
-    } else if (ix->query_kernel >= 3 && !is_ordered && m <= ix->coop_max) {
+    } else if (ix->query_kernel >= 3 && !is_ordered && m <= ((A.kind == PC_Q_NEAREST || !A.R.bounded) ? ix->coop_max_unbounded : ix->coop_max)) {
         // small unordered batch: one warp per query (a thread-per-query search is a chain of dependent loads)
         pc_launch_coop(ix, A, T, d_q, m, qstride, d_idx, d_f, L.stream);
     } else {
